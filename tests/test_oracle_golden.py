@@ -1,0 +1,93 @@
+"""Pin the oracle restatement against the golden vectors generated from the real reference
+(tests/golden/make_golden.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddim_oracle, unet_oracle, weights
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    return np.load(os.path.join(G, name))
+
+
+def _keys(name):
+    with open(os.path.join(G, name)) as f:
+        return json.load(f)
+
+
+def test_schedule_tables_bit_exact():
+    g = _load("schedule.npz")
+    betas = ddim_oracle.make_beta_schedule("linear", 1000, 0.00085, 0.012)
+    assert np.array_equal(betas, g["betas"])
+    sched = ddim_oracle.register_schedule("linear", 1000, 0.00085, 0.012)
+    assert np.array_equal(sched["alphas_cumprod_f64"], g["alphas_cumprod"])
+    # KATs recorded in SURVEY.md 8c
+    assert sched["alphas_cumprod_f64"][0] == pytest.approx(0.99915, abs=1e-12)
+    assert sched["alphas_cumprod_f64"][999] == pytest.approx(0.004660098513077238, rel=1e-12)
+    for S in (20, 50, 100):
+        ts = ddim_oracle.make_ddim_timesteps("uniform", S, 1000)
+        assert np.array_equal(ts, g[f"ts_{S}"])
+        for eta in (0.0, 0.5):
+            tag = f"{S}_{int(eta * 10)}"
+            sig, a, ap = ddim_oracle.make_ddim_sampling_parameters(sched["alphas_cumprod"], ts, eta)
+            assert np.array_equal(np.asarray(a, dtype=np.float32), g[f"alphas_{tag}"])
+            assert np.array_equal(np.asarray(ap, dtype=np.float64), g[f"alphas_prev_{tag}"])
+            assert np.array_equal(np.asarray(sig, dtype=np.float64), g[f"sigmas_{tag}"])
+    assert list(ddim_oracle.make_ddim_timesteps("uniform", 50, 1000)[:3]) == [1, 21, 41]
+    assert np.array_equal(ddim_oracle.make_ddim_timesteps("quad", 20, 1000), g["ts_quad_20"])
+
+
+def test_timestep_embedding_golden():
+    g = _load("timestep_embedding.npz")
+    t = torch.from_numpy(g["t"])
+    assert np.array_equal(unet_oracle.timestep_embedding(t, 320).numpy(), g["e320"])
+    assert np.array_equal(unet_oracle.timestep_embedding(t, 64).numpy(), g["e64"])
+
+
+@pytest.mark.parametrize("name", ["tiny_a", "tiny_b"])
+def test_unet_forward_golden(name):
+    meta = _keys(f"{name}_keys.json")
+    g = _load(f"unet_{name}.npz")
+    sd = weights.make_state_dict({k: tuple(v) for k, v in meta["keys"].items()}, int(g["seed"]))
+    assert weights.checksum(sd) == pytest.approx(float(g["wsum"]), rel=1e-12)
+    cfg = meta["config"]
+    y = torch.from_numpy(g["y"]) if "y" in g.files else None
+    out = unet_oracle.unet_forward(sd, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]),
+                                   torch.from_numpy(g["ctx"]), y,
+                                   num_heads=cfg.get("num_heads", -1),
+                                   num_head_channels=cfg.get("num_head_channels", -1))
+    ref = torch.from_numpy(g["out"])
+    err = (out - ref).norm() / ref.norm()
+    assert ref.abs().max() > 1e-2            # not the zero-init trap
+    assert err < 2e-6, float(err)
+
+
+def test_ddim_loop_golden():
+    meta = _keys("tiny_a_keys.json")
+    cfg = meta["config"]
+    g = _load("ddim_tiny.npz")
+    sd = weights.make_state_dict({k: tuple(v) for k, v in meta["keys"].items()}, 11)
+    sched = ddim_oracle.register_schedule("linear", 1000, 0.00085, 0.012)
+    unet = lambda x, t, context=None, y=None: unet_oracle.unet_forward(
+        sd, x, t, context, y, num_heads=cfg["num_heads"])
+    model_fn = lambda x, t, c: ddim_oracle.apply_model(unet, "hybrid", x, t, c)
+    f = lambda k: torch.from_numpy(g[k])
+    cond = {"c_concat": [f("c_cat")], "c_crossattn": [f("c_txt")]}
+    uncond = {"c_concat": [f("c_cat")], "c_crossattn": [f("u_txt")]}
+    for S, scale in ((10, 7.5), (20, 1.0)):
+        out, inter = ddim_oracle.ddim_sample(model_fn, sched, S, f("x_T"), cond, uncond, scale, eta=0.0,
+                                             log_every_t=3)
+        ref = f(f"final_S{S}")
+        err = (out - ref).norm() / ref.norm()
+        assert err < 1e-5, (S, float(err))
+        assert len(inter["x_inter"]) == int(g[f"n_inter_S{S}"])
+        e2 = (inter["pred_x0"][-1] - f(f"pred_x0_last_S{S}")).norm() / f(f"pred_x0_last_S{S}").norm()
+        assert e2 < 1e-5
+        e3 = (inter["x_inter"][1] - f(f"x_inter_1_S{S}")).norm() / f(f"x_inter_1_S{S}").norm()
+        assert e3 < 1e-5
