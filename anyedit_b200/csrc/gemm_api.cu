@@ -1,0 +1,43 @@
+// anysd_gemm_f16: argument validation and kernel selection for every dense contraction on the path.
+#include "common.cuh"
+
+namespace anysd {
+int launch_gemm_mma(const anysd_gemm_params* q, cudaStream_t st);
+}
+
+using namespace anysd;
+
+extern "C" int anysd_gemm_f16(const anysd_gemm_params* p, anysd_stream_t stream) {
+    ANYSD_REQUIRE(p != nullptr, ANYSD_EINVAL, "gemm: null params");
+    ANYSD_REQUIRE(p->A && p->W && p->out, ANYSD_EINVAL, "gemm: null A/W/out");
+    ANYSD_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0, ANYSD_EINVAL, "gemm: bad M=%d N=%d K=%d", p->M, p->N, p->K);
+    ANYSD_REQUIRE(p->K % 8 == 0 && p->ldw % 8 == 0 && p->ldw >= p->K, ANYSD_EINVAL,
+                  "gemm: K=%d and ldw=%d must be multiples of 8 with ldw >= K", p->K, p->ldw);
+    ANYSD_REQUIRE(((uintptr_t)p->A % 16) == 0 && ((uintptr_t)p->W % 16) == 0, ANYSD_EINVAL,
+                  "gemm: A and W must be 16-byte aligned");
+    ANYSD_REQUIRE(p->act >= 0 && p->act <= 2, ANYSD_EINVAL, "gemm: bad act %d", p->act);
+    ANYSD_REQUIRE(p->out_dtype == ANYSD_F16 || p->out_dtype == ANYSD_F32, ANYSD_EINVAL, "gemm: bad out dtype");
+    const int n_out = (p->act == 2) ? p->N / 2 : p->N;
+    ANYSD_REQUIRE(p->act != 2 || p->N % 2 == 0, ANYSD_EINVAL, "gemm: GEGLU needs an even N");
+    ANYSD_REQUIRE(p->ldo >= n_out, ANYSD_EINVAL, "gemm: ldo=%d < %d output columns", p->ldo, n_out);
+    ANYSD_REQUIRE(!p->residual || p->ldr >= n_out, ANYSD_EINVAL, "gemm: ldr too small");
+    ANYSD_REQUIRE(!p->rowadd || (p->rows_per_batch > 0 && p->ld_rowadd >= p->N), ANYSD_EINVAL,
+                  "gemm: rowadd needs rows_per_batch > 0 and ld_rowadd >= N");
+    if (p->conv) {
+        ANYSD_REQUIRE(p->conv == 1, ANYSD_EINVAL, "gemm: conv must be 0 or 1 (3x3, pad 1)");
+        ANYSD_REQUIRE(p->Nimg > 0 && p->H > 0 && p->Wd > 0 && p->Cin > 0 && p->Cin % 8 == 0, ANYSD_EINVAL,
+                      "conv3x3: bad image dims N=%d H=%d W=%d Cin=%d (Cin must be a multiple of 8)", p->Nimg, p->H,
+                      p->Wd, p->Cin);
+        ANYSD_REQUIRE(p->stride == 1 || p->stride == 2, ANYSD_EINVAL, "conv3x3: stride must be 1 or 2");
+        ANYSD_REQUIRE(p->upsample == 0 || p->upsample == 1, ANYSD_EINVAL, "conv3x3: upsample must be 0 or 1");
+        ANYSD_REQUIRE(p->K == 9 * p->Cin, ANYSD_EINVAL, "conv3x3: K=%d != 9*Cin=%d", p->K, 9 * p->Cin);
+        const int Hl = p->H << p->upsample, Wl = p->Wd << p->upsample;
+        const int Ho = (Hl - 1) / p->stride + 1, Wo = (Wl - 1) / p->stride + 1;
+        ANYSD_REQUIRE((long long)p->Nimg * Ho * Wo == p->M, ANYSD_EINVAL, "conv3x3: M=%d != N*Ho*Wo=%lld", p->M,
+                      (long long)p->Nimg * Ho * Wo);
+    } else {
+        ANYSD_REQUIRE(p->lda % 8 == 0 && p->lda >= p->K, ANYSD_EINVAL, "gemm: lda=%d must be a multiple of 8 and >= K",
+                      p->lda);
+    }
+    return launch_gemm_mma(p, (cudaStream_t)stream);
+}

@@ -1,0 +1,274 @@
+// GroupNorm(+SiLU) on NHWC fp16 and LayerNorm on token rows.  HBM-bound kernels:
+// 16-byte vector loads/stores, fp32 statistics, warp-shuffle / smem reductions.
+//
+// GroupNorm is two launches:
+//   gn_stats_kernel : grid (S, N); each thread owns ONE 8-channel vector column and walks rows,
+//                     so per-channel partial sums live in registers; one smem reduction per block
+//                     writes per-(block, group) {sum, sumsq} partials.
+//   gn_apply_kernel : prologue folds the S partials (in double) into per-channel a = rstd*gamma,
+//                     b = beta - mean*a held in registers, then streams y = silu(a*x + b).
+// The input may be the channel concat of two tensors (x2 != nullptr): columns < C1/8 come from x1.
+#include "common.cuh"
+
+namespace anysd {
+
+constexpr int GN_MAX_SPLITS = 64;
+
+struct GnGeom {
+    int CV;    // 8-channel vectors per row (C/8)
+    int CV1;   // vectors that come from x1
+    int R;     // rows walked in parallel by one block
+    int T;     // threads per block = CV * R
+};
+
+static GnGeom gn_geom(int C1, int C2) {
+    GnGeom g;
+    g.CV = (C1 + C2) / 8;
+    g.CV1 = C1 / 8;
+    g.R = 512 / g.CV;
+    if (g.R < 1) g.R = 1;
+    g.T = g.CV * g.R;
+    return g;
+}
+
+__global__ void gn_stats_kernel(const uint4* __restrict__ x1, const uint4* __restrict__ x2, int CV, int CV1, int R,
+                                int HW, int rows_per_block, int G, int cpg, float* __restrict__ partials) {
+    extern __shared__ float sm[];  // [R][CV*8] sums, then [R][CV*8] squares
+    const int n = blockIdx.y, s = blockIdx.x;
+    const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
+    const int C = CV * 8;
+    const int row0 = s * rows_per_block;
+    int row1 = row0 + rows_per_block;
+    if (row1 > HW) row1 = HW;
+    const bool first = cv < CV1;
+    const int CV2 = CV - CV1;
+    const uint4* base = first ? (x1 + (size_t)n * HW * CV1 + cv) : (x2 + (size_t)n * HW * CV2 + (cv - CV1));
+    const int stride = first ? CV1 : CV2;
+
+    float sum[8], sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+    int row = row0 + r;
+    // 4 independent 16-byte loads in flight per thread
+    for (; row + 3 * R < row1; row += 4 * R) {
+        uint4 v0 = __ldg(base + (size_t)row * stride);
+        uint4 v1 = __ldg(base + (size_t)(row + R) * stride);
+        uint4 v2 = __ldg(base + (size_t)(row + 2 * R) * stride);
+        uint4 v3 = __ldg(base + (size_t)(row + 3 * R) * stride);
+        float f[8];
+#define ANYSD_ACC(v)                        \
+        unpack8(v, f);                          \
+        _Pragma("unroll") for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] += f[j] * f[j]; }
+        ANYSD_ACC(v0) ANYSD_ACC(v1) ANYSD_ACC(v2) ANYSD_ACC(v3)
+    }
+    for (; row < row1; row += R) {
+        uint4 v0 = __ldg(base + (size_t)row * stride);
+        float f[8];
+        ANYSD_ACC(v0)
+    }
+#undef ANYSD_ACC
+    float* ssum = sm;
+    float* ssq = sm + (size_t)R * C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        ssum[(size_t)r * C + j * CV + cv] = sum[j];   // [r][j][cv]: conflict-free
+        ssq[(size_t)r * C + j * CV + cv] = sq[j];
+    }
+    __syncthreads();
+    // thread g < G folds its group's channels over all R row-lanes
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const int idx = (c & 7) * CV + (c >> 3);
+            for (int rr = 0; rr < R; ++rr) {
+                a += ssum[(size_t)rr * C + idx];
+                b += ssq[(size_t)rr * C + idx];
+            }
+        }
+        float* p = partials + (((size_t)n * gridDim.x + s) * G + g) * 2;
+        p[0] = a;
+        p[1] = b;
+    }
+}
+
+__global__ void gn_apply_kernel(const uint4* __restrict__ x1, const uint4* __restrict__ x2, int CV, int CV1, int R,
+                                int HW, int rows_per_block, int G, int cpg, int S, const float* __restrict__ partials,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int fuse_silu,
+                                uint4* __restrict__ y) {
+    __shared__ float s_mean[64], s_rstd[64];
+    const int n = blockIdx.y, s = blockIdx.x;
+    if (threadIdx.x < G) {
+        double a = 0.0, b = 0.0;
+        const float* p = partials + ((size_t)n * S * G + threadIdx.x) * 2;
+        for (int i = 0; i < S; ++i) {
+            a += (double)p[(size_t)i * G * 2];
+            b += (double)p[(size_t)i * G * 2 + 1];
+        }
+        const double cnt = (double)HW * cpg;
+        const double mean = a / cnt;
+        double var = b / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
+    float ca[8], cb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = cv * 8 + j;
+        const int g = c / cpg;
+        const float a = s_rstd[g] * gamma[c];
+        ca[j] = a;
+        cb[j] = beta[c] - s_mean[g] * a;
+    }
+    const int row0 = s * rows_per_block;
+    int row1 = row0 + rows_per_block;
+    if (row1 > HW) row1 = HW;
+    const bool first = cv < CV1;
+    const int CV2 = CV - CV1;
+    const uint4* base = first ? (x1 + (size_t)n * HW * CV1 + cv) : (x2 + (size_t)n * HW * CV2 + (cv - CV1));
+    const int stride = first ? CV1 : CV2;
+    uint4* out = y + (size_t)n * HW * CV + cv;
+    int row = row0 + r;
+    for (; row + R < row1; row += 2 * R) {
+        uint4 v0 = __ldg(base + (size_t)row * stride);
+        uint4 v1 = __ldg(base + (size_t)(row + R) * stride);
+        float f0[8], f1[8];
+        unpack8(v0, f0);
+        unpack8(v1, f1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t0 = f0[j] * ca[j] + cb[j], t1 = f1[j] * ca[j] + cb[j];
+            f0[j] = fuse_silu ? silu_f(t0) : t0;
+            f1[j] = fuse_silu ? silu_f(t1) : t1;
+        }
+        out[(size_t)row * CV] = pack8(f0);
+        out[(size_t)(row + R) * CV] = pack8(f1);
+    }
+    for (; row < row1; row += R) {
+        uint4 v0 = __ldg(base + (size_t)row * stride);
+        float f0[8];
+        unpack8(v0, f0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t0 = f0[j] * ca[j] + cb[j];
+            f0[j] = fuse_silu ? silu_f(t0) : t0;
+        }
+        out[(size_t)row * CV] = pack8(f0);
+    }
+}
+
+// ---- LayerNorm: one warp per token row, row held in registers (C <= 2048) ----------------------
+constexpr int LN_MAX_VEC = 8;
+
+__global__ void layernorm_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, uint4* __restrict__ y, long long M, int CV, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const uint4* xr = x + row * CV;
+    float f[LN_MAX_VEC][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+        const int v = lane + i * 32;
+        if (v < CV) {
+            uint4 u = __ldg(xr + v);
+            unpack8(u, f[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += f[i][j];
+        }
+    }
+    const float inv_c = 1.0f / (float)(CV * 8);
+    const float mean = warp_sum(s) * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+        const int v = lane + i * 32;
+        if (v < CV) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float d = f[i][j] - mean;
+                q += d * d;
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
+    uint4* yr = y + row * CV;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+        const int v = lane + i * 32;
+        if (v < CV) {
+            const float4* g4 = reinterpret_cast<const float4*>(gamma + v * 8);
+            const float4* b4 = reinterpret_cast<const float4*>(beta + v * 8);
+            float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+            float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * gg[j] + bb[j];
+            yr[v] = pack8(o);
+        }
+    }
+}
+
+}  // namespace anysd
+
+using namespace anysd;
+
+extern "C" {
+
+size_t anysd_groupnorm_workspace_bytes(int N, int G, int C) {
+    (void)C;
+    if (N <= 0 || G <= 0) return 0;
+    return (size_t)N * GN_MAX_SPLITS * G * 2 * sizeof(float);
+}
+
+int anysd_groupnorm_nhwc_f16(const void* x1, int C1, const void* x2, int C2, const float* gamma, const float* beta,
+                             void* y, int N, int HW, int G, float eps, int fuse_silu, void* workspace,
+                             size_t workspace_bytes, anysd_stream_t stream) {
+    ANYSD_REQUIRE(x1 && gamma && beta && y && workspace, ANYSD_EINVAL, "groupnorm: null pointer");
+    if (x2 == nullptr) C2 = 0;
+    const int C = C1 + C2;
+    ANYSD_REQUIRE(N > 0 && HW > 0 && G > 0 && G <= 64 && C1 > 0 && C2 >= 0, ANYSD_EINVAL, "groupnorm: bad shape");
+    ANYSD_REQUIRE(C % G == 0 && C1 % 8 == 0 && C2 % 8 == 0, ANYSD_EINVAL,
+                  "groupnorm: C=%d must divide into G=%d groups and both sources must be multiples of 8 channels", C, G);
+    ANYSD_REQUIRE(C / 8 <= 1024, ANYSD_EINVAL, "groupnorm: C=%d too large", C);
+    ANYSD_REQUIRE(workspace_bytes >= anysd_groupnorm_workspace_bytes(N, G, C), ANYSD_EINVAL,
+                  "groupnorm: workspace too small (%zu bytes)", workspace_bytes);
+    const GnGeom g = gn_geom(C1, C2);
+    const int cpg = C / G;
+    // The spatial split depends on the image geometry only (never on N): the summation order, and hence
+    // every output bit, is independent of how many samples share the batch.  >= 8 row-steps per block.
+    int S = HW / (8 * g.R);
+    if (S > 32) S = 32;
+    if (S < 1) S = 1;
+    const int rpb = cdiv(HW, S);
+    S = cdiv(HW, rpb);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)2 * g.R * C * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ANYSD_REQUIRE(e == cudaSuccess, ANYSD_ECUDA, "groupnorm: smem opt-in failed: %s", cudaGetErrorString(e));
+    }
+    gn_stats_kernel<<<dim3(S, N), g.T, smem, st>>>((const uint4*)x1, (const uint4*)x2, g.CV, g.CV1, g.R, HW, rpb, G, cpg,
+                                                   (float*)workspace);
+    int rc = check_launch("groupnorm stats");
+    if (rc) return rc;
+    gn_apply_kernel<<<dim3(S, N), g.T, 0, st>>>((const uint4*)x1, (const uint4*)x2, g.CV, g.CV1, g.R, HW, rpb, G, cpg, S,
+                                                (const float*)workspace, gamma, beta, eps, fuse_silu, (uint4*)y);
+    return check_launch("groupnorm apply");
+}
+
+int anysd_layernorm_f16(const void* x, const float* gamma, const float* beta, void* y, long long M, int C, float eps,
+                        anysd_stream_t stream) {
+    ANYSD_REQUIRE(x && gamma && beta && y && M > 0, ANYSD_EINVAL, "layernorm: bad args");
+    ANYSD_REQUIRE(C > 0 && C % 8 == 0 && C / 8 <= 32 * LN_MAX_VEC, ANYSD_EINVAL,
+                  "layernorm: C=%d must be a multiple of 8 and <= %d", C, 256 * LN_MAX_VEC);
+    const int warps = 8;
+    layernorm_kernel<<<cdiv(M, warps), warps * 32, 0, (cudaStream_t)stream>>>((const uint4*)x, gamma, beta, (uint4*)y, M,
+                                                                              C / 8, eps);
+    return check_launch("layernorm");
+}
+}

@@ -1,0 +1,61 @@
+"""Multi-GPU plumbing for the denoising path: one process per GPU, requests sharded by rank.
+
+The path shards naturally: each edit request's S-step trajectory depends only on its
+own latent, conditioning and the frozen weights, so there is NO collective inside the denoising
+loop.  The only communication is a one-time broadcast of the frozen weights from rank 0
+(the reference's DDP construction does the same through accelerate, train.py:536-538).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's env (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return rank, local, world
+
+
+def shard_range(n_requests, rank, world):
+    """Contiguous slice [lo, hi) of the request list owned by ``rank`` (sizes differ by at most 1;
+    a request's CFG pair always stays on one GPU)."""
+    base, rem = divmod(n_requests, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+@torch.no_grad()
+def broadcast_module_(module, src=0):
+    """One-time broadcast of every parameter and buffer from ``src`` (frozen UNet / adapter / task table)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src)
+    if hasattr(module, "invalidate"):
+        module.invalidate()
+
+
+def barrier():
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(value: float, device) -> float:
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

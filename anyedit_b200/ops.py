@@ -1,0 +1,214 @@
+"""Torch-tensor wrappers over the C ABI (include/anysd_b200.h).
+
+PyTorch is plumbing here: device memory, the current CUDA stream, nothing else.  Every function
+launches hand-written sm_100a kernels from ``libanysd_b200.so`` on ``torch.cuda.current_stream()``
+and raises on failure.  Tensors are NHWC / token-major fp16 unless stated.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import F16, F32, I64, AttnParams, GemmParams
+
+_DT = {torch.float32: F32, torch.float16: F16, torch.int64: I64}
+
+# Incremented by every kernel launch issued through this module (bench.py reports it).
+launch_count = 0
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.AnysdError("anysd_b200 ops need CUDA tensors; there is no CPU fallback")
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def device_info():
+    lib = _lib.load()
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(lib.anysd_device_info(C.byref(a), C.byref(b), C.byref(c)), "device_info")
+    return a.value, b.value, c.value
+
+
+def nchw_to_nhwc(src, dst, c_off=0):
+    """src [N,C,H,W] f32|f16 contiguous -> dst[..., c_off:c_off+C] of NHWC fp16 [N,H,W,dstC]."""
+    _cuda(src, dst)
+    N, Cc, H, W = src.shape
+    assert src.is_contiguous() and dst.is_contiguous() and dst.dtype == torch.float16
+    _lib.check(_lib.load().anysd_nchw_to_nhwc_f16(_ptr(src), _DT[src.dtype], _ptr(dst), N, Cc, H, W,
+                                                  dst.shape[-1], c_off, _stream()), "nchw_to_nhwc")
+    _count()
+
+
+def nhwc_to_nchw(src, dst):
+    """src NHWC f16|f32 [N,H,W,C] -> dst NCHW f32|f16 [N,C,H,W]."""
+    _cuda(src, dst)
+    N, Cc, H, W = dst.shape
+    assert src.is_contiguous() and dst.is_contiguous()
+    _lib.check(_lib.load().anysd_nhwc_to_nchw(_ptr(src), _DT[src.dtype], _ptr(dst), _DT[dst.dtype], N, Cc, H, W,
+                                              _stream()), "nhwc_to_nchw")
+    _count()
+
+
+def concat_channels(a, b, dst):
+    _cuda(a, b, dst)
+    rows = a.numel() // a.shape[-1]
+    _lib.check(_lib.load().anysd_concat_channels_f16(_ptr(a), a.shape[-1], _ptr(b), b.shape[-1], _ptr(dst), rows,
+                                                     _stream()), "concat_channels")
+    _count()
+
+
+def cast_f16(src, dst):
+    _cuda(src, dst)
+    assert src.dtype == torch.float32 and dst.dtype == torch.float16 and src.is_contiguous()
+    _lib.check(_lib.load().anysd_cast_f32_to_f16(_ptr(src), _ptr(dst), src.numel(), _stream()), "cast")
+    _count()
+
+
+def timestep_embedding(t, out, max_period=10000.0):
+    """t [N] int64|f32 -> out fp16 [N, dim] (util.py:154-174)."""
+    _cuda(t, out)
+    if t.dtype not in (torch.int64, torch.float32):
+        t = t.float() if t.is_floating_point() else t.long()
+    _lib.check(_lib.load().anysd_timestep_embedding_f16(_ptr(t), _DT[t.dtype], _ptr(out), out.shape[0], out.shape[1],
+                                                        float(max_period), _stream()), "timestep_embedding")
+    _count()
+
+
+def emb_finalize(emb_lin, silu_out, table=None, idx=None, emb_out=None):
+    _cuda(emb_lin, silu_out)
+    N, D = emb_lin.shape
+    rows = table.shape[0] if table is not None else 0
+    _lib.check(_lib.load().anysd_emb_finalize(_ptr(emb_lin), _ptr(table), _ptr(idx), rows, _ptr(emb_out),
+                                              _ptr(silu_out), N, D, _stream()), "emb_finalize")
+    _count()
+
+
+def router_gate(table, idx, W, bias, gate):
+    """gate[b, l, :] = softmax(W[l] @ table[idx[b]] + bias[l]); W fp16 [L, E, D], gate fp32 [B, L, E]."""
+    _cuda(table, idx, W, bias, gate)
+    L, E, D = W.shape
+    _lib.check(_lib.load().anysd_router_gate_f32(_ptr(table), _ptr(idx), table.shape[0], _ptr(W), _ptr(bias),
+                                                 _ptr(gate), gate.shape[0], L, E, D, _stream()), "router_gate")
+    _count()
+
+
+def groupnorm_workspace(N, G=32, C=0, device="cuda"):
+    nbytes = _lib.load().anysd_groupnorm_workspace_bytes(N, G, C)
+    return torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+
+
+def groupnorm(x1, gamma, beta, y, N, HW, eps, silu, ws, x2=None, G=32):
+    _cuda(x1, y, ws)
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    _lib.check(_lib.load().anysd_groupnorm_nhwc_f16(_ptr(x1), C1, _ptr(x2), C2, _ptr(gamma), _ptr(beta), _ptr(y), N,
+                                                    HW, G, float(eps), int(bool(silu)), _ptr(ws), ws.numel() * 4,
+                                                    _stream()), "groupnorm")
+    _count(2)
+
+
+def layernorm(x, gamma, beta, y, eps=1e-5):
+    _cuda(x, y)
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    _lib.check(_lib.load().anysd_layernorm_f16(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), M, Cc, float(eps),
+                                               _stream()), "layernorm")
+    _count()
+
+
+def gemm(A, W, out, bias=None, rowadd=None, rows_per_batch=0, residual=None, act=0, M=None, K=None, lda=None,
+         N=None, ldw=None, ld_rowadd=None):
+    """out[M, N'] = epilogue(A[M, K] @ W[N, K]^T); see anysd_gemm_params."""
+    _cuda(A, W, out)
+    p = GemmParams()
+    p.A, p.W, p.out = A.data_ptr(), W.data_ptr(), out.data_ptr()
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.rowadd = rowadd.data_ptr() if rowadd is not None else None
+    p.residual = residual.data_ptr() if residual is not None else None
+    p.K = K if K is not None else A.shape[-1]
+    p.M = M if M is not None else A.numel() // A.shape[-1]
+    p.N = N if N is not None else W.shape[0]
+    p.lda = lda if lda is not None else A.stride(-2) if A.dim() >= 2 else p.K
+    p.ldw = ldw if ldw is not None else W.stride(0)
+    p.ldo = out.stride(-2) if out.dim() >= 2 else out.shape[-1]
+    p.ldr = residual.stride(-2) if residual is not None else 0
+    p.ld_rowadd = ld_rowadd if ld_rowadd is not None else (rowadd.stride(0) if rowadd is not None else 0)
+    p.rows_per_batch = rows_per_batch
+    p.act = act
+    p.out_dtype = _DT[out.dtype]
+    p.conv = 0
+    _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "gemm")
+    _count()
+
+
+def conv3x3(x, W, out, bias=None, rowadd=None, residual=None, stride=1, upsample=0, ld_rowadd=None):
+    """x NHWC fp16 [N,H,W,Cin]; W fp16 [Cout, 9*Cin] ((ky,kx,ci) K order); out [N*Ho*Wo, Cout]."""
+    _cuda(x, W, out)
+    Nimg, H, Wd, Cin = x.shape
+    Hl, Wl = H << upsample, Wd << upsample
+    Ho, Wo = (Hl - 1) // stride + 1, (Wl - 1) // stride + 1
+    p = GemmParams()
+    p.A, p.W, p.out = x.data_ptr(), W.data_ptr(), out.data_ptr()
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.rowadd = rowadd.data_ptr() if rowadd is not None else None
+    p.residual = residual.data_ptr() if residual is not None else None
+    p.M, p.N, p.K = Nimg * Ho * Wo, W.shape[0], 9 * Cin
+    p.lda, p.ldw = Cin, W.stride(0)
+    p.ldo = out.stride(-2)
+    p.ldr = residual.stride(-2) if residual is not None else 0
+    p.ld_rowadd = ld_rowadd if ld_rowadd is not None else (rowadd.stride(0) if rowadd is not None else 0)
+    p.rows_per_batch = Ho * Wo
+    p.act = 0
+    p.out_dtype = _DT[out.dtype]
+    p.conv = 1
+    p.Nimg, p.H, p.Wd, p.Cin = Nimg, H, Wd, Cin
+    p.stride, p.upsample = stride, upsample
+    _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "conv3x3")
+    _count()
+    return Ho, Wo
+
+
+def attention(q, k, v, out, B, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o, q_bs=None, k_bs=None, v_bs=None,
+              o_bs=None, scale=None, gate=None, gate_stride=1, accumulate=False):
+    """softmax(q k^T * scale) v per (batch, head); q/k/v may be column slices of fused projections."""
+    _cuda(q, k, v, out)
+    p = AttnParams()
+    p.q, p.k, p.v, p.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    p.q_batch_stride = q_bs if q_bs is not None else n_q * ld_q
+    p.k_batch_stride = k_bs if k_bs is not None else n_kv * ld_k
+    p.v_batch_stride = v_bs if v_bs is not None else n_kv * ld_v
+    p.o_batch_stride = o_bs if o_bs is not None else n_q * ld_o
+    p.ld_q, p.ld_k, p.ld_v, p.ld_o = ld_q, ld_k, ld_v, ld_o
+    p.B, p.heads, p.n_q, p.n_kv, p.d = B, heads, n_q, n_kv, d
+    p.scale = float(scale if scale is not None else d ** -0.5)
+    p.gate = gate.data_ptr() if gate is not None else None
+    p.gate_stride = gate_stride
+    p.accumulate = int(bool(accumulate))
+    _lib.check(_lib.load().anysd_attention_f16(C.byref(p), _stream()), "attention")
+    _count()
+
+
+def cfg_ddim_step(x, eps, coef, scale, cfg, x_prev, pred_x0=None, noise=None):
+    """ddim.py:211-212, 228-250 in one kernel; all fp32 NCHW; coef is a 5-float device tensor."""
+    _cuda(x, eps, coef, x_prev)
+    B = x.shape[0]
+    n_per = x.numel() // B
+    assert x.dtype == torch.float32 and eps.dtype == torch.float32 and x.is_contiguous() and eps.is_contiguous()
+    _lib.check(_lib.load().anysd_cfg_ddim_step_f32(_ptr(x), _ptr(eps), _ptr(noise), _ptr(coef), float(scale),
+                                                   int(bool(cfg)), _ptr(x_prev), _ptr(pred_x0), n_per, B, _stream()),
+               "cfg_ddim_step")
+    _count()

@@ -1,0 +1,146 @@
+/* anysd_b200 -- C ABI of the B200-native AnySD denoising hot path.
+ *
+ * The reference (DCDmllm/AnyEdit) has no FFI boundary on this path: its hot path is eager
+ * PyTorch modules.  This header is therefore the *new* boundary a maintainer
+ * binds to; every entry point names the reference code whose arithmetic it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, sizes, a cudaStream_t passed as void*; no torch types.
+ *   - no ownership transfer: every buffer (workspaces included) belongs to the caller.
+ *   - asynchronous on the given stream, no hidden synchronisation, CUDA-graph capturable.
+ *   - returns 0 on success, a negative ANYSD_E* code on failure; anysd_last_error() returns a
+ *     thread-local message.  There is no CPU fallback: without a CUDA device calls fail.
+ *   - activations are NHWC fp16 ("tokens" [N, H*W, C]); statistics/accumulators are fp32.
+ */
+#ifndef ANYSD_B200_H_
+#define ANYSD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANYSD_OK 0
+#define ANYSD_EINVAL (-1)   /* bad argument / unsupported shape (ValueError in the Python mirror) */
+#define ANYSD_ECUDA (-2)    /* CUDA runtime / launch failure (RuntimeError) */
+#define ANYSD_EUNSUPPORTED (-3)
+
+#define ANYSD_F32 0
+#define ANYSD_F16 1
+#define ANYSD_I64 2
+
+typedef void* anysd_stream_t; /* cudaStream_t */
+
+const char* anysd_last_error(void);
+int anysd_version(void);
+/* sm count and compute capability of the current device */
+int anysd_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- layout ------------------------------------------------------------------------------
+ * x.type(self.dtype) + torch.cat([x] + c_concat, dim=1)   ldm/models/diffusion/ddpm.py:1344-1346,
+ * ldm/modules/diffusionmodules/openaimodel.py:774: NCHW (f32|f16) -> channel slice
+ * [dst_c_off, dst_c_off+C) of an NHWC fp16 tensor with dst_C channels. */
+int anysd_nchw_to_nhwc_f16(const void* src, int src_dtype, void* dst, int N, int C, int H, int W,
+                           int dst_C, int dst_c_off, anysd_stream_t stream);
+/* h.type(x.dtype) on the way out (openaimodel.py:782): NHWC (f16|f32) -> NCHW (f32|f16). */
+int anysd_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, int N, int C, int H, int W,
+                       anysd_stream_t stream);
+/* th.cat([h, hs.pop()], dim=1) (openaimodel.py:780) on NHWC rows: dst[r] = a[r] ++ b[r]. */
+int anysd_concat_channels_f16(const void* a, int Ca, const void* b, int Cb, void* dst, long long rows,
+                              anysd_stream_t stream);
+int anysd_cast_f32_to_f16(const float* src, void* dst, long long n, anysd_stream_t stream);
+
+/* ---- time / task embedding ---------------------------------------------------------------
+ * timestep_embedding (ldm/modules/diffusionmodules/util.py:154-174): cos half first. */
+int anysd_timestep_embedding_f16(const void* t, int t_dtype, void* out_f16, int N, int dim, float max_period,
+                                 anysd_stream_t stream);
+/* emb = time_embed(t_emb) [+ label_emb(y) | task_embs[edit_code]] (openaimodel.py:768-772;
+ * train.py:694-695) and the SiLU that opens every ResBlock.emb_layers (openaimodel.py:217-223):
+ * emb_out[n] = emb_lin[n] + table[idx[n]] ; silu_out = fp16(silu(emb_out)). table/idx/emb_out may be NULL. */
+int anysd_emb_finalize(const float* emb_lin, const float* table, const long long* idx, int table_rows,
+                       float* emb_out, void* silu_out_f16, int N, int D, anysd_stream_t stream);
+
+/* Task-aware router gate (AnySD.model.MoE, source absent -- train.py:420-424, 694-695; restated in
+ * oracle/anysd_oracle.py): gate[b, l, :] = softmax_e(W[l, e, :] . table[idx[b], :] + bias[l, e]) for all
+ * L cross-attention layers at once.  table fp32 [T, D], W fp16 [L, E, D], bias fp32 [L, E], gate fp32 [B, L, E]. */
+int anysd_router_gate_f32(const float* table, const long long* idx, int table_rows, const void* W,
+                          const float* bias, float* gate, int B, int L, int E, int D, anysd_stream_t stream);
+
+/* ---- normalisation -----------------------------------------------------------------------
+ * GroupNorm32 + SiLU (util.py:202-219; openaimodel.py:200-203, 224-227, 726-728) and the
+ * SpatialTransformer GroupNorm (attention.py:88-89, 326; eps 1e-6, no SiLU).  Statistics in fp32.
+ * The input may be the channel concat of two NHWC tensors (x2 != NULL): the skip concat
+ * (openaimodel.py:780) is then never materialised for the norm. y: NHWC fp16 [N, HW, C1+C2]. */
+size_t anysd_groupnorm_workspace_bytes(int N, int G, int C);
+int anysd_groupnorm_nhwc_f16(const void* x1, int C1, const void* x2, int C2, const float* gamma,
+                             const float* beta, void* y, int N, int HW, int G, float eps, int fuse_silu,
+                             void* workspace, size_t workspace_bytes, anysd_stream_t stream);
+/* nn.LayerNorm(dim) (attention.py:262-264), one row per token. */
+int anysd_layernorm_f16(const void* x, const float* gamma, const float* beta, void* y, long long M, int C,
+                        float eps, anysd_stream_t stream);
+
+/* ---- tensor-core contraction ---------------------------------------------------------------
+ * One entry point for every dense contraction on the path:
+ *   nn.Linear / 1x1 conv   attention.py:154-161 (to_q/k/v/out), :52-56 (GEGLU proj), :70 (FF out),
+ *                          :298-318 (proj_in/out); openaimodel.py:240 (skip_connection),
+ *                          :526-530 (time_embed), :217-223 (emb_layers)
+ *   3x3 conv, pad 1        openaimodel.py:203, 228-230 (ResBlock), :552 (input), :729 (out),
+ *                          :148-150 (Downsample, stride 2), :104-117 (Upsample: nearest x2 folded in)
+ * out[m, n] = act(sum_k A[m,k] W[n,k] + bias[n] + rowadd[m / rows_per_batch, n]) + residual[m, n]
+ * fp16 operands, fp32 accumulate.  act: 0 none, 1 SiLU, 2 GEGLU (W rows interleaved (a_j, gate_j);
+ * out has N/2 columns: (acc_a + b_a) * gelu_erf(acc_g + b_g)). */
+typedef struct {
+    const void* A;          /* dense: fp16 [M, lda]; conv: NHWC fp16 image [Nimg, H, W, Cin] */
+    const void* W;          /* fp16 [N, ldw], row n = output channel, K contiguous ((ky,kx,ci) for conv) */
+    const float* bias;      /* [N] or NULL */
+    const float* rowadd;    /* fp32 [*, ld_rowadd] or NULL */
+    const void* residual;   /* fp16 [M, ldr] or NULL */
+    void* out;              /* [M, ldo] fp16 or fp32 */
+    int M, N, K;
+    int lda, ldw, ldo, ldr, ld_rowadd;
+    int rows_per_batch;
+    int act;
+    int out_dtype;          /* ANYSD_F16 | ANYSD_F32 */
+    int conv;               /* 0 dense, 1 conv3x3 pad 1 */
+    int Nimg, H, Wd, Cin;   /* conv: input image dims (before the folded upsample) */
+    int stride;             /* conv: 1 | 2 */
+    int upsample;           /* conv: 1 = nearest x2 before the conv */
+} anysd_gemm_params;
+int anysd_gemm_f16(const anysd_gemm_params* p, anysd_stream_t stream);
+
+/* ---- attention ---------------------------------------------------------------------------
+ * CrossAttention.forward (attention.py:163-194) / xformers memory_efficient_attention (:233):
+ * out = softmax(q k^T * scale) v per (batch, head); fp16 q/k/v, fp32 scores/softmax/accumulate.
+ * q: [B, n_q, ld_q] with head h at columns [h*d, (h+1)*d); same for k, v ([B, n_kv, ld_k|ld_v]) and out.
+ * gate != NULL: out = out_prev * (accumulate ? 1 : 0) + gate[b] * attn  -- the task-router expert sum
+ * (oracle/anysd_oracle.py). */
+typedef struct {
+    const void* q; const void* k; const void* v; void* out;
+    long long q_batch_stride, k_batch_stride, v_batch_stride, o_batch_stride; /* elements */
+    int ld_q, ld_k, ld_v, ld_o;                                               /* elements */
+    int B, heads, n_q, n_kv, d;
+    float scale;
+    const float* gate;      /* [B] stride gate_stride, or NULL */
+    int gate_stride;
+    int accumulate;
+} anysd_attn_params;
+int anysd_attention_f16(const anysd_attn_params* p, anysd_stream_t stream);
+
+/* ---- sampler step ------------------------------------------------------------------------
+ * DDIMSampler.p_sample_ddim (ldm/models/diffusion/ddim.py:211-212, 228-250), eps-parameterisation:
+ *   e = e_u + s (e_c - e_u);  pred_x0 = (x - sqrt(1-a_t) e) / sqrt(a_t);
+ *   x_prev = sqrt(a_prev) pred_x0 + sqrt(1 - a_prev - sigma^2) e + sigma * noise
+ * all fp32, NCHW.  eps holds [uncond ; cond] (2B rows) when cfg != 0, else B rows.
+ * coef[5] = {sqrt(1-a_t), 1/sqrt(a_t) as sqrt(a_t) divisor, sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma}
+ * lives on the device so that one CUDA graph serves all steps.  noise/pred_x0 may be NULL. */
+int anysd_cfg_ddim_step_f32(const float* x, const float* eps, const float* noise, const float* coef,
+                            float guidance_scale, int cfg, float* x_prev, float* pred_x0, long long n_per_batch,
+                            int B, anysd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANYSD_B200_H_ */

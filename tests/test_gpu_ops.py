@@ -1,0 +1,305 @@
+"""Kernel-level parity: each CUDA op, called through the C ABI, against a fp32 CPU reference of the
+same op (oracle / plain torch fp32) on seeded inputs, plus the golden KATs generated from the
+reference's own module classes.  Tolerances: fp16 operands with fp32 accumulation -> relative L2
+error a small multiple of 2^-11; integer / fp32 elementwise work is checked bit-exactly."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from anyedit_b200 import ops as o
+    sms, major, minor = o.device_info()
+    assert major >= 10, f"sm_100a kernels need a Blackwell GPU, got cc {major}.{minor}"
+    return o
+
+
+def randn(seed, *shape, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def to_nhwc16(x):
+    return x.permute(0, 2, 3, 1).contiguous().half().cuda()
+
+
+def from_nhwc(y, N, H, W):
+    return y.float().cpu().reshape(N, H, W, -1).permute(0, 3, 1, 2)
+
+
+def test_layout_roundtrip(ops):
+    x = randn(1, 3, 5, 7, 9)
+    dst = torch.zeros(3, 7, 9, 8, dtype=torch.float16, device="cuda")
+    ops.nchw_to_nhwc(x.cuda(), dst, 2)
+    ref = torch.zeros(3, 7, 9, 8)
+    ref[..., 2:7] = x.permute(0, 2, 3, 1)
+    assert torch.equal(dst.cpu(), ref.half())
+    back = torch.empty(3, 8, 7, 9, dtype=torch.float32, device="cuda")
+    ops.nhwc_to_nchw(dst, back)
+    assert torch.equal(back.cpu(), ref.half().float().permute(0, 3, 1, 2))
+    a, b = randn(2, 10, 16).half().cuda(), randn(3, 10, 24).half().cuda()
+    c = torch.empty(10, 40, dtype=torch.float16, device="cuda")
+    ops.concat_channels(a, b, c)
+    assert torch.equal(c, torch.cat([a, b], 1))
+
+
+def test_timestep_embedding_golden(ops):
+    g = np.load(os.path.join(G, "timestep_embedding.npz"))
+    t = torch.from_numpy(g["t"]).cuda()
+    for dim, key in ((320, "e320"), (64, "e64")):
+        out = torch.empty(len(t), dim, dtype=torch.float16, device="cuda")
+        ops.timestep_embedding(t, out)
+        ref = torch.from_numpy(g[key])
+        # fp16 storage of an fp32 value: half an fp16 ulp, plus the sin/cos argument-reduction ulp
+        assert (out.float().cpu() - ref).abs().max() < 6e-4
+
+
+@pytest.mark.parametrize("shape,C2", [((2, 64, 6, 10), 0), ((3, 320, 16, 16), 0), ((2, 640, 8, 8), 320),
+                                      ((1, 2560, 8, 8), 0), ((2, 960, 32, 32), 640), ((2, 32, 5, 3), 0)])
+@pytest.mark.parametrize("silu,eps", [(True, 1e-5), (False, 1e-6)])
+def test_groupnorm(ops, shape, C2, silu, eps):
+    N, C, H, W = shape
+    x = randn(11, N, C, H, W, scale=2.0) + 0.7
+    gamma, beta = 1 + 0.2 * randn(12, C), 0.1 * randn(13, C)
+    x16 = x.half().float()
+    ref = F.group_norm(x16, 32, gamma, beta, eps)
+    ref = F.silu(ref) if silu else ref
+    xh = to_nhwc16(x)
+    y = torch.empty_like(xh)
+    ws = ops.groupnorm_workspace(N)
+    if C2:
+        x1, x2 = xh[..., :C - C2].contiguous(), xh[..., C - C2:].contiguous()
+        ops.groupnorm(x1, gamma.cuda(), beta.cuda(), y, N, H * W, eps, silu, ws, x2=x2)
+    else:
+        ops.groupnorm(xh, gamma.cuda(), beta.cuda(), y, N, H * W, eps, silu, ws)
+    e = rel(from_nhwc(y, N, H, W), ref)
+    assert e < 1e-3, e
+
+
+def test_groupnorm_silu_golden_kat(ops):
+    from oracle import weights
+    g = np.load(os.path.join(G, "op_kats.npz"))
+    x = torch.from_numpy(g["gn_x"])
+    sd = weights.make_state_dict({"in_layers.0.weight": (64,), "in_layers.0.bias": (64,)}, 21)
+    N, C, H, W = x.shape
+    xh = to_nhwc16(x)
+    y = torch.empty_like(xh)
+    ops.groupnorm(xh, sd["in_layers.0.weight"].cuda(), sd["in_layers.0.bias"].cuda(), y, N, H * W, 1e-5, True,
+                  ops.groupnorm_workspace(N))
+    e = rel(from_nhwc(y, N, H, W), torch.from_numpy(g["gn_silu_out"]))
+    assert e < 2e-3, e
+
+
+@pytest.mark.parametrize("M,C", [(77, 320), (1000, 640), (33, 1280), (5, 64), (64, 2048)])
+def test_layernorm(ops, M, C):
+    x = randn(21, M, C, scale=3.0) + 0.5
+    gamma, beta = 1 + 0.2 * randn(22, C), 0.1 * randn(23, C)
+    xh = x.half().cuda()
+    y = torch.empty_like(xh)
+    ops.layernorm(xh, gamma.cuda(), beta.cuda(), y)
+    ref = F.layer_norm(x.half().float(), (C,), gamma, beta)
+    assert rel(y, ref) < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 320, 320), (4096, 320, 2880 // 9), (77, 640, 768),
+                                   (16, 1280, 1280), (1, 8, 8), (300, 4, 320), (513, 130, 72)])
+def test_gemm_plain(ops, M, N, K):
+    A, W = randn(31, M, K), randn(32, N, K, scale=K ** -0.5)
+    bias = 0.1 * randn(33, N)
+    A16, W16 = A.half(), W.half()
+    ref = A16.float() @ W16.float().t() + bias
+    for odt in (torch.float16, torch.float32):
+        out = torch.empty(M, N, dtype=odt, device="cuda")
+        ops.gemm(A16.cuda(), W16.cuda(), out, bias=bias.cuda())
+        e = rel(out, ref)
+        assert e < (1e-3 if odt == torch.float16 else 2e-5), (odt, e)
+
+
+def test_gemm_epilogues(ops):
+    M, N, K, HW = 384, 256, 192, 96   # 4 "images" of 96 rows
+    A, W = randn(41, M, K).half(), randn(42, N, K, scale=K ** -0.5).half()
+    bias, res = 0.1 * randn(43, N), randn(44, M, N).half()
+    rowadd = randn(45, M // HW, N + 16)
+    base = A.float() @ W.float().t() + bias
+    # bias + rowadd + residual
+    out = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    ops.gemm(A.cuda(), W.cuda(), out, bias=bias.cuda(), rowadd=rowadd.cuda()[:, 8:], rows_per_batch=HW,
+             residual=res.cuda(), ld_rowadd=N + 16)
+    ref = base + rowadd[:, 8:8 + N].repeat_interleave(HW, 0) + res.float()
+    assert rel(out, ref) < 1e-3
+    # SiLU
+    ops.gemm(A.cuda(), W.cuda(), out, bias=bias.cuda(), act=1)
+    assert rel(out, F.silu(base)) < 1e-3
+    # GEGLU with interleaved rows
+    Wg = randn(46, 2 * N, K, scale=K ** -0.5).half()
+    bg = 0.1 * randn(47, 2 * N)
+    full = A.float() @ Wg.float().t() + bg
+    ref = full[:, :N] * F.gelu(full[:, N:])
+    Wi = torch.stack([Wg[:N], Wg[N:]], 1).reshape(2 * N, K).contiguous()
+    bi = torch.stack([bg[:N], bg[N:]], 1).reshape(-1).contiguous()
+    og = torch.empty(M, N, dtype=torch.float16, device="cuda")
+    ops.gemm(A.cuda(), Wi.cuda(), og, bias=bi.cuda(), act=2)
+    assert rel(og, ref) < 1.5e-3
+    # strided A (column slice) and K-sliced W
+    out2 = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    Ac = A.cuda()
+    ops.gemm(Ac[:, 64:], W.cuda()[:, 64:], out2, K=128, lda=K, ldw=K)
+    assert rel(out2, A[:, 64:].float() @ W[:, 64:].float().t()) < 2e-5
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W,stride,up", [
+    (2, 64, 64, 6, 10, 1, 0), (1, 8, 320, 16, 16, 1, 0), (2, 320, 4, 16, 16, 1, 0), (2, 64, 96, 9, 7, 2, 0),
+    (2, 64, 64, 8, 8, 2, 0), (1, 128, 64, 5, 6, 1, 1), (3, 320, 640, 8, 8, 1, 0), (1, 640, 320, 16, 16, 1, 1)])
+def test_conv3x3(ops, N, Cin, Cout, H, W, stride, up):
+    x = randn(51, N, Cin, H, W)
+    w = randn(52, Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5)
+    b = 0.1 * randn(53, Cout)
+    x16, w16 = x.half().float(), w.half().float()
+    xin = F.interpolate(x16, scale_factor=2, mode="nearest") if up else x16
+    ref = F.conv2d(xin, w16, b, stride=stride, padding=1)
+    Ho, Wo = ref.shape[2:]
+    emb = randn(54, N, Cout)
+    res = randn(55, N, Cout, Ho, Wo).half()
+    ref = ref + emb[:, :, None, None] + res.float()
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).half().contiguous().cuda()
+    out = torch.empty(N * Ho * Wo, Cout, dtype=torch.float16, device="cuda")
+    ho, wo = ops.conv3x3(to_nhwc16(x), wp, out, bias=b.cuda(), rowadd=emb.cuda(), residual=to_nhwc16(res.float()).view(-1, Cout),
+                         stride=stride, upsample=up)
+    assert (ho, wo) == (Ho, Wo)
+    e = rel(from_nhwc(out, N, Ho, Wo), ref)
+    assert e < 1e-3, e
+
+
+def test_conv_golden_kats(ops):
+    """Downsample / Upsample outputs of the reference's own modules (openaimodel.py:90-159)."""
+    from oracle import weights
+    g = np.load(os.path.join(G, "op_kats.npz"))
+    x = torch.from_numpy(g["gn_x"])
+    N, C, H, W = x.shape
+    for key, names, seed, kw in (("down_out", ("dn.0.op.weight", "dn.0.op.bias"), 25, dict(stride=2)),
+                                 ("up_out", ("up.0.conv.weight", "up.0.conv.bias"), 26, dict(upsample=1))):
+        sd = weights.make_state_dict({names[0]: (64, 64, 3, 3), names[1]: (64,)}, seed)
+        wp = sd[names[0]].permute(0, 2, 3, 1).reshape(64, -1).half().contiguous().cuda()
+        ref = torch.from_numpy(g[key])
+        Ho, Wo = ref.shape[2:]
+        out = torch.empty(N * Ho * Wo, 64, dtype=torch.float16, device="cuda")
+        ops.conv3x3(to_nhwc16(x), wp, out, bias=sd[names[1]].cuda(), **kw)
+        e = rel(from_nhwc(out, N, Ho, Wo), ref)
+        assert e < 2e-3, (key, e)
+
+
+@pytest.mark.parametrize("B,heads,nq,nkv,d", [(2, 4, 40, 40, 16), (1, 8, 256, 256, 40), (2, 8, 100, 77, 40),
+                                              (1, 8, 128, 128, 80), (1, 8, 64, 77, 160), (2, 5, 200, 257, 64),
+                                              (1, 8, 16, 16, 160), (1, 2, 1024, 1024, 40), (1, 1, 70, 9, 48)])
+def test_attention(ops, B, heads, nq, nkv, d):
+    from oracle import unet_oracle
+    C = heads * d
+    q, k, v = randn(61, B, nq, C), randn(62, B, nkv, C), randn(63, B, nkv, C)
+    q16, k16, v16 = q.half(), k.half(), v.half()
+
+    def split(t):
+        return t.float().reshape(B, t.shape[1], heads, d).permute(0, 2, 1, 3).reshape(B * heads, t.shape[1], d)
+
+    ref = unet_oracle.attention_bhnd(split(q16), split(k16), split(v16))
+    ref = ref.reshape(B, heads, nq, d).permute(0, 2, 1, 3).reshape(B, nq, C)
+    out = torch.empty(B, nq, C, dtype=torch.float16, device="cuda")
+    ops.attention(q16.cuda(), k16.cuda(), v16.cuda(), out, B, heads, nq, nkv, d, C, C, C, C)
+    e = rel(out, ref)
+    assert e < 2e-3, e
+    # fused-projection layout: q/k/v as column slices of one [B*n, 3C] buffer (self-attention)
+    if nq == nkv:
+        qkv = torch.cat([q16, k16, v16], -1).cuda().contiguous()
+        flat = qkv.view(B * nq, 3 * C)
+        out2 = torch.empty_like(out)
+        ops.attention(flat, flat[:, C:], flat[:, 2 * C:], out2, B, heads, nq, nkv, d, 3 * C, 3 * C, 3 * C, C)
+        assert torch.equal(out, out2)
+    # gated accumulate (router expert sum)
+    gate = torch.rand(B, generator=torch.Generator().manual_seed(64))
+    out3 = out.clone()
+    ops.attention(q16.cuda(), k16.cuda(), v16.cuda(), out3, B, heads, nq, nkv, d, C, C, C, C, gate=gate.cuda(),
+                  gate_stride=1, accumulate=True)
+    ref3 = out.float().cpu() + gate[:, None, None] * ref
+    assert rel(out3, ref3) < 2e-3
+
+
+def test_cross_attention_module_golden(ops):
+    """CrossAttention module output of the reference (attention.py:145-194), assembled from our
+    GEMM + attention kernels the way anyedit_b200.unet does."""
+    from oracle import weights
+    g = np.load(os.path.join(G, "op_kats.npz"))
+    x, ctx, ref = (torch.from_numpy(g[k]) for k in ("ca_x", "ca_ctx", "ca_out"))
+    shapes = {"attn2.to_q.weight": (64, 64), "attn2.to_k.weight": (64, 48), "attn2.to_v.weight": (64, 48),
+              "attn2.to_out.0.weight": (64, 64), "attn2.to_out.0.bias": (64,)}
+    sd = weights.make_state_dict(shapes, 22)
+    B, n, C = x.shape
+    L = ctx.shape[1]
+    h16 = lambda t: t.half().cuda().contiguous()
+    q = torch.empty(B * n, C, dtype=torch.float16, device="cuda")
+    ops.gemm(h16(x).view(B * n, C), h16(sd["attn2.to_q.weight"]), q)
+    kv = torch.empty(B * L, 2 * C, dtype=torch.float16, device="cuda")
+    ops.gemm(h16(ctx).view(B * L, -1), h16(torch.cat([sd["attn2.to_k.weight"], sd["attn2.to_v.weight"]], 0)), kv)
+    a = torch.empty(B * n, C, dtype=torch.float16, device="cuda")
+    ops.attention(q, kv, kv[:, C:], a, B, 4, n, L, 16, C, 2 * C, 2 * C, C)
+    out = torch.empty(B * n, C, dtype=torch.float32, device="cuda")
+    ops.gemm(a, h16(sd["attn2.to_out.0.weight"]), out, bias=sd["attn2.to_out.0.bias"].cuda())
+    e = rel(out.view(B, n, C), ref)
+    assert e < 3e-3, e
+
+
+def test_cfg_ddim_step_bit_exact(ops):
+    """The fused update reproduces the reference's fp32 tensor arithmetic bit for bit (ddim.py:211-250)."""
+    from anyedit_b200.ddim import step_coefficients
+    from oracle import ddim_oracle
+    sched = ddim_oracle.register_schedule("linear", 1000, 0.00085, 0.012)
+    ts = ddim_oracle.make_ddim_timesteps("uniform", 50, 1000)
+    for eta in (0.0, 0.7):
+        sig, a, ap = ddim_oracle.make_ddim_sampling_parameters(sched["alphas_cumprod"], ts, eta)
+        soma = np.sqrt(1.0 - a)
+        B, shape = 3, (3, 4, 8, 8)
+        x, eu, ec, nz = randn(71, *shape), randn(72, *shape), randn(73, *shape), randn(74, *shape)
+        for index in (0, 17, 49):
+            coef = torch.tensor(step_coefficients(a, ap, sig, soma, index), dtype=torch.float32).cuda()
+            full = lambda v: torch.full((B, 1, 1, 1), float(v))
+            a_t, a_prev, s_t, so = full(a[index]), full(ap[index]), full(sig[index]), full(soma[index])
+            e_t = eu + 7.5 * (ec - eu)
+            pred = (x - so * e_t) / a_t.sqrt()
+            dirx = (1.0 - a_prev - s_t ** 2).sqrt() * e_t
+            ref = a_prev.sqrt() * pred + dirx + s_t * nz
+            xp, p0 = torch.empty(shape, device="cuda"), torch.empty(shape, device="cuda")
+            ops.cfg_ddim_step(x.cuda(), torch.cat([eu, ec]).cuda(), coef, 7.5, True, xp, p0,
+                              nz.cuda() if eta else None)
+            assert torch.equal(p0.cpu(), pred), (eta, index)
+            assert torch.equal(xp.cpu(), ref), (eta, index)
+
+
+def test_router_gate(ops):
+    T, D, L, E, B = 7, 256, 5, 11, 6
+    table, W, bias = randn(81, T, D, scale=0.5), randn(82, L, E, D, scale=D ** -0.5), 0.1 * randn(83, L, E)
+    idx = torch.tensor([0, 6, 3, 3, 1, 5])
+    gate = torch.empty(B, L, E, device="cuda")
+    ops.router_gate(table.cuda(), idx.cuda(), W.half().cuda(), bias.cuda(), gate)
+    ref = torch.softmax(torch.einsum("led,bd->ble", W.half().float(), table[idx]) + bias, -1)
+    assert (gate.cpu() - ref).abs().max() < 1e-5
+
+
+def test_errors_are_loud(ops):
+    out = torch.empty(4, 4, dtype=torch.float16, device="cuda")
+    with pytest.raises(ValueError):
+        ops.gemm(torch.empty(4, 12, dtype=torch.float16, device="cuda"), torch.empty(4, 12, dtype=torch.float16, device="cuda"), out)
+    with pytest.raises(Exception):
+        ops.gemm(torch.empty(4, 8, dtype=torch.float16), torch.empty(4, 8, dtype=torch.float16), out)  # CPU tensors
