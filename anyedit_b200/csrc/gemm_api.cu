@@ -1,8 +1,12 @@
 // anysd_gemm_f16: argument validation and kernel selection for every dense contraction on the path.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace anysd {
 int launch_gemm_mma(const anysd_gemm_params* q, cudaStream_t st);
+int launch_gemm_tc5(const anysd_gemm_params* q, cudaStream_t st);
+bool tc5_supported(const anysd_gemm_params* q);
 }
 
 using namespace anysd;
@@ -39,5 +43,11 @@ extern "C" int anysd_gemm_f16(const anysd_gemm_params* p, anysd_stream_t stream)
         ANYSD_REQUIRE(p->lda % 8 == 0 && p->lda >= p->K, ANYSD_EINVAL, "gemm: lda=%d must be a multiple of 8 and >= K",
                       p->lda);
     }
+    // tcgen05/TMA kernel wherever its layout constraints hold (every dense contraction and every stride-1
+    // 3x3 conv with Cin % 64 == 0 of the UNet); the mma.sync kernel covers the rest (Cin = 8 input conv,
+    // N = 4 output conv, stride-2 / upsample-folded convs).  ANYSD_FORCE_MMA=1 is a test/debug switch used
+    // to cross-check the two kernels against each other.
+    static const bool force_mma = getenv("ANYSD_FORCE_MMA") != nullptr && getenv("ANYSD_FORCE_MMA")[0] == '1';
+    if (!force_mma && tc5_supported(p)) return launch_gemm_tc5(p, (cudaStream_t)stream);
     return launch_gemm_mma(p, (cudaStream_t)stream);
 }

@@ -318,10 +318,14 @@ class _Stepper:
                     return self.x_prev.clone(), self.pred_x0.clone()
                 g = torch.cuda.CUDAGraph()
                 torch.cuda.synchronize()
+                n0 = ops.launch_count
                 with torch.cuda.graph(g):
                     self._body(scale, nb)
+                self.graph_launches = ops.launch_count - n0    # kernels recorded into the graph
+                ops.launch_count = n0
                 self.graph, self.scale = g, scale
             self.graph.replay()
+            ops.launch_count += self.graph_launches
         else:
             self._body(scale, nb)
         return self.x_prev.clone(), self.pred_x0.clone()

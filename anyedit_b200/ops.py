@@ -36,6 +36,30 @@ def _count(n=1):
     launch_count += n
 
 
+# Optional per-launch tracing for bench.py's roofline leg: when ``trace`` is a list, the tensor-core
+# wrappers bracket their launch with CUDA events on the launching stream and append
+# (kind, algorithmic_flops, start_event, end_event).  None (default) adds no work.
+trace = None
+
+
+class _Traced:
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if trace is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if trace is not None:
+            self.e1.record()
+            trace.append((self.kind, self.flops, self.e0, self.e1))
+        return False
+
+
 def device_info():
     lib = _lib.load()
     a, b, c = C.c_int(), C.c_int(), C.c_int()
@@ -151,7 +175,8 @@ def gemm(A, W, out, bias=None, rowadd=None, rows_per_batch=0, residual=None, act
     p.act = act
     p.out_dtype = _DT[out.dtype]
     p.conv = 0
-    _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "gemm")
+    with _Traced("gemm", 2.0 * p.M * p.N * p.K):
+        _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "gemm")
     _count()
 
 
@@ -177,7 +202,8 @@ def conv3x3(x, W, out, bias=None, rowadd=None, residual=None, stride=1, upsample
     p.conv = 1
     p.Nimg, p.H, p.Wd, p.Cin = Nimg, H, Wd, Cin
     p.stride, p.upsample = stride, upsample
-    _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "conv3x3")
+    with _Traced("conv3x3", 2.0 * p.M * p.N * p.K):
+        _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "conv3x3")
     _count()
     return Ho, Wo
 
@@ -198,7 +224,8 @@ def attention(q, k, v, out, B, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o, q_bs
     p.gate = gate.data_ptr() if gate is not None else None
     p.gate_stride = gate_stride
     p.accumulate = int(bool(accumulate))
-    _lib.check(_lib.load().anysd_attention_f16(C.byref(p), _stream()), "attention")
+    with _Traced("attention", 4.0 * B * heads * n_q * n_kv * d):
+        _lib.check(_lib.load().anysd_attention_f16(C.byref(p), _stream()), "attention")
     _count()
 
 
