@@ -34,6 +34,7 @@ struct Tc5Args {
     int Nimg, Ho, Wo, Cin;
     int BW, BH, NB, tiles_w, tiles_h;
     int kb_per_tap;
+    int stride;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -165,7 +166,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc5_kernel(const __grid_co
                     const int tap = kb / p.kb_per_tap;
                     const int c0 = (kb - tap * p.kb_per_tap) * TC_BK;
                     const int ky = tap / 3, kx = tap - ky * 3;
-                    tma_load_4d(sa, &tmA, full_bar(s), c0, tw * p.BW + kx - 1, th * p.BH + ky - 1, tn * p.NB);
+                    tma_load_4d(sa, &tmA, full_bar(s), c0, tw * p.BW * p.stride + kx - 1, th * p.BH * p.stride + ky - 1,
+                                tn * p.NB);
                 } else {
                     tma_load_2d(sa, &tmA, full_bar(s), kb * TC_BK, m0);
                 }
@@ -321,13 +323,15 @@ static bool encode_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static bool encode_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, int BW, int BH, int NB) {
+// stride s (1|2): the box traverses s*BW x s*BH input pixels with element stride s, i.e. loads BW x BH
+// pixels (cuTensorMapEncodeTiled: "to load N elements along a dimension, boxDim = N * elementStrides").
+static bool encode_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, int BW, int BH, int NB, int s) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)BW, (cuuint32_t)BH, (cuuint32_t)NB};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)(BW * s), (cuuint32_t)(BH * s), (cuuint32_t)NB};
+    cuuint32_t es[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -369,6 +373,27 @@ static void pick_patch(int Ho, int Wo, int* BW, int* BH, int* NB) {
     *NB = 128 / (bw * bh);
 }
 
+// nearest-neighbour x2 (F.interpolate(scale_factor=2, mode="nearest"), openaimodel.py:110-115) on NHWC fp16
+__global__ void upsample2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int H, int W, int CV, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % CV);
+        long long r = i / CV;
+        const int ox = (int)(r % (2 * W));
+        r /= (2 * W);
+        const int oy = (int)(r % (2 * H));
+        const long long n = r / (2 * H);
+        dst[i] = __ldg(src + ((n * H + (oy >> 1)) * W + (ox >> 1)) * CV + cv);
+    }
+}
+
+int launch_upsample2x(const __half* src, __half* dst, int N, int H, int W, int C, cudaStream_t st) {
+    const long long total = (long long)N * 4 * H * W * (C / 8);
+    int grid = (int)((total + 255) / 256);
+    if (grid > sm_count() * 16) grid = sm_count() * 16;
+    upsample2x_kernel<<<grid, 256, 0, st>>>((const uint4*)src, (uint4*)dst, H, W, C / 8, total);
+    return check_launch("upsample2x");
+}
+
 bool tc5_supported(const anysd_gemm_params* q) {
     if (q->N % 8 != 0 || q->K % 8 != 0) return false;
     if (q->act == 2 && q->N % 16 != 0) return false;
@@ -378,7 +403,11 @@ bool tc5_supported(const anysd_gemm_params* q) {
     if (q->bias && ((uintptr_t)q->bias % 16)) return false;
     if (q->rowadd && (((uintptr_t)q->rowadd % 16) || q->ld_rowadd % 4 != 0)) return false;
     if (q->conv) {
-        if (q->stride != 1 || q->upsample != 0 || q->Cin % TC_BK != 0) return false;
+        if (q->Cin % TC_BK != 0) return false;
+        if (q->upsample) {   // nearest x2 is materialised into the caller's workspace first
+            const size_t need = (size_t)q->Nimg * (2 * q->H) * (2 * q->Wd) * q->Cin * sizeof(__half);
+            if (q->workspace == nullptr || q->workspace_bytes < need || ((uintptr_t)q->workspace % 16)) return false;
+        }
     }
     return get_encode() != nullptr;
 }
@@ -410,9 +439,22 @@ int launch_gemm_tc5(const anysd_gemm_params* q, cudaStream_t st) {
     a.rows_per_batch = q->rows_per_batch > 0 ? q->rows_per_batch : 1;
     a.act = q->act; a.out_f16 = q->out_dtype == ANYSD_F16;
     a.num_kb = cdiv(q->K, TC_BK);
-    a.Nimg = q->Nimg; a.Ho = q->H; a.Wo = q->Wd; a.Cin = q->Cin;
+    a.Nimg = q->Nimg; a.Cin = q->Cin;
     a.BW = a.BH = a.NB = a.tiles_w = a.tiles_h = 1;
     a.kb_per_tap = 1;
+    a.stride = q->conv ? q->stride : 1;
+    // conv input as the tensor map sees it (after the optional materialised nearest-x2 upsample)
+    const void* img = q->A;
+    int Hin = q->H, Win = q->Wd;
+    if (q->conv && q->upsample) {
+        int rc = launch_upsample2x((const __half*)q->A, (__half*)q->workspace, q->Nimg, q->H, q->Wd, q->Cin, st);
+        if (rc) return rc;
+        img = q->workspace;
+        Hin = 2 * q->H;
+        Win = 2 * q->Wd;
+    }
+    a.Ho = (Hin - 1) / a.stride + 1;
+    a.Wo = (Win - 1) / a.stride + 1;
     const int BN = pick_bn(q->N);
     CUtensorMap tmA, tmB;
     if (!encode_2d(&tmB, q->W, (uint64_t)q->K, (uint64_t)q->N, (uint64_t)q->ldw, TC_BK, BN)) {
@@ -421,13 +463,13 @@ int launch_gemm_tc5(const anysd_gemm_params* q, cudaStream_t st) {
     }
     dim3 grid;
     if (q->conv) {
-        pick_patch(q->H, q->Wd, &a.BW, &a.BH, &a.NB);
-        a.tiles_w = cdiv(q->Wd, a.BW);
-        a.tiles_h = cdiv(q->H, a.BH);
+        pick_patch(a.Ho, a.Wo, &a.BW, &a.BH, &a.NB);
+        a.tiles_w = cdiv(a.Wo, a.BW);
+        a.tiles_h = cdiv(a.Ho, a.BH);
         const int tiles_n = cdiv(q->Nimg, a.NB);
         a.kb_per_tap = q->Cin / TC_BK;
         a.num_kb = 9 * a.kb_per_tap;
-        if (!encode_nhwc(&tmA, q->A, q->Nimg, q->H, q->Wd, q->Cin, a.BW, a.BH, a.NB)) {
+        if (!encode_nhwc(&tmA, img, q->Nimg, Hin, Win, q->Cin, a.BW, a.BH, a.NB, a.stride)) {
             set_error("tcgen05 conv: cuTensorMapEncodeTiled failed for x (N=%d H=%d W=%d C=%d box %dx%dx%d)", q->Nimg, q->H,
                       q->Wd, q->Cin, a.BW, a.BH, a.NB);
             return ANYSD_ECUDA;

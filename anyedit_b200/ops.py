@@ -202,6 +202,9 @@ def conv3x3(x, W, out, bias=None, rowadd=None, residual=None, stride=1, upsample
     p.conv = 1
     p.Nimg, p.H, p.Wd, p.Cin = Nimg, H, Wd, Cin
     p.stride, p.upsample = stride, upsample
+    if upsample:   # scratch for the materialised nearest-x2 input of the tcgen05 path
+        ws = torch.empty(Nimg * Hl * Wl * Cin, dtype=torch.float16, device=x.device)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel() * 2
     with _Traced("conv3x3", 2.0 * p.M * p.N * p.K):
         _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "conv3x3")
     _count()

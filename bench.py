@@ -101,7 +101,8 @@ def cpu_arm(latent, ddim_steps, scale, n_steps_sample=3):
     import torch
     from oracle import ddim_oracle, unet_oracle, weights
     from anyedit_b200.unet import UNetModel
-    cores = os.cpu_count() or 1
+    from oracle.cpu import usable_cores
+    cores = usable_cores()              # min(affinity, cgroup CPU quota): what the box lets us use
     torch.set_num_threads(cores)
     global _CPU_SD
     if _CPU_SD is None:                 # 859.5 M seeded weights, generated once per process (untimed)

@@ -108,6 +108,8 @@ typedef struct {
     int Nimg, H, Wd, Cin;   /* conv: input image dims (before the folded upsample) */
     int stride;             /* conv: 1 | 2 */
     int upsample;           /* conv: 1 = nearest x2 before the conv */
+    void* workspace;        /* optional scratch (conv with upsample: >= Nimg*2H*2W*Cin fp16), may be NULL */
+    size_t workspace_bytes;
 } anysd_gemm_params;
 int anysd_gemm_f16(const anysd_gemm_params* p, anysd_stream_t stream);
 
