@@ -2,11 +2,14 @@
 #include "common.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace anysd {
 int launch_gemm_mma(const anysd_gemm_params* q, cudaStream_t st);
 int launch_gemm_tc5(const anysd_gemm_params* q, cudaStream_t st);
 bool tc5_supported(const anysd_gemm_params* q);
+int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st);
+bool tc5p_supported(const anysd_gemm_params* q);
 }
 
 using namespace anysd;
@@ -43,11 +46,15 @@ extern "C" int anysd_gemm_f16(const anysd_gemm_params* p, anysd_stream_t stream)
         ANYSD_REQUIRE(p->lda % 8 == 0 && p->lda >= p->K, ANYSD_EINVAL, "gemm: lda=%d must be a multiple of 8 and >= K",
                       p->lda);
     }
-    // tcgen05/TMA kernel wherever its layout constraints hold (every dense contraction and every stride-1
-    // 3x3 conv with Cin % 64 == 0 of the UNet); the mma.sync kernel covers the rest (Cin = 8 input conv,
-    // N = 4 output conv, stride-2 / upsample-folded convs).  ANYSD_FORCE_MMA=1 is a test/debug switch used
-    // to cross-check the two kernels against each other.
-    static const bool force_mma = getenv("ANYSD_FORCE_MMA") != nullptr && getenv("ANYSD_FORCE_MMA")[0] == '1';
-    if (!force_mma && tc5_supported(p)) return launch_gemm_tc5(p, (cudaStream_t)stream);
+    // Kernel selection.  The persistent tcgen05/TMA kernel (gemm_tc5p.cu) takes every fp16-output contraction
+    // whose layout constraints hold: all nn.Linear / 1x1 convs and every 3x3 conv with Cin % 64 == 0 (stride 1|2,
+    // upsample through the workspace).  The one-tile-per-CTA tcgen05 kernel (gemm_tc5.cu) takes the fp32-output
+    // ones (time-embedding path).  mma.sync covers what is left: the Cin = 8 input conv and the N = 4 output conv.
+    // ANYSD_GEMM=mma|tc5|tc5p is a test/debug switch used to cross-check the kernels against each other.
+    static const char* force = getenv("ANYSD_GEMM");
+    const bool allow_p = !force || !strcmp(force, "tc5p");
+    const bool allow_1 = !force || !strcmp(force, "tc5");
+    if (allow_p && tc5p_supported(p)) return launch_gemm_tc5p(p, (cudaStream_t)stream);
+    if ((allow_1 || (force && !strcmp(force, "tc5p"))) && tc5_supported(p)) return launch_gemm_tc5(p, (cudaStream_t)stream);
     return launch_gemm_mma(p, (cudaStream_t)stream);
 }

@@ -1,0 +1,558 @@
+// Persistent tcgen05 contraction (second generation of gemm_tc5.cu; same operand plumbing).
+//
+//   * one CTA per SM, static round-robin over output tiles (128 x <=256), n-tile fastest so that the CTAs
+//     running concurrently share A rows and weight tiles in L2;
+//   * TMA producer warp / single-thread MMA issuer / 4 epilogue warps, smem ring of 3 x (16 KB A + 32 KB B);
+//   * TWO accumulator buffers in TMEM (2 x 256 columns): the MMA warp starts tile t+1 while the epilogue
+//     drains tile t; the TMA ring keeps running across tile boundaries;
+//   * tile width is a run-time quantity (UMMA N in the instruction descriptor): N = 320 is 256 + 64, no padding work;
+//   * epilogue in 64-column sub-tiles through 4 swizzled 16 KB staging buffers: the residual sub-tile is
+//     TMA-PREFETCHED into the buffer, combined in place (bias / time-embedding row add / SiLU / GEGLU /
+//     residual), and written back with a TMA store (2-D map for token matrices, 4-D NHWC map for conv
+//     patches -- edge clipping is the tensor map's job, no per-row predicates, no scattered 16-byte stores).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace anysd {
+
+constexpr int P_BM = 128, P_BK = 64, P_BN = 256, P_STAGES = 3, P_NSTG = 4, P_SUB = 64;
+constexpr int P_THREADS = 256;                       // warps 0..3: TMA, MMA, TMEM-alloc, spare; warps 4..7: epilogue
+constexpr int P_A_BYTES = P_BM * P_BK * 2;           // 16 KB
+constexpr int P_B_BYTES = P_BN * P_BK * 2;           // 32 KB
+constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES; // 48 KB
+constexpr int P_STG_BYTES = P_BM * P_SUB * 2;        // 16 KB
+constexpr int P_SMEM = P_STAGES * P_STAGE_BYTES + P_NSTG * P_STG_BYTES + 1024 + 256;
+
+struct PArgs {
+    const float* bias;
+    const float* rowadd;
+    int M, N, ld_rowadd, rows_per_batch;
+    int act, has_res;
+    int num_kb, tiles_m, tiles_n, num_tiles;
+    // conv geometry
+    int Nimg, Ho, Wo;
+    int BW, BH, NB, tiles_w, tiles_h;
+    int kb_per_tap, stride;
+};
+
+// ---- PTX wrappers (same forms as gemm_tc5.cu) -------------------------------------------------------
+__device__ __forceinline__ void pm_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void pm_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pm_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void pm_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void p_tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void p_tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void p_tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void p_tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void p_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void p_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void p_store_wait() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void p_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void p_umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void p_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void p_tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void p_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void p_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void p_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void p_epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t p_sdesc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// erf with |abs err| < 1.5e-7 (Abramowitz-Stegun 7.1.26): far below fp16 resolution, ~12 instructions
+__device__ __forceinline__ float fast_erf(float x) {
+    const float ax = fabsf(x);
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * __expf(-ax * ax);
+    return copysignf(e, x);
+}
+__device__ __forceinline__ float p_gelu(float v) { return 0.5f * v * (1.0f + fast_erf(v * 0.70710678118654752440f)); }
+
+struct TileCoord {
+    int n0, nw;          // first column, width (multiple of 16, <= 256)
+    int m0;              // dense: first row
+    int tw, th, tn;      // conv: patch indices
+};
+
+template <bool CONV>
+__device__ __forceinline__ TileCoord tile_coord(const PArgs& p, int tile) {
+    TileCoord c;
+    const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+    c.n0 = nt * P_BN;
+    int w = p.N - c.n0;
+    if (w > P_BN) w = P_BN;
+    c.nw = (w + 15) & ~15;
+    c.m0 = mt * P_BM;
+    c.tw = c.th = c.tn = 0;
+    if (CONV) {
+        c.tw = mt % p.tiles_w;
+        c.th = (mt / p.tiles_w) % p.tiles_h;
+        c.tn = mt / (p.tiles_w * p.tiles_h);
+    }
+    return c;
+}
+
+template <bool CONV>
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const PArgs p) {
+    extern __shared__ unsigned char p_smem_raw[];
+    const uint32_t raw = smem_u32(p_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char* smem = p_smem_raw + (base - raw);
+    const uint32_t stg_base = base + P_STAGES * P_STAGE_BYTES;
+    const uint32_t bar_base = stg_base + P_NSTG * P_STG_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (P_STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * P_STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * P_STAGES + 2 + b); };
+    auto res_bar = [&](int b) { return bar_base + 8u * (2 * P_STAGES + 4 + b); };
+    volatile uint32_t* tmem_slot =
+        reinterpret_cast<volatile uint32_t*>(smem + P_STAGES * P_STAGE_BYTES + P_NSTG * P_STG_BYTES + 8 * (2 * P_STAGES + 4 + P_NSTG));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
+        if (p.has_res) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < P_STAGES; ++s) {
+            pm_init(full_bar(s), 1);
+            pm_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            pm_init(tfull_bar(b), 1);
+            pm_init(tempty_bar(b), 4);       // one arrive per epilogue warp
+        }
+        for (int b = 0; b < P_NSTG; ++b) pm_init(res_bar(b), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    p_fence_before();
+    __syncthreads();
+    p_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer: runs ahead across tile boundaries =====
+            uint32_t g = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord c = tile_coord<CONV>(p, tile);
+                for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+                    const int s = g % P_STAGES;
+                    const uint32_t ph = (g / P_STAGES) & 1;
+                    pm_wait(empty_bar(s), ph ^ 1);
+                    pm_expect_tx(full_bar(s), P_STAGE_BYTES);
+                    const uint32_t sa = base + s * P_STAGE_BYTES, sb = sa + P_A_BYTES;
+                    if (CONV) {
+                        const int tap = kb / p.kb_per_tap;
+                        const int c0 = (kb - tap * p.kb_per_tap) * P_BK;
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        p_tma_load_4d(sa, &tmA, full_bar(s), c0, c.tw * p.BW * p.stride + kx - 1,
+                                      c.th * p.BH * p.stride + ky - 1, c.tn * p.NB);
+                    } else {
+                        p_tma_load_2d(sa, &tmA, full_bar(s), kb * P_BK, c.m0);
+                    }
+                    p_tma_load_2d(sb, &tmB, full_bar(s), kb * P_BK, c.n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            uint32_t g = 0, t = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
+                const TileCoord c = tile_coord<CONV>(p, tile);
+                const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+                pm_wait(tempty_bar(buf), bph ^ 1);           // epilogue has drained this accumulator
+                p_fence_after();
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(c.nw >> 3) << 17) | ((uint32_t)(P_BM >> 4) << 24);
+                const uint32_t d = tmem_base + buf * P_BN;
+                for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+                    const int s = g % P_STAGES;
+                    const uint32_t ph = (g / P_STAGES) & 1;
+                    pm_wait(full_bar(s), ph);
+                    p_fence_after();
+                    const uint32_t sa = base + s * P_STAGE_BYTES, sb = sa + P_A_BYTES;
+                    const uint64_t ad = p_sdesc(sa), bd = p_sdesc(sb);
+#pragma unroll
+                    for (int k = 0; k < P_BK / 16; ++k) p_umma(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    p_commit(empty_bar(s));
+                }
+                p_commit(tfull_bar(buf));
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: 4 warps, TMEM lane group = warp % 4, thread = one accumulator row =====
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;
+        const bool elected = (warp == 4 && lane == 0);
+        uint32_t t = 0, q = 0;                                // tile counter, global sub-tile counter
+        const int acc_per_sub = (p.act == 2) ? 2 * P_SUB : P_SUB;   // accumulator columns feeding one 64-column store
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
+            const TileCoord c = tile_coord<CONV>(p, tile);
+            const uint32_t buf = t & 1, bph = (t >> 1) & 1;
+            const int nsub = (c.nw + acc_per_sub - 1) / acc_per_sub;
+            const int out_c0 = (p.act == 2) ? (c.n0 >> 1) : c.n0;   // first output column of the tile
+            // output / residual coordinates of sub-tile j
+            auto issue_res = [&](int j) {
+                const uint32_t b = (q + j) % P_NSTG;
+                pm_expect_tx(res_bar(b), P_STG_BYTES);
+                if (CONV)
+                    p_tma_load_4d(stg_base + b * P_STG_BYTES, &tmR, res_bar(b), out_c0 + j * P_SUB, c.tw * p.BW, c.th * p.BH, c.tn * p.NB);
+                else
+                    p_tma_load_2d(stg_base + b * P_STG_BYTES, &tmR, res_bar(b), out_c0 + j * P_SUB, c.m0);
+            };
+            int img = 0;
+            if (p.rowadd) {
+                if (CONV) {
+                    img = c.tn * p.NB + row / (p.BW * p.BH);
+                    if (img >= p.Nimg) img = p.Nimg - 1;
+                } else {
+                    int m = c.m0 + row;
+                    if (m >= p.M) m = p.M - 1;
+                    img = m / p.rows_per_batch;
+                }
+            }
+            const float* radd = p.rowadd ? p.rowadd + (size_t)img * p.ld_rowadd : nullptr;
+            if (elected && p.has_res) {
+                p_store_wait_read<1>();                        // buffers of the first two sub-tiles are free
+                issue_res(0);
+                if (nsub > 1) issue_res(1);
+            }
+            pm_wait(tfull_bar(buf), bph);
+            p_fence_after();
+            for (int j = 0; j < nsub; ++j) {
+                const uint32_t b = (q + j) % P_NSTG;
+                if (elected) {
+                    p_store_wait_read<1>();                    // every store but the latest has released its buffer
+                    if (p.has_res && j + 2 < nsub) issue_res(j + 2);
+                }
+                p_epi_bar();                                   // staging buffer b is free for everyone
+                unsigned char* stg = smem + P_STAGES * P_STAGE_BYTES + b * P_STG_BYTES + row * 128;
+                if (p.has_res) pm_wait(res_bar(b), ((q + j) / P_NSTG) & 1);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {         // 2 x 32 output columns
+                    float v[32];
+                    const int oc = half * 32;                  // output column offset inside the sub-tile
+                    if (p.act == 2) {
+                        // GEGLU: 64 accumulator columns (a_j, gate_j interleaved) -> 32 outputs
+                        uint32_t r0[32], r1[32];
+                        const int ac = j * 2 * P_SUB + half * 64;
+                        __syncwarp();
+                        p_tmem_ld32(tmem_base + buf * P_BN + ((uint32_t)(lg * 32) << 16) + ac, r0);
+                        p_tmem_ld32(tmem_base + buf * P_BN + ((uint32_t)(lg * 32) << 16) + ac + 32, r1);
+                        p_tmem_wait_ld();
+                        const int nb = c.n0 + ac;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float a0 = __uint_as_float(r0[2 * i]), g0 = __uint_as_float(r0[2 * i + 1]);
+                            float a1 = __uint_as_float(r1[2 * i]), g1 = __uint_as_float(r1[2 * i + 1]);
+                            if (p.bias) {
+                                const int n_a = nb + 2 * i, n_b = nb + 32 + 2 * i;
+                                if (n_a + 1 < p.N) { a0 += __ldg(p.bias + n_a); g0 += __ldg(p.bias + n_a + 1); }
+                                if (n_b + 1 < p.N) { a1 += __ldg(p.bias + n_b); g1 += __ldg(p.bias + n_b + 1); }
+                            }
+                            v[i] = a0 * p_gelu(g0);
+                            v[16 + i] = a1 * p_gelu(g1);
+                        }
+                    } else {
+                        uint32_t r[32];
+                        const int ac = j * P_SUB + oc;
+                        __syncwarp();
+                        p_tmem_ld32(tmem_base + buf * P_BN + ((uint32_t)(lg * 32) << 16) + ac, r);
+                        p_tmem_wait_ld();
+                        const int nb = c.n0 + ac;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                        if (nb + 32 <= p.N) {
+                            if (p.bias) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + i);
+                                    v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+                                }
+                            }
+                            if (radd) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 bb = __ldg(reinterpret_cast<const float4*>(radd + nb) + i);
+                                    v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                if (nb + i < p.N) {
+                                    if (p.bias) v[i] += __ldg(p.bias + nb + i);
+                                    if (radd) v[i] += __ldg(radd + nb + i);
+                                }
+                            }
+                        }
+                        if (p.act == 1) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+                        }
+                    }
+                    // combine with the prefetched residual in place; 128-byte swizzled staging row
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        const int chunk = (oc >> 3) + ch;       // 16-byte chunk index 0..7 in the 128-byte row
+                        uint4* slot = reinterpret_cast<uint4*>(stg + ((chunk ^ (row & 7)) << 4));
+                        float* vv = v + ch * 8;
+                        if (p.has_res) {
+                            float rr[8];
+                            unpack8(*slot, rr);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) vv[i] += rr[i];
+                        }
+                        *slot = pack8(vv);
+                    }
+                }
+                p_fence_async_smem();                          // generic-proxy writes -> visible to the TMA store
+                p_epi_bar();
+                if (elected) {
+                    if (CONV)
+                        p_tma_store_4d(&tmO, stg_base + b * P_STG_BYTES, out_c0 + j * P_SUB, c.tw * p.BW, c.th * p.BH, c.tn * p.NB);
+                    else
+                        p_tma_store_2d(&tmO, stg_base + b * P_STG_BYTES, out_c0 + j * P_SUB, c.m0);
+                    p_store_commit();
+                }
+            }
+            q += nsub;
+            // accumulator fully read: hand the TMEM buffer back to the MMA warp
+            p_fence_before();
+            __syncwarp();
+            if (lane == 0) pm_arrive(tempty_bar(buf));
+        }
+        if (elected) p_store_wait<0>();                        // smem must outlive the last store
+    }
+    p_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFnP)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFnP p_get_encode() {
+    static EncodeTiledFnP fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFnP)f;
+    }
+    return fn;
+}
+
+static bool p_map_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t bi, uint32_t bo) {
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {bi, bo};
+    cuuint32_t es[2] = {1, 1};
+    return p_get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// NHWC tensor [N, H, W, C] with row pitch ld (elements per pixel), box 64 x BW x BH x NB, element stride s in W/H
+static bool p_map_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, int ld, int BW, int BH, int NB, int s) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+    cuuint32_t box[4] = {64u, (cuuint32_t)(BW * s), (cuuint32_t)(BH * s), (cuuint32_t)NB};
+    cuuint32_t es[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+    return p_get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int p_pow2_ceil(int v) {
+    int r = 1;
+    while (r < v) r <<= 1;
+    return r;
+}
+static int p_pick_extent(int len, int cap) {
+    int lim = p_pow2_ceil(len);
+    if (lim > cap) lim = cap;
+    for (int c = lim; c >= 4; c >>= 1)
+        if (len % c == 0) return c;
+    return lim;
+}
+
+int launch_upsample2x(const __half* src, __half* dst, int N, int H, int W, int C, cudaStream_t st);
+
+bool tc5p_supported(const anysd_gemm_params* q) {
+    if (q->out_dtype != ANYSD_F16) return false;
+    if (q->N % 8 != 0 || q->K % 8 != 0) return false;
+    if (q->act == 2 && q->N % 128 != 0) return false;
+    const int n_out = q->act == 2 ? q->N / 2 : q->N;
+    if (((uintptr_t)q->out % 16) || q->ldo % 8 != 0 || n_out % 8 != 0) return false;
+    if (q->residual && (((uintptr_t)q->residual % 16) || q->ldr % 8 != 0)) return false;
+    if (q->bias && ((uintptr_t)q->bias % 16)) return false;
+    if (q->rowadd && (((uintptr_t)q->rowadd % 16) || q->ld_rowadd % 4 != 0)) return false;
+    if (q->conv) {
+        if (q->Cin % P_BK != 0) return false;
+        if (q->upsample) {
+            const size_t need = (size_t)q->Nimg * (2 * q->H) * (2 * q->Wd) * q->Cin * sizeof(__half);
+            if (q->workspace == nullptr || q->workspace_bytes < need || ((uintptr_t)q->workspace % 16)) return false;
+        }
+    }
+    return p_get_encode() != nullptr;
+}
+
+int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
+    PArgs a;
+    a.bias = q->bias;
+    a.rowadd = q->rowadd;
+    a.M = q->M;
+    a.N = q->N;
+    a.ld_rowadd = q->ld_rowadd;
+    a.rows_per_batch = q->rows_per_batch > 0 ? q->rows_per_batch : 1;
+    a.act = q->act;
+    a.has_res = q->residual != nullptr;
+    a.num_kb = cdiv(q->K, P_BK);
+    a.tiles_n = cdiv(q->N, P_BN);
+    a.Nimg = q->Nimg;
+    a.BW = a.BH = a.NB = a.tiles_w = a.tiles_h = 1;
+    a.kb_per_tap = 1;
+    a.stride = q->conv ? q->stride : 1;
+    a.Ho = a.Wo = 0;
+    const int n_out = q->act == 2 ? q->N / 2 : q->N;
+    CUtensorMap tmA, tmB, tmO, tmR;
+    if (!p_map_2d(&tmB, q->W, (uint64_t)q->K, (uint64_t)q->N, (uint64_t)q->ldw, P_BK, P_BN)) {
+        set_error("tcgen05 gemm: tensor map for W failed (N=%d K=%d ldw=%d)", q->N, q->K, q->ldw);
+        return ANYSD_ECUDA;
+    }
+    bool ok = true;
+    if (q->conv) {
+        const void* img = q->A;
+        int Hin = q->H, Win = q->Wd;
+        if (q->upsample) {
+            int rc = launch_upsample2x((const __half*)q->A, (__half*)q->workspace, q->Nimg, q->H, q->Wd, q->Cin, st);
+            if (rc) return rc;
+            img = q->workspace;
+            Hin *= 2;
+            Win *= 2;
+        }
+        a.Ho = (Hin - 1) / a.stride + 1;
+        a.Wo = (Win - 1) / a.stride + 1;
+        a.BW = p_pick_extent(a.Wo, 128);
+        a.BH = p_pick_extent(a.Ho, 128 / a.BW);
+        a.NB = 128 / (a.BW * a.BH);
+        a.tiles_w = cdiv(a.Wo, a.BW);
+        a.tiles_h = cdiv(a.Ho, a.BH);
+        a.tiles_m = a.tiles_w * a.tiles_h * cdiv(q->Nimg, a.NB);
+        a.kb_per_tap = q->Cin / P_BK;
+        a.num_kb = 9 * a.kb_per_tap;
+        ok = ok && p_map_nhwc(&tmA, img, q->Nimg, Hin, Win, q->Cin, q->Cin, a.BW, a.BH, a.NB, a.stride);
+        ok = ok && p_map_nhwc(&tmO, q->out, q->Nimg, a.Ho, a.Wo, n_out, q->ldo, a.BW, a.BH, a.NB, 1);
+        if (q->residual) ok = ok && p_map_nhwc(&tmR, q->residual, q->Nimg, a.Ho, a.Wo, n_out, q->ldr, a.BW, a.BH, a.NB, 1);
+    } else {
+        a.tiles_m = cdiv(q->M, P_BM);
+        ok = ok && p_map_2d(&tmA, q->A, (uint64_t)q->K, (uint64_t)q->M, (uint64_t)q->lda, P_BK, P_BM);
+        ok = ok && p_map_2d(&tmO, q->out, (uint64_t)n_out, (uint64_t)q->M, (uint64_t)q->ldo, P_SUB, P_BM);
+        if (q->residual) ok = ok && p_map_2d(&tmR, q->residual, (uint64_t)n_out, (uint64_t)q->M, (uint64_t)q->ldr, P_SUB, P_BM);
+    }
+    if (!ok) {
+        set_error("tcgen05 gemm: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d conv=%d)", q->M, q->N, q->K, q->conv);
+        return ANYSD_ECUDA;
+    }
+    if (!q->residual) tmR = tmO;
+    a.num_tiles = a.tiles_m * a.tiles_n;
+    static bool done[64][2];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    const int ci = q->conv ? 1 : 0;
+    if (!done[dev][ci]) {
+        cudaError_t e = q->conv ? cudaFuncSetAttribute(gemm_tc5p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM)
+                                : cudaFuncSetAttribute(gemm_tc5p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+        if (e != cudaSuccess) {
+            set_error("tcgen05 gemm: smem opt-in failed: %s", cudaGetErrorString(e));
+            return ANYSD_ECUDA;
+        }
+        done[dev][ci] = true;
+    }
+    int grid = sm_count();
+    if (grid > a.num_tiles) grid = a.num_tiles;
+    if (q->conv)
+        gemm_tc5p_kernel<true><<<grid, P_THREADS, P_SMEM, st>>>(tmA, tmB, tmO, tmR, a);
+    else
+        gemm_tc5p_kernel<false><<<grid, P_THREADS, P_SMEM, st>>>(tmA, tmB, tmO, tmR, a);
+    return check_launch(q->conv ? "conv3x3 (tcgen05 persistent)" : "gemm (tcgen05 persistent)");
+}
+
+}  // namespace anysd
