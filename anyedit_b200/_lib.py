@@ -34,6 +34,7 @@ class AttnParams(C.Structure):
         ("ld_q", C.c_int), ("ld_k", C.c_int), ("ld_v", C.c_int), ("ld_o", C.c_int),
         ("B", C.c_int), ("heads", C.c_int), ("n_q", C.c_int), ("n_kv", C.c_int), ("d", C.c_int),
         ("scale", C.c_float), ("gate", C.c_void_p), ("gate_stride", C.c_int), ("accumulate", C.c_int),
+        ("head_stride", C.c_int),
     ]
 
 

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .unet import UNetModel, _Param
+from .unet import UNetModel, _Param, head_stride_for, pad_heads
 
 
 class _Adapter(nn.Module):
@@ -56,13 +56,14 @@ class MoE(nn.Module):
         d_emb = unet.time_embed_dim
         ctx_dim = unet.context_dim if isinstance(unet.context_dim, int) else unet.context_dim[0]
         self.task_embs = _TaskEmb(num_tasks, d_emb)
-        sites = []
+        sites, self._site_heads = [], []
         from .unet import _SpatialTransformer
         for blk in list(unet.input_blocks) + [unet.middle_block] + list(unet.output_blocks):
             for m in blk:
                 if isinstance(m, _SpatialTransformer):
                     for _tb in m.transformer_blocks:
                         sites.append(m.inner)
+                        self._site_heads.append((m.heads, m.d_head))
         self.adapter_modules = nn.ModuleList([_Adapter(c, ctx_dim, expert_num, d_emb) for c in sites])
         self.image_proj_model = nn.Identity()
         self._pack, self._pack_key = None, None
@@ -76,13 +77,17 @@ class MoE(nn.Module):
             return self._pack
         E = self.expert_num
         P = {"task": self.task_embs.weight.detach().to(dev, torch.float32).contiguous(), "layers": []}
-        for ad in self.adapter_modules:
+        for ad, (heads, dh) in zip(self.adapter_modules, self._site_heads):
             c = ad.to_k_ip.weight.shape[0] // E
+            hs = head_stride_for(dh)
+            cp = heads * hs                                   # padded-head projection width
             wk = ad.to_k_ip.weight.detach().reshape(E, c, -1)
             wv = ad.to_v_ip.weight.detach().reshape(E, c, -1)
-            # rows: expert-major, [K_e ; V_e] per expert -> one GEMM gives [.., e*2C : e*2C+C] = K_e
-            kv = torch.stack([wk, wv], 1).reshape(E * 2 * c, -1)
-            P["layers"].append({"c": c, "kv_w": kv.to(dev, torch.float16).contiguous()})
+            wk = torch.stack([pad_heads(wk[e], heads, dh, hs) for e in range(E)], 0)
+            wv = torch.stack([pad_heads(wv[e], heads, dh, hs) for e in range(E)], 0)
+            # rows: expert-major, [K_e ; V_e] per expert -> one GEMM gives [.., e*2Cp : e*2Cp+Cp] = K_e
+            kv = torch.stack([wk, wv], 1).reshape(E * 2 * cp, -1)
+            P["layers"].append({"c": c, "cp": cp, "kv_w": kv.to(dev, torch.float16).contiguous()})
         P["router_w"] = torch.stack([ad.router.weight.detach() for ad in self.adapter_modules], 0).to(
             dev, torch.float16).contiguous()                                   # [L, E, D]
         P["router_b"] = torch.stack([ad.router.bias.detach() for ad in self.adapter_modules], 0).to(
@@ -111,15 +116,16 @@ class MoE(nn.Module):
             gates = torch.empty(N, nl, E, dtype=torch.float32, device=dev)
             ops.router_gate(P["task"], edit_code, P["router_w"], P["router_b"], gates)   # all layers at once
 
-            def experts(layer, q, a, N_, n_q, heads, d):
+            def experts(layer, q, a, N_, n_q, heads, d, hs):
                 L = P["layers"][layer]
-                C = L["c"]
-                kv = torch.empty(N_ * n_vis, E * 2 * C, dtype=torch.float16, device=dev)
+                C, Cp = L["c"], L["cp"]
+                kv = torch.empty(N_ * n_vis, E * 2 * Cp, dtype=torch.float16, device=dev)
                 ops.gemm(v16.view(N_ * n_vis, -1), L["kv_w"], kv)
-                ld = E * 2 * C
+                ld = E * 2 * Cp
                 for e in range(E):
-                    ops.attention(q, kv[:, e * 2 * C:], kv[:, e * 2 * C + C:], a, N_, heads, n_q, n_vis, d,
-                                  C, ld, ld, C, gate=gates[:, layer, e:], gate_stride=nl * E, accumulate=True)
+                    ops.attention(q, kv[:, e * 2 * Cp:], kv[:, e * 2 * Cp + Cp:], a, N_, heads, n_q, n_vis, d,
+                                  Cp, ld, ld, C, gate=gates[:, layer, e:], gate_stride=nl * E, accumulate=True,
+                                  head_stride=hs)
 
             hook["experts"] = experts
         return self.unet(noisy_latents, timesteps, context=encoder_hidden_states, anysd=hook)

@@ -4,10 +4,15 @@
 // One CTA = 64 query rows of one (batch, head); 4 warps x 16 rows; KV tiles of 64.
 // Head dims 40 / 64 / 80 / 160 (any multiple of 8 up to 160 via the padded template sizes).
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
 namespace anysd {
+
+int launch_attention_tc5(const anysd_attn_params* q, cudaStream_t st);
+bool attention_tc5_supported(const anysd_attn_params* q);
 
 constexpr int ATT_BQ = 64, ATT_BKV = 64, ATT_THREADS = 128;
 
@@ -15,7 +20,7 @@ struct AttnArgs {
     const __half* q; const __half* k; const __half* v; __half* out;
     long long qbs, kbs, vbs, obs;
     int ldq, ldk, ldv, ldo;
-    int n_q, n_kv, d;
+    int n_q, n_kv, d, hs;
     float scale_log2;
     const float* gate;
     int gate_stride, accumulate;
@@ -40,9 +45,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_mma_kernel(const AttnAr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATT_BQ;
     const int dch = p.d / 8;                  // real chunks per row
-    const __half* qg = p.q + (size_t)b * p.qbs + (size_t)h * p.d;
-    const __half* kg = p.k + (size_t)b * p.kbs + (size_t)h * p.d;
-    const __half* vg = p.v + (size_t)b * p.vbs + (size_t)h * p.d;
+    const __half* qg = p.q + (size_t)b * p.qbs + (size_t)h * p.hs;
+    const __half* kg = p.k + (size_t)b * p.kbs + (size_t)h * p.hs;
+    const __half* vg = p.v + (size_t)b * p.vbs + (size_t)h * p.hs;
 
     auto load_tile = [&](const __half* g, int ld, int row0, int nrows, __half* s) {
         for (int i = tid; i < ATT_BKV * CH; i += ATT_THREADS) {
@@ -209,6 +214,7 @@ int launch_attention_mma(const anysd_attn_params* q, cudaStream_t st) {
     a.qbs = q->q_batch_stride; a.kbs = q->k_batch_stride; a.vbs = q->v_batch_stride; a.obs = q->o_batch_stride;
     a.ldq = q->ld_q; a.ldk = q->ld_k; a.ldv = q->ld_v; a.ldo = q->ld_o;
     a.n_q = q->n_q; a.n_kv = q->n_kv; a.d = q->d;
+    a.hs = q->head_stride > 0 ? q->head_stride : q->d;
     a.scale_log2 = q->scale * 1.4426950408889634f;
     a.gate = q->gate; a.gate_stride = q->gate_stride; a.accumulate = q->accumulate;
     const int dp = (q->d + 15) / 16 * 16;
@@ -245,5 +251,11 @@ extern "C" int anysd_attention_f16(const anysd_attn_params* p, anysd_stream_t st
                       ((uintptr_t)p->out % 4) == 0,
                   ANYSD_EINVAL, "attention: q/k/v must be 16-byte aligned");
     ANYSD_REQUIRE(p->heads <= 65535 && p->B <= 65535, ANYSD_EINVAL, "attention: grid too large");
+    ANYSD_REQUIRE(p->head_stride == 0 || (p->head_stride >= p->d && p->head_stride % 8 == 0), ANYSD_EINVAL,
+                  "attention: head_stride must be 0 or a multiple of 8 >= d");
+    // tcgen05 kernel whenever its layout constraints hold; ANYSD_ATTN=mma|tc5 is a test/debug switch.
+    static const char* force = getenv("ANYSD_ATTN");
+    const bool want_tc5 = !force || !strcmp(force, "tc5");
+    if (want_tc5 && attention_tc5_supported(p)) return launch_attention_tc5(p, (cudaStream_t)stream);
     return launch_attention_mma(p, (cudaStream_t)stream);
 }

@@ -1,0 +1,420 @@
+// Blackwell-native attention: S = Q K^T and O += P V on tcgen05 (accumulators in TMEM), operands staged by
+// TMA, softmax in fp32 registers with ONE thread per query row (no shuffles), lazy accumulator rescale.
+// Replaces the n x n score tensor of the reference's eager CrossAttention (ldm/modules/attention.py:171-193).
+//
+//   CTA = 128 query rows of one (batch, head).  192 threads: warp 0 TMA producer, warp 1 MMA issuer,
+//   warps 2..5 softmax/correction/epilogue (TMEM lane group = warp % 4, lane = row).
+//   TMEM: S [128 x 128] fp32 at columns 0..127, O [128 x d_ext] fp32 at columns 128...
+//   smem: Q (NA atoms of 128 x 64 fp16, 128B swizzle), 2-stage ring of (K, V) tiles, P [128 x 128] fp16.
+//   Pipeline per kv tile j:   MMA: S(j+1) = Q K(j+1)^T is issued as soon as the softmax warps have pulled
+//   S(j) into registers, so the tensor pipe works under the exp; then O += P(j) V(j).
+//   Softmax: p = exp2(s*scale*log2e - m) with m only raised when the tile max exceeds it by > 8 (p <= 256,
+//   safe in fp16; any reference max gives the same O / l), so the TMEM read-modify-write rescale of O is rare.
+//   d = 40 needs the head stride padded to >= 48 with zero columns (anyedit_b200.unet packs q/k/v that way);
+//   K-extent = ceil16(d), V is consumed as an MN-major B operand straight from its row-major tile.
+#include <cuda.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace anysd {
+
+constexpr int AT_BQ = 128, AT_BKV = 128, AT_THREADS = 192, AT_ATOM = 128 * 128;   // 16 KB atom: 128 rows x 64 halves
+
+struct AtArgs {
+    __half* out;
+    long long obs;
+    int ldo;
+    int n_q, n_kv, d, d_ext, hs;       // hs = head stride (elements) inside q/k/v rows
+    int NA, stages, tmem_cols;
+    float scale_log2;
+    const float* gate;
+    int gate_stride, accumulate;
+};
+
+__device__ __forceinline__ void am_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void am_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void am_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void am_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void a_tma_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void a_umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void a_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void a_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void a_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void a_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void a_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void a_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void a_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void a_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ float a_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// K-major SW128 operand (rows 128 B apart inside an atom, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t a_desc_k(uint32_t addr) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// MN-major SW128 operand: 64-element MN blocks `lbo_bytes` apart, 8-row K groups 1024 B apart
+__device__ __forceinline__ uint64_t a_desc_mn(uint32_t addr, uint32_t lbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (64ull << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AtArgs p) {
+    // 128B-swizzled tiles need a 1024-byte aligned base; the dynamic smem window of a kernel without static
+    // smem starts 1024-aligned (declared so below; checked, not padded: padding would cost the 2nd CTA per SM).
+    extern __shared__ __align__(1024) unsigned char at_smem_raw[];
+    const uint32_t base = smem_u32(at_smem_raw);
+    if (base & 1023u) __trap();
+    unsigned char* smem = at_smem_raw;
+    const int NA = p.NA, ST = p.stages;
+    const uint32_t q_off = 0;
+    const uint32_t kv_off = NA * AT_ATOM;                       // stage s: K at kv_off + s*2*NA*ATOM, V right after K
+    const uint32_t p_off = kv_off + ST * 2 * NA * AT_ATOM;      // P: 2 atoms
+    const uint32_t bar_off = p_off + 2 * AT_ATOM;
+    const uint32_t bars = base + bar_off;
+    // barriers: 0 q_full | 1,2 kv_full | 3,4 kv_empty | 5 s_full | 6 s_free | 7 p_full | 8 o_done
+    auto BAR = [&](int i) { return bars + 8u * i; };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AT_BQ;
+    const int nt = (p.n_kv + AT_BKV - 1) / AT_BKV;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        am_init(BAR(0), 1);
+        am_init(BAR(1), 1); am_init(BAR(2), 1);
+        am_init(BAR(3), 1); am_init(BAR(4), 1);
+        am_init(BAR(5), 1);
+        am_init(BAR(6), 4);      // one arrive per softmax warp
+        am_init(BAR(7), 4);
+        am_init(BAR(8), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    a_fence_before();
+    __syncthreads();
+    a_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            const int col0 = h * p.hs;
+            am_expect_tx(BAR(0), NA * AT_ATOM);
+            for (int a = 0; a < NA; ++a) a_tma_2d(base + q_off + a * AT_ATOM, &tmQ, BAR(0), col0 + a * 64, b * p.n_q + q0);
+            for (int j = 0; j < nt; ++j) {
+                const int s = j % ST;
+                am_wait(BAR(3 + s), (((uint32_t)j / ST) & 1) ^ 1);
+                am_expect_tx(BAR(1 + s), 2 * NA * AT_ATOM);
+                const uint32_t kb = base + kv_off + s * 2 * NA * AT_ATOM, vb = kb + NA * AT_ATOM;
+                for (int a = 0; a < NA; ++a) a_tma_2d(kb + a * AT_ATOM, &tmK, BAR(1 + s), col0 + a * 64, b * p.n_kv + j * AT_BKV);
+                for (int a = 0; a < NA; ++a) a_tma_2d(vb + a * AT_ATOM, &tmV, BAR(1 + s), col0 + a * 64, b * p.n_kv + j * AT_BKV);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc_s = (1u << 4) | ((uint32_t)(AT_BKV >> 3) << 17) | ((uint32_t)(AT_BQ >> 4) << 24);
+            const uint32_t idesc_o = (1u << 4) | (1u << 16) /*B is MN-major*/ | ((uint32_t)(p.d_ext >> 3) << 17) |
+                                     ((uint32_t)(AT_BQ >> 4) << 24);
+            const int ksteps = p.d_ext / 16;
+            auto issue_S = [&](int j) {
+                const uint32_t kb = base + kv_off + (j % ST) * 2 * NA * AT_ATOM;
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint32_t off = (k >> 2) * AT_ATOM + (k & 3) * 32;
+                    a_umma(tmem_S, a_desc_k(base + q_off + off), a_desc_k(kb + off), idesc_s, k ? 1u : 0u);
+                }
+                a_commit(BAR(5));
+            };
+            am_wait(BAR(0), 0);
+            am_wait(BAR(1), 0);
+            a_fence_after();
+            issue_S(0);
+            for (int j = 0; j < nt; ++j) {
+                if (j + 1 < nt && ST > 1) {                               // run S(j+1) under the softmax of tile j
+                    const int s1 = (j + 1) % ST;
+                    am_wait(BAR(1 + s1), ((uint32_t)(j + 1) / ST) & 1);   // K(j+1), V(j+1) landed
+                    am_wait(BAR(6), j & 1);                               // S(j) is in registers
+                    a_fence_after();
+                    issue_S(j + 1);
+                }
+                am_wait(BAR(7), j & 1);                                   // P(j) written (and O rescaled)
+                a_fence_after();
+                const uint32_t vb = base + kv_off + (j % ST) * 2 * NA * AT_ATOM + NA * AT_ATOM;
+                for (int k = 0; k < AT_BKV / 16; ++k) {
+                    const uint32_t poff = (k >> 2) * AT_ATOM + (k & 3) * 32;
+                    a_umma(tmem_O, a_desc_k(base + p_off + poff), a_desc_mn(vb + k * 2048, AT_ATOM), idesc_o, (j | k) ? 1u : 0u);
+                }
+                a_commit(BAR(8));                 // O(j) accumulated, P free
+                a_commit(BAR(3 + (j % ST)));      // K/V stage free
+                if (j + 1 < nt && ST == 1) {      // single K/V stage (d = 160): the next tile can only land now
+                    am_wait(BAR(1), (uint32_t)(j + 1) & 1);
+                    am_wait(BAR(6), j & 1);
+                    a_fence_after();
+                    issue_S(j + 1);
+                }
+            }
+        }
+    } else {
+        // ===== softmax / correction / epilogue: 4 warps, one thread per query row =====
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
+        float m_run = -INFINITY, l_run = 0.f;
+        unsigned char* prow = smem + p_off + row * 128;
+        for (int j = 0; j < nt; ++j) {
+            am_wait(BAR(5), j & 1);
+            a_fence_after();
+            uint32_t sr[128];
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) a_ld32(tmem_S + lane_addr + c * 32, sr + c * 32);
+            a_wait_ld();
+            a_fence_before();
+            __syncwarp();
+            if (lane == 0) am_arrive(BAR(6));                 // S(j) consumed: the MMA warp may overwrite it
+            const int kv_left = p.n_kv - j * AT_BKV;
+            float mx = -INFINITY;
+            if (kv_left >= AT_BKV) {
+#pragma unroll
+                for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 128; ++i) {
+                    float v = (i < kv_left) ? __uint_as_float(sr[i]) : -INFINITY;
+                    sr[i] = __float_as_uint(v);
+                    mx = fmaxf(mx, v);
+                }
+            }
+            mx *= p.scale_log2;
+            // lazy max: only move the reference when the tile max exceeds it by more than 8 (2^8 headroom)
+            const bool upd = mx > m_run + 8.0f;
+            const float m_new = upd ? mx : m_run;
+            const float corr = upd ? a_ex2(m_run - m_new) : 1.0f;    // first tile: ex2(-inf) = 0
+            m_run = m_new;
+            float sum = 0.f;
+            uint32_t pk[64];
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                const float p0 = a_ex2(fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, -m_new));
+                const float p1 = a_ex2(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, -m_new));
+                sum += p0 + p1;
+                __half2 hh = __floats2half2_rn(p0, p1);
+                pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+            l_run = l_run * corr + sum;
+            // P smem and the O accumulator are free once PV(j-1) has retired
+            if (j > 0) {
+                am_wait(BAR(8), (j - 1) & 1);
+                a_fence_after();
+            }
+            const bool need = __any_sync(0xffffffffu, upd) && j > 0;
+            if (need) {
+                for (int c = 0; c < p.d_ext; c += 16) {
+                    uint32_t o[16];
+                    a_ld16(tmem_O + lane_addr + c, o);
+                    a_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+                    a_st16(tmem_O + lane_addr + c, o);
+                }
+                a_wait_st();
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {                    // 16 chunks of 8 halves; chunk c lives in atom c/8
+                uint4 u = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                *reinterpret_cast<uint4*>(prow + (c >> 3) * AT_ATOM + (((c & 7) ^ (row & 7)) << 4)) = u;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            a_fence_before();
+            __syncwarp();
+            if (lane == 0) am_arrive(BAR(7));
+        }
+        // ---- epilogue: O / l -> fp16 -> global ----
+        am_wait(BAR(8), (nt - 1) & 1);
+        a_fence_after();
+        const float g = p.gate ? p.gate[(size_t)b * p.gate_stride] : 1.0f;
+        const float inv = g / l_run;
+        const int qr = q0 + row;
+        __half* orow = p.out + (size_t)b * p.obs + (size_t)qr * p.ldo + (size_t)h * p.d;
+        for (int c = 0; c < p.d_ext; c += 16) {
+            uint32_t o[16];
+            __syncwarp();
+            a_ld16(tmem_O + lane_addr + c, o);
+            a_wait_ld();
+            if (qr < p.n_q) {
+#pragma unroll
+                for (int g8 = 0; g8 < 2; ++g8) {
+                    const int col = c + g8 * 8;
+                    if (col >= p.d) break;
+                    float f[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[g8 * 8 + i]) * inv;
+                    uint4* dst = reinterpret_cast<uint4*>(orow + col);
+                    if (p.accumulate) {
+                        float prev[8];
+                        unpack8(*dst, prev);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] += prev[i];
+                    }
+                    *dst = pack8(f);
+                }
+            }
+        }
+    }
+    a_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFnA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFnA a_get_encode() {
+    static EncodeTiledFnA fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFnA)f;
+    }
+    return fn;
+}
+static bool a_map(CUtensorMap* tm, const void* ptr, uint64_t width, uint64_t rows, uint64_t ld) {
+    cuuint64_t dims[2] = {width, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t es[2] = {1, 1};
+    return a_get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool attention_tc5_supported(const anysd_attn_params* q) {
+    const int hs = q->head_stride > 0 ? q->head_stride : q->d;
+    const int d_ext = (q->d + 15) / 16 * 16;
+    if (d_ext > hs && q->heads > 1) return false;              // K-extent would reach into the next head's columns
+    if (q->d % 8 != 0 || d_ext > 160) return false;
+    if (q->ld_q % 8 || q->ld_k % 8 || q->ld_v % 8 || q->ld_o % 8) return false;
+    if (((uintptr_t)q->q % 16) || ((uintptr_t)q->k % 16) || ((uintptr_t)q->v % 16) || ((uintptr_t)q->out % 16)) return false;
+    // batches must be stacked rows of one matrix (what the UNet produces): batch stride = n * ld
+    if (q->q_batch_stride != (long long)q->n_q * q->ld_q || q->k_batch_stride != (long long)q->n_kv * q->ld_k ||
+        q->v_batch_stride != (long long)q->n_kv * q->ld_v)
+        return false;
+    if ((q->o_batch_stride % 8) != 0) return false;
+    return a_get_encode() != nullptr;
+}
+
+int launch_attention_tc5(const anysd_attn_params* q, cudaStream_t st) {
+    AtArgs a;
+    const int hs = q->head_stride > 0 ? q->head_stride : q->d;
+    a.out = (__half*)q->out;
+    a.obs = q->o_batch_stride;
+    a.ldo = q->ld_o;
+    a.n_q = q->n_q; a.n_kv = q->n_kv; a.d = q->d; a.hs = hs;
+    a.d_ext = (q->d + 15) / 16 * 16;
+    a.NA = (a.d_ext + 63) / 64;
+    a.stages = a.NA <= 2 ? 2 : 1;
+    a.tmem_cols = (128 + a.d_ext) <= 256 ? 256 : 512;
+    a.scale_log2 = q->scale * 1.4426950408889634f;
+    a.gate = q->gate; a.gate_stride = q->gate_stride; a.accumulate = q->accumulate;
+    CUtensorMap tmQ, tmK, tmV;
+    const uint64_t width = (uint64_t)(q->heads - 1) * hs + q->d;     // valid columns from the slice pointer
+    bool ok = a_map(&tmQ, q->q, width, (uint64_t)q->B * q->n_q, q->ld_q) &&
+              a_map(&tmK, q->k, width, (uint64_t)q->B * q->n_kv, q->ld_k) &&
+              a_map(&tmV, q->v, width, (uint64_t)q->B * q->n_kv, q->ld_v);
+    if (!ok) {
+        set_error("attention (tcgen05): cuTensorMapEncodeTiled failed (B=%d n_q=%d n_kv=%d d=%d)", q->B, q->n_q, q->n_kv, q->d);
+        return ANYSD_ECUDA;
+    }
+    const int smem = (a.NA + a.stages * 2 * a.NA + 2) * AT_ATOM + 128;
+    static int attr_set[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (attr_set[dev] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_error("attention (tcgen05): smem opt-in failed: %s", cudaGetErrorString(e));
+            return ANYSD_ECUDA;
+        }
+        attr_set[dev] = smem;
+    }
+    dim3 grid(cdiv(q->n_q, AT_BQ), q->heads, q->B);
+    attention_tc5_kernel<<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a);
+    return check_launch("attention (tcgen05)");
+}
+
+}  // namespace anysd

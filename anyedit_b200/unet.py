@@ -159,6 +159,22 @@ def _f(t, dev):
     return t.detach().to(device=dev, dtype=torch.float32).contiguous()
 
 
+def head_stride_for(d):
+    """Head stride of packed q/k/v projections: d, or ceil16(d) when d is not a multiple of 16 -- the tcgen05
+    attention kernel contracts over ceil16(d) columns and needs the extra ones to be exact zeros (d = 40 -> 48)."""
+    return d if d % 16 == 0 else (d + 15) // 16 * 16
+
+
+def pad_heads(w, heads, d, hs):
+    """[heads*d, K] projection weight -> [heads*hs, K] with (hs - d) zero rows appended to every head."""
+    if hs == d:
+        return w
+    k = w.shape[1]
+    out = w.new_zeros(heads, hs, k)
+    out[:, :d] = w.reshape(heads, d, k)
+    return out.reshape(heads * hs, k)
+
+
 def _pack_conv3(w, dev, cin_pad=None):
     """OIHW -> [Cout, 9*Cin_pad] fp16 with K order (ky, kx, ci)."""
     co, ci = w.shape[0], w.shape[1]
@@ -337,12 +353,14 @@ class UNetModel(nn.Module):
             return d
 
         def pack_attn(at, self_attn):
-            d = {"heads": at.heads, "d": at.dim_head}
+            hs = head_stride_for(at.dim_head)
+            d = {"heads": at.heads, "d": at.dim_head, "hs": hs}
+            ph = lambda w: pad_heads(w.detach(), at.heads, at.dim_head, hs)
             if self_attn:
-                d["qkv_w"] = _h(torch.cat([at.to_q.weight, at.to_k.weight, at.to_v.weight], 0), dev)
+                d["qkv_w"] = _h(torch.cat([ph(at.to_q.weight), ph(at.to_k.weight), ph(at.to_v.weight)], 0), dev)
             else:
-                d["q_w"] = _h(at.to_q.weight, dev)
-                d["kv_w"] = _h(torch.cat([at.to_k.weight, at.to_v.weight], 0), dev)
+                d["q_w"] = _h(ph(at.to_q.weight), dev)
+                d["kv_w"] = _h(torch.cat([ph(at.to_k.weight), ph(at.to_v.weight)], 0), dev)
             d["o_w"], d["o_b"] = _h(at.to_out[0].weight, dev), _f(at.to_out[0].bias, dev)
             return d
 
@@ -527,22 +545,24 @@ class UNetModel(nn.Module):
     def _attn(self, ad, xq, ctx, N, n_q, st, self_attn, residual, out, expert=False):
         """CrossAttention.forward (attention.py:163-194) + residual add of the caller (:272-273)."""
         C = ad["heads"] * ad["d"]
+        hs = ad["hs"]
+        Cp = ad["heads"] * hs                     # projection width with padded heads (== C unless d % 16 != 0)
         dev = xq.device
         a = torch.empty(N * n_q, C, dtype=torch.float16, device=dev)
         if self_attn:
-            qkv = torch.empty(N * n_q, 3 * C, dtype=torch.float16, device=dev)
+            qkv = torch.empty(N * n_q, 3 * Cp, dtype=torch.float16, device=dev)
             ops.gemm(xq, ad["qkv_w"], qkv)
-            ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], a, N, ad["heads"], n_q, n_q, ad["d"],
-                          3 * C, 3 * C, 3 * C, C)
+            ops.attention(qkv, qkv[:, Cp:], qkv[:, 2 * Cp:], a, N, ad["heads"], n_q, n_q, ad["d"],
+                          3 * Cp, 3 * Cp, 3 * Cp, C, head_stride=hs)
         else:
             L = ctx.shape[1]
-            q = torch.empty(N * n_q, C, dtype=torch.float16, device=dev)
+            q = torch.empty(N * n_q, Cp, dtype=torch.float16, device=dev)
             ops.gemm(xq, ad["q_w"], q)
-            kv = torch.empty(N * L, 2 * C, dtype=torch.float16, device=dev)
+            kv = torch.empty(N * L, 2 * Cp, dtype=torch.float16, device=dev)
             ops.gemm(ctx.view(N * L, -1), ad["kv_w"], kv)
-            ops.attention(q, kv, kv[:, C:], a, N, ad["heads"], n_q, L, ad["d"], C, 2 * C, 2 * C, C)
+            ops.attention(q, kv, kv[:, Cp:], a, N, ad["heads"], n_q, L, ad["d"], Cp, 2 * Cp, 2 * Cp, C, head_stride=hs)
             if expert and st["anysd"] is not None and st["anysd"].get("experts") is not None:
-                st["anysd"]["experts"](st["layer"], q, a, N, n_q, ad["heads"], ad["d"])
+                st["anysd"]["experts"](st["layer"], q, a, N, n_q, ad["heads"], ad["d"], hs)
             if expert:
                 st["layer"] += 1
         ops.gemm(a, ad["o_w"], out, bias=ad["o_b"], residual=residual)

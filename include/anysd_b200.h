@@ -128,6 +128,8 @@ typedef struct {
     const float* gate;      /* [B] stride gate_stride, or NULL */
     int gate_stride;
     int accumulate;
+    int head_stride;        /* elements between consecutive heads inside a q/k/v row; 0 = d.  The tcgen05 kernel
+                               needs head_stride >= ceil16(d) with zero padding columns when d % 16 != 0 */
 } anysd_attn_params;
 int anysd_attention_f16(const anysd_attn_params* p, anysd_stream_t stream);
 

@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Diagnostic (not a pytest file): attention kernel timing on the UNet's shapes. ANYSD_ATTN=mma|tc5 selects the kernel."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
+from anyedit_b200 import ops  # noqa: E402
+from anyedit_b200.unet import head_stride_for  # noqa: E402
+
+
+def run(B, heads, n, nkv, d, check=True):
+    hs = head_stride_for(d)
+    C, Cp = heads * d, heads * hs
+    g = torch.Generator(device="cuda").manual_seed(0)
+    def mk(rows):
+        t = torch.zeros(B, rows, heads, hs, dtype=torch.float16, device="cuda")
+        t[..., :d] = torch.randn(B, rows, heads, d, device="cuda", generator=g).half()
+        return t.reshape(B, rows, Cp)
+    q, k, v = mk(n), mk(nkv), mk(nkv)
+    out = torch.empty(B, n, C, dtype=torch.float16, device="cuda")
+    fn = lambda: ops.attention(q, k, v, out, B, heads, n, nkv, d, Cp, Cp, Cp, C, head_stride=hs)
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 5 * 1e-3
+    err = float("nan")
+    if check:
+        qq = q.view(B, n, heads, hs)[..., :d].permute(0, 2, 1, 3).float()
+        kk = k.view(B, nkv, heads, hs)[..., :d].permute(0, 2, 1, 3).float()
+        vv = v.view(B, nkv, heads, hs)[..., :d].permute(0, 2, 1, 3).float()
+        ref = torch.nn.functional.scaled_dot_product_attention(qq[:1], kk[:1], vv[:1])
+        ref = ref.permute(0, 2, 1, 3).reshape(1, n, C)
+        err = float((out[:1].float() - ref).norm() / ref.norm())
+    fl = 4.0 * B * heads * n * nkv * d
+    print(f"attn B={B} h={heads} n={n} kv={nkv} d={d}: {t * 1e6:9.1f} us {fl / t / 1e12:7.1f} TFLOP/s rel={err:.2e}", flush=True)
+
+
+if __name__ == "__main__":
+    print("ANYSD_ATTN =", os.environ.get("ANYSD_ATTN"))
+    for c in ((1, 2, 128, 128, 64), (1, 2, 256, 256, 40), (2, 8, 300, 77, 40), (1, 8, 256, 256, 80), (1, 8, 256, 256, 160)):
+        run(*c)
+    if "--quick" not in sys.argv:
+        for c in ((16, 8, 4096, 4096, 40), (16, 8, 1024, 1024, 80), (16, 8, 256, 256, 160), (16, 8, 4096, 77, 40)):
+            run(*c)

@@ -303,3 +303,31 @@ def test_errors_are_loud(ops):
         ops.gemm(torch.empty(4, 12, dtype=torch.float16, device="cuda"), torch.empty(4, 12, dtype=torch.float16, device="cuda"), out)
     with pytest.raises(Exception):
         ops.gemm(torch.empty(4, 8, dtype=torch.float16), torch.empty(4, 8, dtype=torch.float16), out)  # CPU tensors
+
+
+@pytest.mark.parametrize("B,heads,nq,nkv,d", [(1, 8, 256, 256, 40), (2, 8, 300, 300, 40), (2, 8, 100, 77, 40),
+                                              (1, 8, 1024, 1024, 40), (1, 3, 130, 513, 24)])
+def test_attention_padded_heads(ops, B, heads, nq, nkv, d):
+    """Head stride padded to ceil16(d) with zero columns (the layout anyedit_b200.unet packs when d % 16 != 0,
+    required by the tcgen05 kernel): same result as the unpadded reference."""
+    from anyedit_b200.unet import head_stride_for
+    from oracle import unet_oracle
+    hs = head_stride_for(d)
+    C, Cp = heads * d, heads * hs
+    q, k, v = randn(91, B, nq, C), randn(92, B, nkv, C), randn(93, B, nkv, C)
+    q16, k16, v16 = q.half(), k.half(), v.half()
+
+    def split(t):
+        return t.float().reshape(B, t.shape[1], heads, d).permute(0, 2, 1, 3).reshape(B * heads, t.shape[1], d)
+
+    def pad(t):
+        o = torch.zeros(B, t.shape[1], heads, hs, dtype=torch.float16)
+        o[..., :d] = t.reshape(B, t.shape[1], heads, d)
+        return o.reshape(B, t.shape[1], Cp).cuda().contiguous()
+
+    ref = unet_oracle.attention_bhnd(split(q16), split(k16), split(v16))
+    ref = ref.reshape(B, heads, nq, d).permute(0, 2, 1, 3).reshape(B, nq, C)
+    out = torch.empty(B, nq, C, dtype=torch.float16, device="cuda")
+    ops.attention(pad(q16), pad(k16), pad(v16), out, B, heads, nq, nkv, d, Cp, Cp, Cp, C, head_stride=hs)
+    e = rel(out, ref)
+    assert e < 2e-3, e
