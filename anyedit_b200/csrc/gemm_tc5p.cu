@@ -17,7 +17,7 @@
 namespace anysd {
 
 constexpr int P_BM = 128, P_BK = 64, P_BN = 256, P_STAGES = 3, P_NSTG = 4, P_SUB = 64;
-constexpr int P_THREADS = 256;                       // warps 0..3: TMA, MMA, TMEM-alloc, spare; warps 4..7: epilogue
+constexpr int P_THREADS = 384;                       // warps 0..3: TMA, MMA, TMEM-alloc, spare; warps 4..11: epilogue
 constexpr int P_A_BYTES = P_BM * P_BK * 2;           // 16 KB
 constexpr int P_B_BYTES = P_BN * P_BK * 2;           // 32 KB
 constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES; // 48 KB
@@ -108,7 +108,7 @@ __device__ __forceinline__ void p_tmem_ld32(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void p_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void p_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void p_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void p_epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void p_epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ uint64_t p_sdesc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -184,7 +184,7 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int b = 0; b < 2; ++b) {
             pm_init(tfull_bar(b), 1);
-            pm_init(tempty_bar(b), 4);       // one arrive per epilogue warp
+            pm_init(tempty_bar(b), 8);       // one arrive per epilogue warp
         }
         for (int b = 0; b < P_NSTG; ++b) pm_init(res_bar(b), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -250,8 +250,10 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: 4 warps, TMEM lane group = warp % 4, thread = one accumulator row =====
+        // ===== epilogue: 8 warps.  TMEM lane group = warp % 4 (hardware rule), thread = one accumulator row;
+        // warps 4..7 take output columns 0..31 of every 64-column sub-tile, warps 8..11 columns 32..63 =====
         const int lg = warp & 3;
+        const int half = (warp - 4) >> 2;
         const int row = lg * 32 + lane;
         const bool elected = (warp == 4 && lane == 0);
         uint32_t t = 0, q = 0;                                // tile counter, global sub-tile counter
@@ -298,8 +300,7 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 p_epi_bar();                                   // staging buffer b is free for everyone
                 unsigned char* stg = smem + P_STAGES * P_STAGE_BYTES + b * P_STG_BYTES + row * 128;
                 if (p.has_res) pm_wait(res_bar(b), ((q + j) / P_NSTG) & 1);
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {         // 2 x 32 output columns
+                {
                     float v[32];
                     const int oc = half * 32;                  // output column offset inside the sub-tile
                     if (p.act == 2) {
@@ -311,17 +312,25 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         p_tmem_ld32(tmem_base + buf * P_BN + ((uint32_t)(lg * 32) << 16) + ac + 32, r1);
                         p_tmem_wait_ld();
                         const int nb = c.n0 + ac;
+                        if (p.bias) {                           // N % 128 == 0 for GEGLU: the 64 columns are in range
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + i);
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 32) + i);
+                                r0[4 * i] = __float_as_uint(__uint_as_float(r0[4 * i]) + b0.x);
+                                r0[4 * i + 1] = __float_as_uint(__uint_as_float(r0[4 * i + 1]) + b0.y);
+                                r0[4 * i + 2] = __float_as_uint(__uint_as_float(r0[4 * i + 2]) + b0.z);
+                                r0[4 * i + 3] = __float_as_uint(__uint_as_float(r0[4 * i + 3]) + b0.w);
+                                r1[4 * i] = __float_as_uint(__uint_as_float(r1[4 * i]) + b1.x);
+                                r1[4 * i + 1] = __float_as_uint(__uint_as_float(r1[4 * i + 1]) + b1.y);
+                                r1[4 * i + 2] = __float_as_uint(__uint_as_float(r1[4 * i + 2]) + b1.z);
+                                r1[4 * i + 3] = __float_as_uint(__uint_as_float(r1[4 * i + 3]) + b1.w);
+                            }
+                        }
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            float a0 = __uint_as_float(r0[2 * i]), g0 = __uint_as_float(r0[2 * i + 1]);
-                            float a1 = __uint_as_float(r1[2 * i]), g1 = __uint_as_float(r1[2 * i + 1]);
-                            if (p.bias) {
-                                const int n_a = nb + 2 * i, n_b = nb + 32 + 2 * i;
-                                if (n_a + 1 < p.N) { a0 += __ldg(p.bias + n_a); g0 += __ldg(p.bias + n_a + 1); }
-                                if (n_b + 1 < p.N) { a1 += __ldg(p.bias + n_b); g1 += __ldg(p.bias + n_b + 1); }
-                            }
-                            v[i] = a0 * p_gelu(g0);
-                            v[16 + i] = a1 * p_gelu(g1);
+                            v[i] = __uint_as_float(r0[2 * i]) * p_gelu(__uint_as_float(r0[2 * i + 1]));
+                            v[16 + i] = __uint_as_float(r1[2 * i]) * p_gelu(__uint_as_float(r1[2 * i + 1]));
                         }
                     } else {
                         uint32_t r[32];

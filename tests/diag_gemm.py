@@ -96,6 +96,11 @@ def main():
                     (B * 1024, 640, 640), (B * 1024, 5120, 640), (B * 256, 1280, 1280), (B * 256, 10240, 1280),
                     (B * 256, 1280, 5120), (B * 64, 1280, 1280), (B * 77, 640, 768), (B, 20160, 1280)):
         gemm_case(M, N, K, check=False)
+    gemm_case(B * 4096, 2560, 320, check=False, act=2)
+    gemm_case(B * 1024, 5120, 640, check=False, act=2)
+    gemm_case(B * 256, 10240, 1280, check=False, act=2)
+    gemm_case(B * 4096, 320, 1280, check=False, res=True)
+    gemm_case(B * 4096, 320, 320, check=False, res=True)
     for c in ((B, 320, 320, 64, 64), (B, 640, 320, 64, 64), (B, 960, 320, 64, 64), (B, 640, 640, 32, 32), (B, 1280, 640, 32, 32),
               (B, 1920, 640, 32, 32), (B, 1280, 1280, 16, 16), (B, 2560, 1280, 16, 16), (B, 1280, 1280, 8, 8), (B, 2560, 1280, 8, 8)):
         conv_case(*c, check=False)
