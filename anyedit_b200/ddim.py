@@ -68,6 +68,22 @@ class DDIMSampler(object):
         self.use_cuda_graph = kwargs.get("use_cuda_graph", True)
         self._graphs = {}
 
+    def _get_stepper(self, cond, uncond, use_cfg, b, shape, device, graph):
+        """One stepper (static buffers + captured CUDA graph) per request geometry, reused across ``sample``
+        calls: a serving loop captures once and only rebinds conditioning values afterwards."""
+        gk = getattr(self.model, "graph_key", None)      # changes whenever the model's packed weights change
+        key = (b, tuple(shape), bool(use_cfg), bool(graph), str(device), _tree_sig(cond),
+               _tree_sig(uncond) if use_cfg else None, gk() if callable(gk) else gk)
+        st = self._graphs.get(key)
+        if st is None:
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            st = _Stepper(self, cond, uncond, use_cfg, b, shape, device, graph)
+            self._graphs[key] = st
+        else:
+            st.rebind(cond, uncond)
+        return st
+
     def register_buffer(self, name, attr):
         # the reference forces every buffer to "cuda" (ddim.py:17-21); follow the model instead
         if isinstance(attr, torch.Tensor) and attr.device != self.model.device:
@@ -167,8 +183,8 @@ class DDIMSampler(object):
         use_cfg = not (unconditional_conditioning is None or unconditional_guidance_scale == 1.)
         sigma_nonzero = bool(np.any(np.asarray(self.ddim_sigmas[:total_steps]) != 0))
 
-        stepper = _Stepper(self, cond, unconditional_conditioning, use_cfg, b, shape, device,
-                           graph=self.use_cuda_graph and ucg_schedule is None)
+        stepper = self._get_stepper(cond, unconditional_conditioning, use_cfg, b, tuple(shape), device,
+                                    graph=self.use_cuda_graph and ucg_schedule is None)
         for i, step in enumerate(time_range):
             index = total_steps - i - 1
             if mask is not None:
@@ -261,6 +277,35 @@ def _cat_cond(uc, c):
     return torch.cat([uc, c])
 
 
+def _tree_sig(c):
+    if isinstance(c, dict):
+        return tuple((k, _tree_sig(c[k])) for k in sorted(c))
+    if isinstance(c, (list, tuple)):
+        return tuple(_tree_sig(v) for v in c)
+    if isinstance(c, torch.Tensor):
+        return (tuple(c.shape), str(c.dtype), str(c.device))
+    return repr(c)
+
+
+def _tree_clone(c):
+    if isinstance(c, dict):
+        return {k: _tree_clone(v) for k, v in c.items()}
+    if isinstance(c, (list, tuple)):
+        return [_tree_clone(v) for v in c]
+    return c.clone() if isinstance(c, torch.Tensor) else c
+
+
+def _tree_copy_(dst, src):
+    if isinstance(dst, dict):
+        for k in dst:
+            _tree_copy_(dst[k], src[k])
+    elif isinstance(dst, (list, tuple)):
+        for d, s_ in zip(dst, src):
+            _tree_copy_(d, s_)
+    elif isinstance(dst, torch.Tensor):
+        dst.copy_(src)
+
+
 class _Stepper:
     """Runs one DDIM step: model call on the (CFG-doubled) batch + fused update.  The conditioning
     batch is assembled once per ``sample`` call (it does not change across steps).  With
@@ -272,7 +317,9 @@ class _Stepper:
         self.use_cfg = use_cfg
         self.b = b
         self.device = device
-        self.c_in = _cat_cond(uncond, cond) if use_cfg else cond
+        # static copy of the (CFG-batched) conditioning: a cached stepper / captured graph is re-bound to new
+        # requests by copying values into these tensors (rebind), never by re-capturing
+        self.c_in = _tree_clone(_cat_cond(uncond, cond) if use_cfg else cond)
         nb = 2 * b if use_cfg else b
         self.t_buf = torch.zeros(nb, dtype=torch.long, device=device)
         self.coef_buf = torch.zeros(5, dtype=torch.float32, device=device)
@@ -285,6 +332,9 @@ class _Stepper:
         self.want_graph = bool(graph) and device.type == "cuda" and getattr(sampler.model, "graph_safe", False)
         self.scale = None
         self.n_eager = 0
+
+    def rebind(self, cond, uncond):
+        _tree_copy_(self.c_in, _cat_cond(uncond, cond) if self.use_cfg else cond)
 
     def _body(self, scale, noise):
         if self.use_cfg:

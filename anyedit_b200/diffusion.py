@@ -109,6 +109,11 @@ class LatentDenoiser(nn.Module):
         m = self.model.diffusion_model
         return isinstance(m, UNetModel) or getattr(m, "graph_safe", False)
 
+    def graph_key(self):
+        """Identity of the packed weights a captured CUDA graph would point at (parameter versions + device)."""
+        m = self.model.diffusion_model
+        return tuple((str(p.device), p._version, p.data_ptr()) for p in m.parameters()).__hash__()
+
     def register_schedule(self, given_betas=None, beta_schedule="linear", timesteps=1000, linear_start=1e-4,
                           linear_end=2e-2, cosine_s=8e-3):
         betas = given_betas if given_betas is not None else make_beta_schedule(
