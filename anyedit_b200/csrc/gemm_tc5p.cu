@@ -11,18 +11,27 @@
 //     residual), and written back with a TMA store (2-D map for token matrices, 4-D NHWC map for conv
 //     patches -- edge clipping is the tensor map's job, no per-row predicates, no scattered 16-byte stores).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace anysd {
 
-constexpr int P_BM = 128, P_BK = 64, P_BN = 256, P_STAGES = 3, P_NSTG = 4, P_SUB = 64;
+constexpr int P_BM = 128, P_BK = 64, P_BN = 256, P_NSTG = 4, P_SUB = 64;
 constexpr int P_THREADS = 384;                       // warps 0..3: TMA, MMA, TMEM-alloc, spare; warps 4..11: epilogue
 constexpr int P_A_BYTES = P_BM * P_BK * 2;           // 16 KB
-constexpr int P_B_BYTES = P_BN * P_BK * 2;           // 32 KB
-constexpr int P_STAGE_BYTES = P_A_BYTES + P_B_BYTES; // 48 KB
 constexpr int P_STG_BYTES = P_BM * P_SUB * 2;        // 16 KB
-constexpr int P_SMEM = P_STAGES * P_STAGE_BYTES + P_NSTG * P_STG_BYTES + 1024 + 256;
+// CTAS = 1: one CTA owns a 128 x <=256 tile, stage = 16 KB A + 32 KB B, 3 stages.
+// CTAS = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2, UMMA M = 256) owns a 256 x <=256 tile; each CTA
+//           stages its 128 rows of A and HALF of the B rows (16 + 16 KB), 4 stages: L2->SM operand traffic per
+//           FLOP is two thirds of the single-CTA tile's, which is what bounds the 128-row kernel.
+template <int CTAS>
+struct PCfg {
+    static constexpr int B_BYTES = (P_BN / CTAS) * P_BK * 2;
+    static constexpr int STAGE_BYTES = P_A_BYTES + B_BYTES;
+    static constexpr int STAGES = CTAS == 2 ? 4 : 3;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + P_NSTG * P_STG_BYTES + 1024 + 256;
+};
 
 struct PArgs {
     const float* bias;
@@ -73,6 +82,55 @@ __device__ __forceinline__ void p_tma_store_4d(const CUtensorMap* tm, uint32_t s
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// ---- 2-CTA (cta_group::2) forms ----
+__device__ __forceinline__ uint32_t p_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void p_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (+ expect_tx) on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void pm_expect_tx_remote(uint32_t bar, uint32_t bytes, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %2;\n\t"
+        "}" ::"r"(bar), "r"(cta), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pm_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(bar), "r"(cta) : "memory");
+}
+// TMA loads of a CTA pair: the transaction bytes are credited to the LEADER's barrier (peer bit cleared)
+__device__ __forceinline__ void p_tma2_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void p_tma2_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void p_umma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// completion of all prior MMAs of the pair -> arrive on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void p_commit2(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+
 __device__ __forceinline__ void p_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void p_store_wait_read() {
@@ -133,14 +191,14 @@ struct TileCoord {
     int tw, th, tn;      // conv: patch indices
 };
 
-template <bool CONV>
-__device__ __forceinline__ TileCoord tile_coord(const PArgs& p, int tile) {
+template <bool CONV, int CTAS>
+__device__ __forceinline__ TileCoord tile_coord(const PArgs& p, int tile, int rank) {
     TileCoord c;
-    const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+    const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CTAS + rank;   // a pair owns m-tiles 2t, 2t+1
     c.n0 = nt * P_BN;
     int w = p.N - c.n0;
     if (w > P_BN) w = P_BN;
-    c.nw = (w + 15) & ~15;
+    c.nw = CTAS == 2 ? ((w + 31) & ~31) : ((w + 15) & ~15);
     c.m0 = mt * P_BM;
     c.tw = c.th = c.tn = 0;
     if (CONV) {
@@ -151,7 +209,7 @@ __device__ __forceinline__ TileCoord tile_coord(const PArgs& p, int tile) {
     return c;
 }
 
-template <bool CONV>
+template <bool CONV, int CTAS>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const PArgs p) {
@@ -159,6 +217,10 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t raw = smem_u32(p_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* smem = p_smem_raw + (base - raw);
+    constexpr int P_STAGES = PCfg<CTAS>::STAGES, P_STAGE_BYTES = PCfg<CTAS>::STAGE_BYTES;
+    const int rank = CTAS == 2 ? (int)p_cluster_rank() : 0;
+    const bool leader = rank == 0;
+    const int cta_stride = gridDim.x / CTAS, cta_first = blockIdx.x / CTAS;     // tile loop runs over CTA pairs
     const uint32_t stg_base = base + P_STAGES * P_STAGE_BYTES;
     const uint32_t bar_base = stg_base + P_NSTG * P_STG_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -179,23 +241,30 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < P_STAGES; ++s) {
-            pm_init(full_bar(s), 1);
+            pm_init(full_bar(s), CTAS);      // one arrive.expect_tx per CTA of the pair (on the leader's barrier)
             pm_init(empty_bar(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
             pm_init(tfull_bar(b), 1);
-            pm_init(tempty_bar(b), 8);       // one arrive per epilogue warp
+            pm_init(tempty_bar(b), 8 * CTAS);   // one arrive per epilogue warp of every CTA of the pair
         }
         for (int b = 0; b < P_NSTG; ++b) pm_init(res_bar(b), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CTAS == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     p_fence_before();
     __syncthreads();
+    if (CTAS == 2) p_cluster_sync();         // the peer's barriers exist before anything remote touches them
     p_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -203,37 +272,50 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             // ===== TMA producer: runs ahead across tile boundaries =====
             uint32_t g = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const TileCoord c = tile_coord<CONV>(p, tile);
+            for (int tile = cta_first; tile < p.num_tiles; tile += cta_stride) {
+                const TileCoord c = tile_coord<CONV, CTAS>(p, tile, rank);
                 for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
                     const int s = g % P_STAGES;
                     const uint32_t ph = (g / P_STAGES) & 1;
                     pm_wait(empty_bar(s), ph ^ 1);
-                    pm_expect_tx(full_bar(s), P_STAGE_BYTES);
                     const uint32_t sa = base + s * P_STAGE_BYTES, sb = sa + P_A_BYTES;
+                    int tap = 0, c0 = 0, ky = 0, kx = 0;
                     if (CONV) {
-                        const int tap = kb / p.kb_per_tap;
-                        const int c0 = (kb - tap * p.kb_per_tap) * P_BK;
-                        const int ky = tap / 3, kx = tap - ky * 3;
-                        p_tma_load_4d(sa, &tmA, full_bar(s), c0, c.tw * p.BW * p.stride + kx - 1,
-                                      c.th * p.BH * p.stride + ky - 1, c.tn * p.NB);
-                    } else {
-                        p_tma_load_2d(sa, &tmA, full_bar(s), kb * P_BK, c.m0);
+                        tap = kb / p.kb_per_tap;
+                        c0 = (kb - tap * p.kb_per_tap) * P_BK;
+                        ky = tap / 3;
+                        kx = tap - ky * 3;
                     }
-                    p_tma_load_2d(sb, &tmB, full_bar(s), kb * P_BK, c.n0);
+                    if (CTAS == 2) {
+                        pm_expect_tx_remote(full_bar(s), P_STAGE_BYTES, 0);      // credited to the leader's barrier
+                        if (CONV)
+                            p_tma2_load_4d(sa, &tmA, full_bar(s), c0, c.tw * p.BW * p.stride + kx - 1,
+                                           c.th * p.BH * p.stride + ky - 1, c.tn * p.NB);
+                        else
+                            p_tma2_load_2d(sa, &tmA, full_bar(s), kb * P_BK, c.m0);
+                        p_tma2_load_2d(sb, &tmB, full_bar(s), kb * P_BK, c.n0 + rank * (c.nw >> 1));   // its half of B
+                    } else {
+                        pm_expect_tx(full_bar(s), P_STAGE_BYTES);
+                        if (CONV)
+                            p_tma_load_4d(sa, &tmA, full_bar(s), c0, c.tw * p.BW * p.stride + kx - 1,
+                                          c.th * p.BH * p.stride + ky - 1, c.tn * p.NB);
+                        else
+                            p_tma_load_2d(sa, &tmA, full_bar(s), kb * P_BK, c.m0);
+                        p_tma_load_2d(sb, &tmB, full_bar(s), kb * P_BK, c.n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
+        if (lane == 0 && leader) {
+            // ===== MMA issuer (the leader CTA issues for the pair) =====
             uint32_t g = 0, t = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
-                const TileCoord c = tile_coord<CONV>(p, tile);
+            for (int tile = cta_first; tile < p.num_tiles; tile += cta_stride, ++t) {
+                const TileCoord c = tile_coord<CONV, CTAS>(p, tile, 0);
                 const uint32_t buf = t & 1, bph = (t >> 1) & 1;
-                pm_wait(tempty_bar(buf), bph ^ 1);           // epilogue has drained this accumulator
+                pm_wait(tempty_bar(buf), bph ^ 1);           // epilogue(s) have drained this accumulator
                 p_fence_after();
-                const uint32_t idesc = (1u << 4) | ((uint32_t)(c.nw >> 3) << 17) | ((uint32_t)(P_BM >> 4) << 24);
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(c.nw >> 3) << 17) | ((uint32_t)((P_BM * CTAS) >> 4) << 24);
                 const uint32_t d = tmem_base + buf * P_BN;
                 for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
                     const int s = g % P_STAGES;
@@ -243,10 +325,13 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint32_t sa = base + s * P_STAGE_BYTES, sb = sa + P_A_BYTES;
                     const uint64_t ad = p_sdesc(sa), bd = p_sdesc(sb);
 #pragma unroll
-                    for (int k = 0; k < P_BK / 16; ++k) p_umma(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                    p_commit(empty_bar(s));
+                    for (int k = 0; k < P_BK / 16; ++k) {
+                        if (CTAS == 2) p_umma2(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        else p_umma(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    }
+                    if (CTAS == 2) p_commit2(empty_bar(s)); else p_commit(empty_bar(s));
                 }
-                p_commit(tfull_bar(buf));
+                if (CTAS == 2) p_commit2(tfull_bar(buf)); else p_commit(tfull_bar(buf));
             }
         }
     } else if (warp >= 4) {
@@ -258,8 +343,8 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool elected = (warp == 4 && lane == 0);
         uint32_t t = 0, q = 0;                                // tile counter, global sub-tile counter
         const int acc_per_sub = (p.act == 2) ? 2 * P_SUB : P_SUB;   // accumulator columns feeding one 64-column store
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++t) {
-            const TileCoord c = tile_coord<CONV>(p, tile);
+        for (int tile = cta_first; tile < p.num_tiles; tile += cta_stride, ++t) {
+            const TileCoord c = tile_coord<CONV, CTAS>(p, tile, rank);
             const uint32_t buf = t & 1, bph = (t >> 1) & 1;
             const int nsub = (c.nw + acc_per_sub - 1) / acc_per_sub;
             const int out_c0 = (p.act == 2) ? (c.n0 >> 1) : c.n0;   // first output column of the tile
@@ -399,14 +484,20 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // accumulator fully read: hand the TMEM buffer back to the MMA warp
             p_fence_before();
             __syncwarp();
-            if (lane == 0) pm_arrive(tempty_bar(buf));
+            if (lane == 0) {
+                if (CTAS == 2) pm_arrive_remote(tempty_bar(buf), 0); else pm_arrive(tempty_bar(buf));
+            }
         }
         if (elected) p_store_wait<0>();                        // smem must outlive the last store
     }
     p_fence_before();
     __syncthreads();
+    if (CTAS == 2) p_cluster_sync();         // neither CTA leaves while the pair's MMAs / remote arrives may still touch it
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (CTAS == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -482,6 +573,45 @@ bool tc5p_supported(const anysd_gemm_params* q) {
     return p_get_encode() != nullptr;
 }
 
+template <bool CONV, int CTAS>
+static int p_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
+                    const PArgs& a, cudaStream_t st) {
+    static bool done[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc5p_kernel<CONV, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             PCfg<CTAS>::SMEM);
+        if (e != cudaSuccess) {
+            set_error("tcgen05 gemm: smem opt-in failed: %s", cudaGetErrorString(e));
+            return ANYSD_ECUDA;
+        }
+        done[dev] = true;
+    }
+    int grid = sm_count();
+    if (grid > a.num_tiles * CTAS) grid = a.num_tiles * CTAS;
+    grid -= grid % CTAS;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(P_THREADS);
+    cfg.dynamicSmemBytes = PCfg<CTAS>::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CTAS == 2 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc5p_kernel<CONV, CTAS>, tmA, tmB, tmO, tmR, a);
+    if (e != cudaSuccess) {
+        set_error("tcgen05 gemm launch failed: %s", cudaGetErrorString(e));
+        return ANYSD_ECUDA;
+    }
+    return check_launch(CONV ? "conv3x3 (tcgen05 persistent)" : "gemm (tcgen05 persistent)");
+}
+
 int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
     PArgs a;
     a.bias = q->bias;
@@ -501,10 +631,6 @@ int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
     a.Ho = a.Wo = 0;
     const int n_out = q->act == 2 ? q->N / 2 : q->N;
     CUtensorMap tmA, tmB, tmO, tmR;
-    if (!p_map_2d(&tmB, q->W, (uint64_t)q->K, (uint64_t)q->N, (uint64_t)q->ldw, P_BK, P_BN)) {
-        set_error("tcgen05 gemm: tensor map for W failed (N=%d K=%d ldw=%d)", q->N, q->K, q->ldw);
-        return ANYSD_ECUDA;
-    }
     bool ok = true;
     if (q->conv) {
         const void* img = q->A;
@@ -535,33 +661,21 @@ int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
         ok = ok && p_map_2d(&tmO, q->out, (uint64_t)n_out, (uint64_t)q->M, (uint64_t)q->ldo, P_SUB, P_BM);
         if (q->residual) ok = ok && p_map_2d(&tmR, q->residual, (uint64_t)n_out, (uint64_t)q->M, (uint64_t)q->ldr, P_SUB, P_BM);
     }
+    // CTA pairs (cta_group::2, 256-row tiles) unless the problem has too few row tiles to feed pairs;
+    // ANYSD_GEMM_CTAS=1|2 forces either form (tests cross-check them).
+    static const char* force = getenv("ANYSD_GEMM_CTAS");
+    int ctas = (a.tiles_m >= 16) ? 2 : 1;
+    if (force && (force[0] == '1' || force[0] == '2')) ctas = force[0] - '0';
+    if (ctas == 2 && sm_count() < 2) ctas = 1;
+    ok = ok && p_map_2d(&tmB, q->W, (uint64_t)q->K, (uint64_t)q->N, (uint64_t)q->ldw, P_BK, P_BN / ctas);
     if (!ok) {
         set_error("tcgen05 gemm: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d conv=%d)", q->M, q->N, q->K, q->conv);
         return ANYSD_ECUDA;
     }
     if (!q->residual) tmR = tmO;
-    a.num_tiles = a.tiles_m * a.tiles_n;
-    static bool done[64][2];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    dev &= 63;
-    const int ci = q->conv ? 1 : 0;
-    if (!done[dev][ci]) {
-        cudaError_t e = q->conv ? cudaFuncSetAttribute(gemm_tc5p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM)
-                                : cudaFuncSetAttribute(gemm_tc5p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
-        if (e != cudaSuccess) {
-            set_error("tcgen05 gemm: smem opt-in failed: %s", cudaGetErrorString(e));
-            return ANYSD_ECUDA;
-        }
-        done[dev][ci] = true;
-    }
-    int grid = sm_count();
-    if (grid > a.num_tiles) grid = a.num_tiles;
-    if (q->conv)
-        gemm_tc5p_kernel<true><<<grid, P_THREADS, P_SMEM, st>>>(tmA, tmB, tmO, tmR, a);
-    else
-        gemm_tc5p_kernel<false><<<grid, P_THREADS, P_SMEM, st>>>(tmA, tmB, tmO, tmR, a);
-    return check_launch(q->conv ? "conv3x3 (tcgen05 persistent)" : "gemm (tcgen05 persistent)");
+    a.num_tiles = cdiv(a.tiles_m, ctas) * a.tiles_n;
+    if (q->conv) return ctas == 2 ? p_launch<true, 2>(tmA, tmB, tmO, tmR, a, st) : p_launch<true, 1>(tmA, tmB, tmO, tmR, a, st);
+    return ctas == 2 ? p_launch<false, 2>(tmA, tmB, tmO, tmR, a, st) : p_launch<false, 1>(tmA, tmB, tmO, tmR, a, st);
 }
 
 }  // namespace anysd
