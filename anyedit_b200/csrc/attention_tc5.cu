@@ -14,6 +14,7 @@
 //   K-extent = ceil16(d), V is consumed as an MN-major B operand straight from its row-major tile.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -48,6 +49,20 @@ __device__ __forceinline__ void am_wait(uint32_t bar, uint32_t parity) {
         "WAIT_LOOP:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
         "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// Waiter that is NOT on the critical path (producer / MMA lane waiting for the softmax warps): back off with
+// nanosleep between probes so the spin does not steal issue slots from the 8 softmax warps of the SM.
+__device__ __forceinline__ void am_wait_relaxed(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "nanosleep.u32 96;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t"
         "}" ::"r"(bar), "r"(parity) : "memory");
@@ -103,6 +118,19 @@ __device__ __forceinline__ float a_ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], near-minimax cubic for
+// 2^f (max rel. err 7.6e-5, below the 4.9e-4 rounding of the fp16 P it feeds), exponent patched by integer add.
+// Used for a fixed fraction of the scores so that the exp work is shared between the XU pipe (MUFU.EX2,
+// 16/clk/SM -- the measured bottleneck at d = 40) and the under-used FMA pipe.
+__device__ __forceinline__ float a_ex2_poly(float x) {
+    x = fmaxf(x, -125.0f);
+    const float xr = x + 12582912.0f;                 // 1.5 * 2^23: integer part lands in the low mantissa bits
+    const float f = x - (xr - 12582912.0f);
+    float p = fmaf(0.05520551f, f, 0.24261396f);
+    p = fmaf(p, f, 0.69325476f);
+    p = fmaf(p, f, 0.99992773f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
 // K-major SW128 operand (rows 128 B apart inside an atom, 8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t a_desc_k(uint32_t addr) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -113,6 +141,7 @@ __device__ __forceinline__ uint64_t a_desc_mn(uint32_t addr, uint32_t lbo_bytes)
            (2ull << 61);
 }
 
+template <int EMU>    // EMU of every 8 scores take the polynomial exp2
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AtArgs p) {
@@ -170,7 +199,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             for (int a = 0; a < NA; ++a) a_tma_2d(base + q_off + a * AT_ATOM, &tmQ, BAR(0), col0 + a * 64, b * p.n_q + q0);
             for (int j = 0; j < nt; ++j) {
                 const int s = j % ST;
-                am_wait(BAR(3 + s), (((uint32_t)j / ST) & 1) ^ 1);
+                am_wait_relaxed(BAR(3 + s), (((uint32_t)j / ST) & 1) ^ 1);
                 am_expect_tx(BAR(1 + s), 2 * NA * AT_ATOM);
                 const uint32_t kb = base + kv_off + s * 2 * NA * AT_ATOM, vb = kb + NA * AT_ATOM;
                 for (int a = 0; a < NA; ++a) a_tma_2d(kb + a * AT_ATOM, &tmK, BAR(1 + s), col0 + a * 64, b * p.n_kv + j * AT_BKV);
@@ -200,11 +229,11 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 if (j + 1 < nt && ST > 1) {                               // run S(j+1) under the softmax of tile j
                     const int s1 = (j + 1) % ST;
                     am_wait(BAR(1 + s1), ((uint32_t)(j + 1) / ST) & 1);   // K(j+1), V(j+1) landed
-                    am_wait(BAR(6), j & 1);                               // S(j) is in registers
+                    am_wait_relaxed(BAR(6), j & 1);                       // S(j) is in registers
                     a_fence_after();
                     issue_S(j + 1);
                 }
-                am_wait(BAR(7), j & 1);                                   // P(j) written (and O rescaled)
+                am_wait_relaxed(BAR(7), j & 1);                           // P(j) written (and O rescaled)
                 a_fence_after();
                 const uint32_t vb = base + kv_off + (j % ST) * 2 * NA * AT_ATOM + NA * AT_ATOM;
                 for (int k = 0; k < AT_BKV / 16; ++k) {
@@ -242,8 +271,16 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const int kv_left = p.n_kv - j * AT_BKV;
             float mx = -INFINITY;
             if (kv_left >= AT_BKV) {
+                // four independent chains (a single running max is a 128-deep dependent chain)
+                float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+                for (int i = 0; i < 128; i += 8) {
+                    m0 = fmaxf(m0, fmaxf(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])));
+                    m1 = fmaxf(m1, fmaxf(__uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3])));
+                    m2 = fmaxf(m2, fmaxf(__uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5])));
+                    m3 = fmaxf(m3, fmaxf(__uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7])));
+                }
+                mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
             } else {
 #pragma unroll
                 for (int i = 0; i < 128; ++i) {
@@ -258,17 +295,23 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const float m_new = upd ? mx : m_run;
             const float corr = upd ? a_ex2(m_run - m_new) : 1.0f;    // first tile: ex2(-inf) = 0
             m_run = m_new;
-            float sum = 0.f;
+            float sum = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
             uint32_t pk[64];
 #pragma unroll
             for (int i = 0; i < 64; ++i) {
-                const float p0 = a_ex2(fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, -m_new));
-                const float p1 = a_ex2(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, -m_new));
-                sum += p0 + p1;
+                const float x0 = fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, -m_new);
+                const float x1 = fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, -m_new);
+                // elements (2i, 2i+1) within each group of 8: the first EMU go to the polynomial
+                const float p0 = (((2 * i) & 7) < EMU) ? a_ex2_poly(x0) : a_ex2(x0);
+                const float p1 = (((2 * i + 1) & 7) < EMU) ? a_ex2_poly(x1) : a_ex2(x1);
+                if ((i & 3) == 0) sum += p0 + p1;          // four independent accumulation chains
+                else if ((i & 3) == 1) sum1 += p0 + p1;
+                else if ((i & 3) == 2) sum2 += p0 + p1;
+                else sum3 += p0 + p1;
                 __half2 hh = __floats2half2_rn(p0, p1);
                 pk[i] = *reinterpret_cast<uint32_t*>(&hh);
             }
-            l_run = l_run * corr + sum;
+            l_run = l_run * corr + ((sum + sum1) + (sum2 + sum3));
             // P smem and the O accumulator are free once PV(j-1) has retired
             if (j > 0) {
                 am_wait(BAR(8), (j - 1) & 1);
@@ -405,7 +448,10 @@ int launch_attention_tc5(const anysd_attn_params* q, cudaStream_t st) {
     cudaGetDevice(&dev);
     dev &= 63;
     if (attr_set[dev] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(attention_tc5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc5_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc5_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             set_error("attention (tcgen05): smem opt-in failed: %s", cudaGetErrorString(e));
             return ANYSD_ECUDA;
@@ -413,7 +459,16 @@ int launch_attention_tc5(const anysd_attn_params* q, cudaStream_t st) {
         attr_set[dev] = smem;
     }
     dim3 grid(cdiv(q->n_q, AT_BQ), q->heads, q->B);
-    attention_tc5_kernel<<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a);
+    // exp2 split between MUFU and the FMA-pipe polynomial: matters when the kernel is exp-bound (small d)
+    static const char* emu_env = getenv("ANYSD_ATTN_EMU");
+    int emu = 0;   // measured on B200: the kernel is latency-, not MUFU-bound; the polynomial split does not pay (yet)
+    if (emu_env) emu = atoi(emu_env);
+    switch (emu) {
+        case 2: attention_tc5_kernel<2><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a); break;
+        case 3: attention_tc5_kernel<3><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a); break;
+        case 4: attention_tc5_kernel<4><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a); break;
+        default: attention_tc5_kernel<0><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a); break;
+    }
     return check_launch("attention (tcgen05)");
 }
 

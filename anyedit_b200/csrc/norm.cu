@@ -131,6 +131,22 @@ __global__ void gn_apply_kernel(const uint4* __restrict__ x1, const uint4* __res
     const int stride = first ? CV1 : CV2;
     uint4* out = y + (size_t)n * HW * CV + cv;
     int row = row0 + r;
+    for (; row + 3 * R < row1; row += 4 * R) {      // 4 independent 16-byte loads in flight per thread
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(base + (size_t)(row + u * R) * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8(v[u], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float t = f[j] * ca[j] + cb[j];
+                f[j] = fuse_silu ? silu_f(t) : t;
+            }
+            out[(size_t)(row + u * R) * CV] = pack8(f);
+        }
+    }
     for (; row + R < row1; row += 2 * R) {
         uint4 v0 = __ldg(base + (size_t)row * stride);
         uint4 v1 = __ldg(base + (size_t)(row + R) * stride);
@@ -159,20 +175,24 @@ __global__ void gn_apply_kernel(const uint4* __restrict__ x1, const uint4* __res
     }
 }
 
-// ---- LayerNorm: one warp per token row, row held in registers (C <= 2048) ----------------------
-constexpr int LN_MAX_VEC = 8;
-
+// ---- LayerNorm: LPR lanes per token row (8 / 16 / 32), VPL 16-byte vectors per lane held in registers ---------
+// C = 320 / 640 / 1280 map to LPR = 8 / 16 / 32 with exactly 5 vectors per lane: a warp then normalises
+// 4 / 2 / 1 rows at once with 5 independent 16-byte loads in flight per lane (the one-warp-per-row version left
+// 24 of 32 lanes with a single load at C = 320 and ran at 1.6 TB/s).  Two-pass exact variance from registers.
+template <int LPR, int VPL>
 __global__ void layernorm_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, uint4* __restrict__ y, long long M, int CV, float eps) {
+    constexpr int RPW = 32 / LPR;                       // rows per warp
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= M) return;
-    const uint4* xr = x + row * CV;
-    float f[LN_MAX_VEC][8];
+    const int sub = lane / LPR, l = lane % LPR;
+    const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+    const bool row_ok = row < M;
+    const uint4* xr = x + (row_ok ? row : 0) * CV;
+    float f[VPL][8];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
-        const int v = lane + i * 32;
+    for (int i = 0; i < VPL; ++i) {
+        const int v = l + i * LPR;
         if (v < CV) {
             uint4 u = __ldg(xr + v);
             unpack8(u, f[i]);
@@ -180,12 +200,14 @@ __global__ void layernorm_kernel(const uint4* __restrict__ x, const float* __res
             for (int j = 0; j < 8; ++j) s += f[i][j];
         }
     }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float inv_c = 1.0f / (float)(CV * 8);
-    const float mean = warp_sum(s) * inv_c;
+    const float mean = s * inv_c;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
-        const int v = lane + i * 32;
+    for (int i = 0; i < VPL; ++i) {
+        const int v = l + i * LPR;
         if (v < CV) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -194,11 +216,14 @@ __global__ void layernorm_kernel(const uint4* __restrict__ x, const float* __res
             }
         }
     }
-    const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_c + eps);
+    if (!row_ok) return;
     uint4* yr = y + row * CV;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
-        const int v = lane + i * 32;
+    for (int i = 0; i < VPL; ++i) {
+        const int v = l + i * LPR;
         if (v < CV) {
             const float4* g4 = reinterpret_cast<const float4*>(gamma + v * 8);
             const float4* b4 = reinterpret_cast<const float4*>(beta + v * 8);
@@ -264,11 +289,26 @@ int anysd_groupnorm_nhwc_f16(const void* x1, int C1, const void* x2, int C2, con
 int anysd_layernorm_f16(const void* x, const float* gamma, const float* beta, void* y, long long M, int C, float eps,
                         anysd_stream_t stream) {
     ANYSD_REQUIRE(x && gamma && beta && y && M > 0, ANYSD_EINVAL, "layernorm: bad args");
-    ANYSD_REQUIRE(C > 0 && C % 8 == 0 && C / 8 <= 32 * LN_MAX_VEC, ANYSD_EINVAL,
-                  "layernorm: C=%d must be a multiple of 8 and <= %d", C, 256 * LN_MAX_VEC);
-    const int warps = 8;
-    layernorm_kernel<<<cdiv(M, warps), warps * 32, 0, (cudaStream_t)stream>>>((const uint4*)x, gamma, beta, (uint4*)y, M,
-                                                                              C / 8, eps);
+    ANYSD_REQUIRE(C > 0 && C % 8 == 0 && C / 8 <= 256, ANYSD_EINVAL, "layernorm: C=%d must be a multiple of 8 and <= 2048", C);
+    const int CV = C / 8, warps = 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint4* xi = (const uint4*)x;
+    uint4* yo = (uint4*)y;
+#define ANYSD_LN(LPR, VPL)                                                                                     \
+    layernorm_kernel<LPR, VPL><<<cdiv(M, (long long)warps * (32 / LPR)), warps * 32, 0, st>>>(xi, gamma, beta, yo, M, CV, eps)
+    if (CV <= 8 * 5) {
+        if (CV <= 8) ANYSD_LN(8, 1);
+        else if (CV <= 16) ANYSD_LN(8, 2);
+        else if (CV <= 24) ANYSD_LN(8, 3);
+        else ANYSD_LN(8, 5);
+    } else if (CV <= 16 * 5) {
+        ANYSD_LN(16, 5);
+    } else if (CV <= 32 * 5) {
+        ANYSD_LN(32, 5);
+    } else {
+        ANYSD_LN(32, 8);
+    }
+#undef ANYSD_LN
     return check_launch("layernorm");
 }
 }
