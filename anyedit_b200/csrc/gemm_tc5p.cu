@@ -39,6 +39,7 @@ struct PArgs {
     int M, N, ld_rowadd, rows_per_batch;
     int act, has_res;
     int num_kb, tiles_m, tiles_n, num_tiles;
+    int bn, stage_tx;        // tile width (64 | 128 | 256) and TMA bytes per stage per CTA (A + its share of B)
     // conv geometry
     int Nimg, Ho, Wo;
     int BW, BH, NB, tiles_w, tiles_h;
@@ -195,9 +196,9 @@ template <bool CONV, int CTAS>
 __device__ __forceinline__ TileCoord tile_coord(const PArgs& p, int tile, int rank) {
     TileCoord c;
     const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CTAS + rank;   // a pair owns m-tiles 2t, 2t+1
-    c.n0 = nt * P_BN;
+    c.n0 = nt * p.bn;
     int w = p.N - c.n0;
-    if (w > P_BN) w = P_BN;
+    if (w > p.bn) w = p.bn;
     c.nw = CTAS == 2 ? ((w + 31) & ~31) : ((w + 15) & ~15);
     c.m0 = mt * P_BM;
     c.tw = c.th = c.tn = 0;
@@ -287,7 +288,7 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         kx = tap - ky * 3;
                     }
                     if (CTAS == 2) {
-                        pm_expect_tx_remote(full_bar(s), P_STAGE_BYTES, 0);      // credited to the leader's barrier
+                        pm_expect_tx_remote(full_bar(s), p.stage_tx, 0);         // credited to the leader's barrier
                         if (CONV)
                             p_tma2_load_4d(sa, &tmA, full_bar(s), c0, c.tw * p.BW * p.stride + kx - 1,
                                            c.th * p.BH * p.stride + ky - 1, c.tn * p.NB);
@@ -295,7 +296,7 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             p_tma2_load_2d(sa, &tmA, full_bar(s), kb * P_BK, c.m0);
                         p_tma2_load_2d(sb, &tmB, full_bar(s), kb * P_BK, c.n0 + rank * (c.nw >> 1));   // its half of B
                     } else {
-                        pm_expect_tx(full_bar(s), P_STAGE_BYTES);
+                        pm_expect_tx(full_bar(s), p.stage_tx);
                         if (CONV)
                             p_tma_load_4d(sa, &tmA, full_bar(s), c0, c.tw * p.BW * p.stride + kx - 1,
                                           c.th * p.BH * p.stride + ky - 1, c.tn * p.NB);
@@ -623,7 +624,6 @@ int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
     a.act = q->act;
     a.has_res = q->residual != nullptr;
     a.num_kb = cdiv(q->K, P_BK);
-    a.tiles_n = cdiv(q->N, P_BN);
     a.Nimg = q->Nimg;
     a.BW = a.BH = a.NB = a.tiles_w = a.tiles_h = 1;
     a.kb_per_tap = 1;
@@ -661,13 +661,31 @@ int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
         ok = ok && p_map_2d(&tmO, q->out, (uint64_t)n_out, (uint64_t)q->M, (uint64_t)q->ldo, P_SUB, P_BM);
         if (q->residual) ok = ok && p_map_2d(&tmR, q->residual, (uint64_t)n_out, (uint64_t)q->M, (uint64_t)q->ldr, P_SUB, P_BM);
     }
-    // CTA pairs (cta_group::2, 256-row tiles) unless the problem has too few row tiles to feed pairs;
-    // ANYSD_GEMM_CTAS=1|2 forces either form (tests cross-check them).
+    // Tile shape selection.  Candidates: CTA pairs (cta_group::2, 256-row tiles, less L2 traffic per FLOP) or
+    // single CTAs, tile width 256 / 128 / 64 (GEGLU pairs need >= 128).  Cost model = scheduling rounds on the
+    // 148 SMs x per-tile time ~ (bn + 270): deep levels (8 row tiles x 5 column tiles) otherwise leave most of the
+    // machine idle, mid levels suffer from wave quantisation.  ANYSD_GEMM_CTAS=1|2 / ANYSD_GEMM_BN force a choice.
     static const char* force = getenv("ANYSD_GEMM_CTAS");
-    int ctas = (a.tiles_m >= 16) ? 2 : 1;
-    if (force && (force[0] == '1' || force[0] == '2')) ctas = force[0] - '0';
-    if (ctas == 2 && sm_count() < 2) ctas = 1;
-    ok = ok && p_map_2d(&tmB, q->W, (uint64_t)q->K, (uint64_t)q->N, (uint64_t)q->ldw, P_BK, P_BN / ctas);
+    static const char* force_bn = getenv("ANYSD_GEMM_BN");
+    int ctas = 1, bn = 256;
+    {
+        long best = -1;
+        for (int c = 2; c >= 1; --c) {
+            if (c == 2 && (a.tiles_m < 2 || sm_count() < 2)) continue;
+            if (force && (force[0] == '1' || force[0] == '2') && c != force[0] - '0') continue;
+            for (int w = 256; w >= (q->act == 2 ? 128 : 64); w >>= 1) {
+                if (force_bn && atoi(force_bn) != w) continue;
+                const long tiles = (long)cdiv(a.tiles_m, c) * cdiv(q->N, w);
+                const long rounds = (tiles + sm_count() / c - 1) / (sm_count() / c);
+                const long cost = rounds * (w + 270);   // fitted: a 128-wide tile costs 0.76x a 256-wide one
+                if (best < 0 || cost < best) { best = cost; ctas = c; bn = w; }
+            }
+        }
+    }
+    a.bn = bn;
+    a.tiles_n = cdiv(q->N, bn);
+    a.stage_tx = P_A_BYTES + (bn / ctas) * P_BK * 2;
+    ok = ok && p_map_2d(&tmB, q->W, (uint64_t)q->K, (uint64_t)q->N, (uint64_t)q->ldw, P_BK, bn / ctas);
     if (!ok) {
         set_error("tcgen05 gemm: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d conv=%d)", q->M, q->N, q->K, q->conv);
         return ANYSD_ECUDA;
