@@ -32,7 +32,8 @@ static GnGeom gn_geom(int C1, int C2) {
 }
 
 __global__ void gn_stats_kernel(const uint4* __restrict__ x1, const uint4* __restrict__ x2, int CV, int CV1, int R,
-                                int HW, int rows_per_block, int G, int cpg, float* __restrict__ partials) {
+                                int HW, int rows_per_block, int G, int cpg, float eps, float* __restrict__ partials,
+                                float* __restrict__ meanrstd, unsigned int* __restrict__ counters) {
     extern __shared__ float sm[];  // [R][CV*8] sums, then [R][CV*8] squares
     const int n = blockIdx.y, s = blockIdx.x;
     const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
@@ -75,41 +76,68 @@ __global__ void gn_stats_kernel(const uint4* __restrict__ x1, const uint4* __res
         ssq[(size_t)r * C + j * CV + cv] = sq[j];
     }
     __syncthreads();
-    // thread g < G folds its group's channels over all R row-lanes
+    // fold 1: one thread per channel slot sums the R row-lanes (R loads), result back into row-lane 0
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int rr = 0; rr < R; ++rr) {
+            a += ssum[(size_t)rr * C + i];
+            b += ssq[(size_t)rr * C + i];
+        }
+        ssum[i] = a;
+        ssq[i] = b;
+    }
+    __syncthreads();
+    // fold 2: thread g < G sums its group's cpg channels
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         float a = 0.f, b = 0.f;
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
             const int idx = (c & 7) * CV + (c >> 3);
-            for (int rr = 0; rr < R; ++rr) {
-                a += ssum[(size_t)rr * C + idx];
-                b += ssq[(size_t)rr * C + idx];
-            }
+            a += ssum[idx];
+            b += ssq[idx];
         }
         float* p = partials + (((size_t)n * gridDim.x + s) * G + g) * 2;
         p[0] = a;
         p[1] = b;
     }
+    // The last block of image n to finish folds the S partials (fixed order, in double: deterministic and
+    // independent of which block happens to be last) into mean / rstd, so the apply pass starts streaming at once.
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(&counters[n], 1u);
+        is_last = (done == gridDim.x - 1);
+        if (is_last) counters[n] = 0;                 // re-arm for the next launch (stream-ordered)
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int g = threadIdx.x; g < G; g += blockDim.x) {
+            double a = 0.0, b = 0.0;
+            const float* p = partials + ((size_t)n * gridDim.x * G + g) * 2;
+            for (int i = 0; i < (int)gridDim.x; ++i) {
+                a += (double)__ldcg(p + (size_t)i * G * 2);
+                b += (double)__ldcg(p + (size_t)i * G * 2 + 1);
+            }
+            const double cnt = (double)HW * cpg;
+            const double mean = a / cnt;
+            double var = b / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            meanrstd[((size_t)n * G + g) * 2] = (float)mean;
+            meanrstd[((size_t)n * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+        }
+    }
 }
 
 __global__ void gn_apply_kernel(const uint4* __restrict__ x1, const uint4* __restrict__ x2, int CV, int CV1, int R,
-                                int HW, int rows_per_block, int G, int cpg, int S, const float* __restrict__ partials,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int fuse_silu,
+                                int HW, int rows_per_block, int G, int cpg, const float* __restrict__ meanrstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int fuse_silu,
                                 uint4* __restrict__ y) {
     __shared__ float s_mean[64], s_rstd[64];
     const int n = blockIdx.y, s = blockIdx.x;
     if (threadIdx.x < G) {
-        double a = 0.0, b = 0.0;
-        const float* p = partials + ((size_t)n * S * G + threadIdx.x) * 2;
-        for (int i = 0; i < S; ++i) {
-            a += (double)p[(size_t)i * G * 2];
-            b += (double)p[(size_t)i * G * 2 + 1];
-        }
-        const double cnt = (double)HW * cpg;
-        const double mean = a / cnt;
-        double var = b / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        s_mean[threadIdx.x] = (float)mean;
-        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+        s_mean[threadIdx.x] = meanrstd[((size_t)n * G + threadIdx.x) * 2];
+        s_rstd[threadIdx.x] = meanrstd[((size_t)n * G + threadIdx.x) * 2 + 1];
     }
     __syncthreads();
     const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
@@ -247,7 +275,9 @@ extern "C" {
 size_t anysd_groupnorm_workspace_bytes(int N, int G, int C) {
     (void)C;
     if (N <= 0 || G <= 0) return 0;
-    return (size_t)N * GN_MAX_SPLITS * G * 2 * sizeof(float);
+    // partials [N, 64, G, 2] | mean/rstd [N, G, 2] | per-image completion counters [N] (must be zero on first use:
+    // the caller zero-fills the workspace once; every launch re-arms them)
+    return (size_t)N * GN_MAX_SPLITS * G * 2 * sizeof(float) + (size_t)N * G * 2 * sizeof(float) + (size_t)N * sizeof(unsigned int);
 }
 
 int anysd_groupnorm_nhwc_f16(const void* x1, int C1, const void* x2, int C2, const float* gamma, const float* beta,
@@ -277,12 +307,15 @@ int anysd_groupnorm_nhwc_f16(const void* x1, int C1, const void* x2, int C2, con
         cudaError_t e = cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         ANYSD_REQUIRE(e == cudaSuccess, ANYSD_ECUDA, "groupnorm: smem opt-in failed: %s", cudaGetErrorString(e));
     }
-    gn_stats_kernel<<<dim3(S, N), g.T, smem, st>>>((const uint4*)x1, (const uint4*)x2, g.CV, g.CV1, g.R, HW, rpb, G, cpg,
-                                                   (float*)workspace);
+    float* partials = (float*)workspace;
+    float* meanrstd = partials + (size_t)N * GN_MAX_SPLITS * G * 2;
+    unsigned int* counters = (unsigned int*)(meanrstd + (size_t)N * G * 2);
+    gn_stats_kernel<<<dim3(S, N), g.T, smem, st>>>((const uint4*)x1, (const uint4*)x2, g.CV, g.CV1, g.R, HW, rpb, G, cpg, eps,
+                                                   partials, meanrstd, counters);
     int rc = check_launch("groupnorm stats");
     if (rc) return rc;
-    gn_apply_kernel<<<dim3(S, N), g.T, 0, st>>>((const uint4*)x1, (const uint4*)x2, g.CV, g.CV1, g.R, HW, rpb, G, cpg, S,
-                                                (const float*)workspace, gamma, beta, eps, fuse_silu, (uint4*)y);
+    gn_apply_kernel<<<dim3(S, N), g.T, 0, st>>>((const uint4*)x1, (const uint4*)x2, g.CV, g.CV1, g.R, HW, rpb, G, cpg,
+                                                meanrstd, gamma, beta, fuse_silu, (uint4*)y);
     return check_launch("groupnorm apply");
 }
 

@@ -132,7 +132,7 @@ def router_gate(table, idx, W, bias, gate):
 
 def groupnorm_workspace(N, G=32, C=0, device="cuda"):
     nbytes = _lib.load().anysd_groupnorm_workspace_bytes(N, G, C)
-    return torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+    return torch.zeros(nbytes // 4, dtype=torch.float32, device=device)   # completion counters start at zero
 
 
 def groupnorm(x1, gamma, beta, y, N, HW, eps, silu, ws, x2=None, G=32):
