@@ -20,7 +20,7 @@
 
 namespace anysd {
 
-constexpr int AT_BQ = 128, AT_BKV = 128, AT_THREADS = 192, AT_ATOM = 128 * 128;   // 16 KB atom: 128 rows x 64 halves
+constexpr int AT_BQ = 128, AT_THREADS = 192, AT_ATOM = 128 * 128;   // 16 KB atom: 128 rows x 64 halves
 
 struct AtArgs {
     __half* out;
@@ -118,19 +118,6 @@ __device__ __forceinline__ float a_ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], near-minimax cubic for
-// 2^f (max rel. err 7.6e-5, below the 4.9e-4 rounding of the fp16 P it feeds), exponent patched by integer add.
-// Used for a fixed fraction of the scores so that the exp work is shared between the XU pipe (MUFU.EX2,
-// 16/clk/SM -- the measured bottleneck at d = 40) and the under-used FMA pipe.
-__device__ __forceinline__ float a_ex2_poly(float x) {
-    x = fmaxf(x, -125.0f);
-    const float xr = x + 12582912.0f;                 // 1.5 * 2^23: integer part lands in the low mantissa bits
-    const float f = x - (xr - 12582912.0f);
-    float p = fmaf(0.05520551f, f, 0.24261396f);
-    p = fmaf(p, f, 0.69325476f);
-    p = fmaf(p, f, 0.99992773f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
-}
 // K-major SW128 operand (rows 128 B apart inside an atom, 8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t a_desc_k(uint32_t addr) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -141,8 +128,11 @@ __device__ __forceinline__ uint64_t a_desc_mn(uint32_t addr, uint32_t lbo_bytes)
            (2ull << 61);
 }
 
-template <int EMU>    // EMU of every 8 scores take the polynomial exp2
-__global__ void __launch_bounds__(AT_THREADS, 2)
+// BKV = kv rows per tile.  128: 2 CTAs/SM (TMEM 256 columns each).  64: S + O fit 128 TMEM columns, ~100 registers
+// and 56 KB smem per CTA -> 3 CTAs/SM = 12 softmax warps per SM, which is what the latency-bound exp/max/pack
+// stream of the d = 40, 4096-token level needs (ncu: XU 64 %, issue 46 %, top stall "wait").
+template <int BKV>
+__global__ void __launch_bounds__(AT_THREADS, BKV == 64 ? 3 : 2)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AtArgs p) {
     // 128B-swizzled tiles need a 1024-byte aligned base; the dynamic smem window of a kernel without static
@@ -152,10 +142,12 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (base & 1023u) __trap();
     unsigned char* smem = at_smem_raw;
     const int NA = p.NA, ST = p.stages;
+    constexpr int KV_ATOM = BKV * 128;                          // bytes of one [BKV x 64] K/V atom
+    constexpr int AT_BKV = BKV;
     const uint32_t q_off = 0;
-    const uint32_t kv_off = NA * AT_ATOM;                       // stage s: K at kv_off + s*2*NA*ATOM, V right after K
-    const uint32_t p_off = kv_off + ST * 2 * NA * AT_ATOM;      // P: 2 atoms
-    const uint32_t bar_off = p_off + 2 * AT_ATOM;
+    const uint32_t kv_off = NA * AT_ATOM;                       // stage s: K at kv_off + s*2*NA*KV_ATOM, V right after K
+    const uint32_t p_off = kv_off + ST * 2 * NA * KV_ATOM;      // P: BKV/64 atoms of [128 x 64]
+    const uint32_t bar_off = p_off + (BKV / 64) * AT_ATOM;
     const uint32_t bars = base + bar_off;
     // barriers: 0 q_full | 1,2 kv_full | 3,4 kv_empty | 5 s_full | 6 s_free | 7 p_full | 8 o_done
     auto BAR = [&](int i) { return bars + 8u * i; };
@@ -189,7 +181,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     __syncthreads();
     a_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
+    const uint32_t tmem_S = tmem, tmem_O = tmem + BKV;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -200,10 +192,10 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             for (int j = 0; j < nt; ++j) {
                 const int s = j % ST;
                 am_wait_relaxed(BAR(3 + s), (((uint32_t)j / ST) & 1) ^ 1);
-                am_expect_tx(BAR(1 + s), 2 * NA * AT_ATOM);
-                const uint32_t kb = base + kv_off + s * 2 * NA * AT_ATOM, vb = kb + NA * AT_ATOM;
-                for (int a = 0; a < NA; ++a) a_tma_2d(kb + a * AT_ATOM, &tmK, BAR(1 + s), col0 + a * 64, b * p.n_kv + j * AT_BKV);
-                for (int a = 0; a < NA; ++a) a_tma_2d(vb + a * AT_ATOM, &tmV, BAR(1 + s), col0 + a * 64, b * p.n_kv + j * AT_BKV);
+                am_expect_tx(BAR(1 + s), 2 * NA * KV_ATOM);
+                const uint32_t kb = base + kv_off + s * 2 * NA * KV_ATOM, vb = kb + NA * KV_ATOM;
+                for (int a = 0; a < NA; ++a) a_tma_2d(kb + a * KV_ATOM, &tmK, BAR(1 + s), col0 + a * 64, b * p.n_kv + j * AT_BKV);
+                for (int a = 0; a < NA; ++a) a_tma_2d(vb + a * KV_ATOM, &tmV, BAR(1 + s), col0 + a * 64, b * p.n_kv + j * AT_BKV);
             }
         }
     } else if (warp == 1) {
@@ -214,10 +206,10 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                                      ((uint32_t)(AT_BQ >> 4) << 24);
             const int ksteps = p.d_ext / 16;
             auto issue_S = [&](int j) {
-                const uint32_t kb = base + kv_off + (j % ST) * 2 * NA * AT_ATOM;
+                const uint32_t kb = base + kv_off + (j % ST) * 2 * NA * KV_ATOM;
                 for (int k = 0; k < ksteps; ++k) {
-                    const uint32_t off = (k >> 2) * AT_ATOM + (k & 3) * 32;
-                    a_umma(tmem_S, a_desc_k(base + q_off + off), a_desc_k(kb + off), idesc_s, k ? 1u : 0u);
+                    const uint32_t qo = (k >> 2) * AT_ATOM + (k & 3) * 32, ko = (k >> 2) * KV_ATOM + (k & 3) * 32;
+                    a_umma(tmem_S, a_desc_k(base + q_off + qo), a_desc_k(kb + ko), idesc_s, k ? 1u : 0u);
                 }
                 a_commit(BAR(5));
             };
@@ -235,10 +227,10 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 }
                 am_wait_relaxed(BAR(7), j & 1);                           // P(j) written (and O rescaled)
                 a_fence_after();
-                const uint32_t vb = base + kv_off + (j % ST) * 2 * NA * AT_ATOM + NA * AT_ATOM;
+                const uint32_t vb = base + kv_off + (j % ST) * 2 * NA * KV_ATOM + NA * KV_ATOM;
                 for (int k = 0; k < AT_BKV / 16; ++k) {
                     const uint32_t poff = (k >> 2) * AT_ATOM + (k & 3) * 32;
-                    a_umma(tmem_O, a_desc_k(base + p_off + poff), a_desc_mn(vb + k * 2048, AT_ATOM), idesc_o, (j | k) ? 1u : 0u);
+                    a_umma(tmem_O, a_desc_k(base + p_off + poff), a_desc_mn(vb + k * 2048, KV_ATOM), idesc_o, (j | k) ? 1u : 0u);
                 }
                 a_commit(BAR(8));                 // O(j) accumulated, P free
                 a_commit(BAR(3 + (j % ST)));      // K/V stage free
@@ -260,10 +252,10 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int j = 0; j < nt; ++j) {
             am_wait(BAR(5), j & 1);
             a_fence_after();
-            uint32_t sr[128];
+            uint32_t sr[BKV];
             __syncwarp();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) a_ld32(tmem_S + lane_addr + c * 32, sr + c * 32);
+            for (int c = 0; c < BKV / 32; ++c) a_ld32(tmem_S + lane_addr + c * 32, sr + c * 32);
             a_wait_ld();
             a_fence_before();
             __syncwarp();
@@ -274,7 +266,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 // four independent chains (a single running max is a 128-deep dependent chain)
                 float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 128; i += 8) {
+                for (int i = 0; i < BKV; i += 8) {
                     m0 = fmaxf(m0, fmaxf(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])));
                     m1 = fmaxf(m1, fmaxf(__uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3])));
                     m2 = fmaxf(m2, fmaxf(__uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5])));
@@ -283,7 +275,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
             } else {
 #pragma unroll
-                for (int i = 0; i < 128; ++i) {
+                for (int i = 0; i < BKV; ++i) {
                     float v = (i < kv_left) ? __uint_as_float(sr[i]) : -INFINITY;
                     sr[i] = __float_as_uint(v);
                     mx = fmaxf(mx, v);
@@ -296,14 +288,11 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const float corr = upd ? a_ex2(m_run - m_new) : 1.0f;    // first tile: ex2(-inf) = 0
             m_run = m_new;
             float sum = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-            uint32_t pk[64];
+            uint32_t pk[BKV / 2];
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                const float x0 = fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, -m_new);
-                const float x1 = fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, -m_new);
-                // elements (2i, 2i+1) within each group of 8: the first EMU go to the polynomial
-                const float p0 = (((2 * i) & 7) < EMU) ? a_ex2_poly(x0) : a_ex2(x0);
-                const float p1 = (((2 * i + 1) & 7) < EMU) ? a_ex2_poly(x1) : a_ex2(x1);
+            for (int i = 0; i < BKV / 2; ++i) {
+                const float p0 = a_ex2(fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, -m_new));
+                const float p1 = a_ex2(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, -m_new));
                 if ((i & 3) == 0) sum += p0 + p1;          // four independent accumulation chains
                 else if ((i & 3) == 1) sum1 += p0 + p1;
                 else if ((i & 3) == 2) sum2 += p0 + p1;
@@ -330,7 +319,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 a_wait_st();
             }
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {                    // 16 chunks of 8 halves; chunk c lives in atom c/8
+            for (int c = 0; c < BKV / 8; ++c) {               // chunks of 8 halves; chunk c lives in atom c/8
                 uint4 u = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                 *reinterpret_cast<uint4*>(prow + (c >> 3) * AT_ATOM + (((c & 7) ^ (row & 7)) << 4)) = u;
             }
@@ -395,10 +384,10 @@ static EncodeTiledFnA a_get_encode() {
     }
     return fn;
 }
-static bool a_map(CUtensorMap* tm, const void* ptr, uint64_t width, uint64_t rows, uint64_t ld) {
+static bool a_map(CUtensorMap* tm, const void* ptr, uint64_t width, uint64_t rows, uint64_t ld, uint32_t box_rows) {
     cuuint64_t dims[2] = {width, rows};
     cuuint64_t strides[1] = {ld * 2};
-    cuuint32_t box[2] = {64, 128};
+    cuuint32_t box[2] = {64, box_rows};
     cuuint32_t es[2] = {1, 1};
     return a_get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -429,46 +418,46 @@ int launch_attention_tc5(const anysd_attn_params* q, cudaStream_t st) {
     a.n_q = q->n_q; a.n_kv = q->n_kv; a.d = q->d; a.hs = hs;
     a.d_ext = (q->d + 15) / 16 * 16;
     a.NA = (a.d_ext + 63) / 64;
-    a.stages = a.NA <= 2 ? 2 : 1;
-    a.tmem_cols = (128 + a.d_ext) <= 256 ? 256 : 512;
+    // kv tile [measured, B200]: 128 rows for the long small-head case (d = 40, 4096 tokens: 835 us vs 942 us),
+    // 64 rows elsewhere (d = 80 @1024: 121 vs 133 us; 77-token cross attention: 70 vs 83 us)
+    static const char* bkv_env = getenv("ANYSD_ATTN_BKV");
+    int bkv = (a.d_ext <= 64 && q->n_kv >= 1024) ? 128 : 64;
+    if (bkv_env) bkv = atoi(bkv_env) == 64 ? 64 : 128;
+    a.stages = (bkv == 64 || a.NA <= 2) ? 2 : 1;
+    int need_cols = bkv + a.d_ext;
+    a.tmem_cols = 32;
+    while (a.tmem_cols < need_cols) a.tmem_cols <<= 1;
     a.scale_log2 = q->scale * 1.4426950408889634f;
     a.gate = q->gate; a.gate_stride = q->gate_stride; a.accumulate = q->accumulate;
     CUtensorMap tmQ, tmK, tmV;
     const uint64_t width = (uint64_t)(q->heads - 1) * hs + q->d;     // valid columns from the slice pointer
-    bool ok = a_map(&tmQ, q->q, width, (uint64_t)q->B * q->n_q, q->ld_q) &&
-              a_map(&tmK, q->k, width, (uint64_t)q->B * q->n_kv, q->ld_k) &&
-              a_map(&tmV, q->v, width, (uint64_t)q->B * q->n_kv, q->ld_v);
+    bool ok = a_map(&tmQ, q->q, width, (uint64_t)q->B * q->n_q, q->ld_q, 128) &&
+              a_map(&tmK, q->k, width, (uint64_t)q->B * q->n_kv, q->ld_k, bkv) &&
+              a_map(&tmV, q->v, width, (uint64_t)q->B * q->n_kv, q->ld_v, bkv);
     if (!ok) {
         set_error("attention (tcgen05): cuTensorMapEncodeTiled failed (B=%d n_q=%d n_kv=%d d=%d)", q->B, q->n_q, q->n_kv, q->d);
         return ANYSD_ECUDA;
     }
-    const int smem = (a.NA + a.stages * 2 * a.NA + 2) * AT_ATOM + 128;
-    static int attr_set[64];
+    const int smem = a.NA * AT_ATOM + a.stages * 2 * a.NA * bkv * 128 + (bkv / 64) * AT_ATOM + 128;
+    static int attr_set[64][2];
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    if (attr_set[dev] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(attention_tc5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc5_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc5_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int vi = bkv == 64 ? 1 : 0;
+    if (attr_set[dev][vi] < smem) {
+        cudaError_t e = bkv == 64 ? cudaFuncSetAttribute(attention_tc5_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                  : cudaFuncSetAttribute(attention_tc5_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             set_error("attention (tcgen05): smem opt-in failed: %s", cudaGetErrorString(e));
             return ANYSD_ECUDA;
         }
-        attr_set[dev] = smem;
+        attr_set[dev][vi] = smem;
     }
     dim3 grid(cdiv(q->n_q, AT_BQ), q->heads, q->B);
-    // exp2 split between MUFU and the FMA-pipe polynomial: matters when the kernel is exp-bound (small d)
-    static const char* emu_env = getenv("ANYSD_ATTN_EMU");
-    int emu = 0;   // measured on B200: the kernel is latency-, not MUFU-bound; the polynomial split does not pay (yet)
-    if (emu_env) emu = atoi(emu_env);
-    switch (emu) {
-        case 2: attention_tc5_kernel<2><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a); break;
-        case 3: attention_tc5_kernel<3><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a); break;
-        case 4: attention_tc5_kernel<4><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a); break;
-        default: attention_tc5_kernel<0><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a); break;
-    }
+    if (bkv == 64)
+        attention_tc5_kernel<64><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a);
+    else
+        attention_tc5_kernel<128><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a);
     return check_launch("attention (tcgen05)");
 }
 
