@@ -230,7 +230,7 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * P_STAGES + 2 + b); };
     auto res_bar = [&](int b) { return bar_base + 8u * (2 * P_STAGES + 4 + b); };
     volatile uint32_t* tmem_slot =
-        reinterpret_cast<volatile uint32_t*>(smem + P_STAGES * P_STAGE_BYTES + P_NSTG * P_STG_BYTES + 8 * (2 * P_STAGES + 4 + P_NSTG));
+        reinterpret_cast<volatile uint32_t*>(smem + P_STAGES * P_STAGE_BYTES + P_NSTG * P_STG_BYTES + 8 * (2 * P_STAGES + 4 + 16));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -249,7 +249,7 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             pm_init(tfull_bar(b), 1);
             pm_init(tempty_bar(b), 8 * CTAS);   // one arrive per epilogue warp of every CTA of the pair
         }
-        for (int b = 0; b < P_NSTG; ++b) pm_init(res_bar(b), 1);
+        for (int b = 0; b < 16; ++b) pm_init(res_bar(b), 1);      // 8 epilogue warps x 2 residual slabs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -336,28 +336,49 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: 8 warps.  TMEM lane group = warp % 4 (hardware rule), thread = one accumulator row;
-        // warps 4..7 take output columns 0..31 of every 64-column sub-tile, warps 8..11 columns 32..63 =====
-        const int lg = warp & 3;
-        const int half = (warp - 4) >> 2;
+        // ===== epilogue: 8 INDEPENDENT warps (no CTA-wide barriers).  TMEM lane group = warp % 4 (hardware rule),
+        // lane = accumulator row.  Warps 4..7 take the even 64-column sub-tiles, warps 8..11 the odd ones.  Each warp
+        // owns two 4 KB staging slabs [32 rows x 64 cols, 128B swizzle]: lane 0 TMA-prefetches the residual slab of
+        // the warp's NEXT sub-tile while the current one is combined in place and TMA-stored. =====
+        const int ew = warp - 4, lg = warp & 3, set = ew >> 2;
         const int row = lg * 32 + lane;
-        const bool elected = (warp == 4 && lane == 0);
-        uint32_t t = 0, q = 0;                                // tile counter, global sub-tile counter
+        constexpr uint32_t SLAB = 32 * 128;                                  // bytes
+        const uint32_t wstg = stg_base + ew * 2 * SLAB;
+        unsigned char* wstg_ptr = smem + P_STAGES * P_STAGE_BYTES + ew * 2 * SLAB;
+        auto rbar = [&](uint32_t b) { return res_bar(0) + 8u * (ew * 2 + b); };
         const int acc_per_sub = (p.act == 2) ? 2 * P_SUB : P_SUB;   // accumulator columns feeding one 64-column store
+        int sdx = 0, sdy = 0, sdn = 0;                               // slab origin inside a conv patch
+        if (CONV) {
+            const int r0 = lg * 32;
+            sdx = r0 % p.BW;
+            sdy = (r0 / p.BW) % p.BH;
+            sdn = r0 / (p.BW * p.BH);
+        }
+        auto nsub_of = [&](const TileCoord& c) { return (c.nw + acc_per_sub - 1) / acc_per_sub; };
+        auto slab_load = [&](uint32_t b, const TileCoord& c, int j) {        // residual slab -> staging buffer b
+            const int col = ((p.act == 2) ? (c.n0 >> 1) : c.n0) + j * P_SUB;
+            pm_expect_tx(rbar(b), SLAB);
+            if (CONV) p_tma_load_4d(wstg + b * SLAB, &tmR, rbar(b), col, c.tw * p.BW + sdx, c.th * p.BH + sdy, c.tn * p.NB + sdn);
+            else p_tma_load_2d(wstg + b * SLAB, &tmR, rbar(b), col, c.m0 + lg * 32);
+        };
+        auto slab_store = [&](uint32_t b, const TileCoord& c, int j) {
+            const int col = ((p.act == 2) ? (c.n0 >> 1) : c.n0) + j * P_SUB;
+            if (CONV) p_tma_store_4d(&tmO, wstg + b * SLAB, col, c.tw * p.BW + sdx, c.th * p.BH + sdy, c.tn * p.NB + sdn);
+            else p_tma_store_2d(&tmO, wstg + b * SLAB, col, c.m0 + lg * 32);
+            p_store_commit();
+        };
+        // this warp's first slab: residual prefetch before anything else
+        uint32_t t = 0, q = 0;                                // tile counter, per-warp slab counter
+        if (p.has_res && lane == 0) {
+            for (int tl = cta_first; tl < p.num_tiles; tl += cta_stride) {
+                const TileCoord c0 = tile_coord<CONV, CTAS>(p, tl, rank);
+                if (set < nsub_of(c0)) { slab_load(0, c0, set); break; }
+            }
+        }
         for (int tile = cta_first; tile < p.num_tiles; tile += cta_stride, ++t) {
             const TileCoord c = tile_coord<CONV, CTAS>(p, tile, rank);
             const uint32_t buf = t & 1, bph = (t >> 1) & 1;
-            const int nsub = (c.nw + acc_per_sub - 1) / acc_per_sub;
-            const int out_c0 = (p.act == 2) ? (c.n0 >> 1) : c.n0;   // first output column of the tile
-            // output / residual coordinates of sub-tile j
-            auto issue_res = [&](int j) {
-                const uint32_t b = (q + j) % P_NSTG;
-                pm_expect_tx(res_bar(b), P_STG_BYTES);
-                if (CONV)
-                    p_tma_load_4d(stg_base + b * P_STG_BYTES, &tmR, res_bar(b), out_c0 + j * P_SUB, c.tw * p.BW, c.th * p.BH, c.tn * p.NB);
-                else
-                    p_tma_load_2d(stg_base + b * P_STG_BYTES, &tmR, res_bar(b), out_c0 + j * P_SUB, c.m0);
-            };
+            const int nsub = nsub_of(c);
             int img = 0;
             if (p.rowadd) {
                 if (CONV) {
@@ -370,23 +391,28 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
             const float* radd = p.rowadd ? p.rowadd + (size_t)img * p.ld_rowadd : nullptr;
-            if (elected && p.has_res) {
-                p_store_wait_read<1>();                        // buffers of the first two sub-tiles are free
-                issue_res(0);
-                if (nsub > 1) issue_res(1);
-            }
             pm_wait(tfull_bar(buf), bph);
             p_fence_after();
-            for (int j = 0; j < nsub; ++j) {
-                const uint32_t b = (q + j) % P_NSTG;
-                if (elected) {
-                    p_store_wait_read<1>();                    // every store but the latest has released its buffer
-                    if (p.has_res && j + 2 < nsub) issue_res(j + 2);
+            for (int j = set; j < nsub; j += 2, ++q) {
+                const uint32_t b = q & 1;
+                if (lane == 0) {
+                    p_store_wait_read<0>();                    // the previous slab's store has released buffer b^1
+                    if (p.has_res) {                           // prefetch the residual of this warp's next slab
+                        if (j + 2 < nsub) {
+                            slab_load(b ^ 1, c, j + 2);
+                        } else {
+                            for (int tl = tile + cta_stride; tl < p.num_tiles; tl += cta_stride) {
+                                const TileCoord c2 = tile_coord<CONV, CTAS>(p, tl, rank);
+                                if (set < nsub_of(c2)) { slab_load(b ^ 1, c2, set); break; }
+                            }
+                        }
+                    }
                 }
-                p_epi_bar();                                   // staging buffer b is free for everyone
-                unsigned char* stg = smem + P_STAGES * P_STAGE_BYTES + b * P_STG_BYTES + row * 128;
-                if (p.has_res) pm_wait(res_bar(b), ((q + j) / P_NSTG) & 1);
-                {
+                __syncwarp();
+                unsigned char* stg = wstg_ptr + b * SLAB + lane * 128;
+                if (p.has_res) pm_wait(rbar(b), (q >> 1) & 1);
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {         // 2 x 32 output columns
                     float v[32];
                     const int oc = half * 32;                  // output column offset inside the sub-tile
                     if (p.act == 2) {
@@ -460,7 +486,7 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int ch = 0; ch < 4; ++ch) {
                         const int chunk = (oc >> 3) + ch;       // 16-byte chunk index 0..7 in the 128-byte row
-                        uint4* slot = reinterpret_cast<uint4*>(stg + ((chunk ^ (row & 7)) << 4));
+                        uint4* slot = reinterpret_cast<uint4*>(stg + ((chunk ^ (lane & 7)) << 4));
                         float* vv = v + ch * 8;
                         if (p.has_res) {
                             float rr[8];
@@ -472,24 +498,17 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
                 p_fence_async_smem();                          // generic-proxy writes -> visible to the TMA store
-                p_epi_bar();
-                if (elected) {
-                    if (CONV)
-                        p_tma_store_4d(&tmO, stg_base + b * P_STG_BYTES, out_c0 + j * P_SUB, c.tw * p.BW, c.th * p.BH, c.tn * p.NB);
-                    else
-                        p_tma_store_2d(&tmO, stg_base + b * P_STG_BYTES, out_c0 + j * P_SUB, c.m0);
-                    p_store_commit();
-                }
+                __syncwarp();
+                if (lane == 0) slab_store(b, c, j);
             }
-            q += nsub;
-            // accumulator fully read: hand the TMEM buffer back to the MMA warp
+            // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
             p_fence_before();
             __syncwarp();
             if (lane == 0) {
                 if (CTAS == 2) pm_arrive_remote(tempty_bar(buf), 0); else pm_arrive(tempty_bar(buf));
             }
         }
-        if (elected) p_store_wait<0>();                        // smem must outlive the last store
+        if (lane == 0) p_store_wait<0>();                      // smem must outlive the last store
     }
     p_fence_before();
     __syncthreads();
@@ -653,13 +672,15 @@ int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
         a.kb_per_tap = q->Cin / P_BK;
         a.num_kb = 9 * a.kb_per_tap;
         ok = ok && p_map_nhwc(&tmA, img, q->Nimg, Hin, Win, q->Cin, q->Cin, a.BW, a.BH, a.NB, a.stride);
-        ok = ok && p_map_nhwc(&tmO, q->out, q->Nimg, a.Ho, a.Wo, n_out, q->ldo, a.BW, a.BH, a.NB, 1);
-        if (q->residual) ok = ok && p_map_nhwc(&tmR, q->residual, q->Nimg, a.Ho, a.Wo, n_out, q->ldr, a.BW, a.BH, a.NB, 1);
+        // output / residual move in 32-pixel slabs of the 128-pixel patch (one per epilogue warp)
+        const int sw = a.BW < 32 ? a.BW : 32, sh = (32 / sw) < a.BH ? (32 / sw) : a.BH, sn = 32 / (sw * sh);
+        ok = ok && p_map_nhwc(&tmO, q->out, q->Nimg, a.Ho, a.Wo, n_out, q->ldo, sw, sh, sn, 1);
+        if (q->residual) ok = ok && p_map_nhwc(&tmR, q->residual, q->Nimg, a.Ho, a.Wo, n_out, q->ldr, sw, sh, sn, 1);
     } else {
         a.tiles_m = cdiv(q->M, P_BM);
         ok = ok && p_map_2d(&tmA, q->A, (uint64_t)q->K, (uint64_t)q->M, (uint64_t)q->lda, P_BK, P_BM);
-        ok = ok && p_map_2d(&tmO, q->out, (uint64_t)n_out, (uint64_t)q->M, (uint64_t)q->ldo, P_SUB, P_BM);
-        if (q->residual) ok = ok && p_map_2d(&tmR, q->residual, (uint64_t)n_out, (uint64_t)q->M, (uint64_t)q->ldr, P_SUB, P_BM);
+        ok = ok && p_map_2d(&tmO, q->out, (uint64_t)n_out, (uint64_t)q->M, (uint64_t)q->ldo, P_SUB, 32);
+        if (q->residual) ok = ok && p_map_2d(&tmR, q->residual, (uint64_t)n_out, (uint64_t)q->M, (uint64_t)q->ldr, P_SUB, 32);
     }
     // Tile shape selection.  Candidates: CTA pairs (cta_group::2, 256-row tiles, less L2 traffic per FLOP) or
     // single CTAs, tile width 256 / 128 / 64 (GEGLU pairs need >= 128).  Cost model = scheduling rounds on the
