@@ -694,7 +694,10 @@ int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
         for (int c = 2; c >= 1; --c) {
             if (c == 2 && (a.tiles_m < 2 || sm_count() < 2)) continue;
             if (force && (force[0] == '1' || force[0] == '2') && c != force[0] - '0') continue;
-            for (int w = 256; w >= (q->act == 2 ? 128 : 64); w >>= 1) {
+            static const int widths[4] = {256, 192, 128, 64};     // 192 balances N = 320 (192 + 128) and divides 960 / 1920
+            for (int wi = 0; wi < 4; ++wi) {
+                const int w = widths[wi];
+                if (w < (q->act == 2 ? 128 : 64) || (q->act == 2 && w == 192)) continue;
                 if (force_bn && atoi(force_bn) != w) continue;
                 const long tiles = (long)cdiv(a.tiles_m, c) * cdiv(q->N, w);
                 const long rounds = (tiles + sm_count() / c - 1) / (sm_count() / c);
