@@ -24,14 +24,14 @@ __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, __half* __restric
 }
 
 template <typename S, typename T>
-__global__ void nhwc_to_nchw_kernel(const S* __restrict__ src, T* __restrict__ dst, int C, int HW) {
+__global__ void nhwc_to_nchw_kernel(const S* __restrict__ src, T* __restrict__ dst, int C, int HW, int src_ld) {
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const S* s = src + (size_t)n * HW * C;
+    const S* s = src + (size_t)n * HW * src_ld;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int hw = hw0 + i, c = c0 + threadIdx.x;
-        if (c < C && hw < HW) tile[i][threadIdx.x] = (float)s[(size_t)hw * C + c];
+        if (c < C && hw < HW) tile[i][threadIdx.x] = (float)s[(size_t)hw * src_ld + c];
     }
     __syncthreads();
     T* d = dst + (size_t)n * C * HW;
@@ -184,23 +184,23 @@ int anysd_nchw_to_nhwc_f16(const void* src, int src_dtype, void* dst, int N, int
     return check_launch("nchw_to_nhwc");
 }
 
-int anysd_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, int N, int C, int H, int W,
+int anysd_nhwc_to_nchw(const void* src, int src_dtype, int src_C, void* dst, int dst_dtype, int N, int C, int H, int W,
                        anysd_stream_t stream) {
     ANYSD_REQUIRE(src && dst, ANYSD_EINVAL, "nhwc_to_nchw: null pointer");
-    ANYSD_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0, ANYSD_EINVAL, "nhwc_to_nchw: bad shape");
+    ANYSD_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && src_C >= C, ANYSD_EINVAL, "nhwc_to_nchw: bad shape");
     ANYSD_REQUIRE((dst_dtype == ANYSD_F32 || dst_dtype == ANYSD_F16) && (src_dtype == ANYSD_F32 || src_dtype == ANYSD_F16),
                   ANYSD_EINVAL, "nhwc_to_nchw: bad dtype");
     const int HW = H * W;
     dim3 grid(cdiv(HW, 32), cdiv(C, 32), N), block(32, 8);
     cudaStream_t st = (cudaStream_t)stream;
     if (src_dtype == ANYSD_F16 && dst_dtype == ANYSD_F32)
-        nhwc_to_nchw_kernel<__half, float><<<grid, block, 0, st>>>((const __half*)src, (float*)dst, C, HW);
+        nhwc_to_nchw_kernel<__half, float><<<grid, block, 0, st>>>((const __half*)src, (float*)dst, C, HW, src_C);
     else if (src_dtype == ANYSD_F16)
-        nhwc_to_nchw_kernel<__half, __half><<<grid, block, 0, st>>>((const __half*)src, (__half*)dst, C, HW);
+        nhwc_to_nchw_kernel<__half, __half><<<grid, block, 0, st>>>((const __half*)src, (__half*)dst, C, HW, src_C);
     else if (dst_dtype == ANYSD_F32)
-        nhwc_to_nchw_kernel<float, float><<<grid, block, 0, st>>>((const float*)src, (float*)dst, C, HW);
+        nhwc_to_nchw_kernel<float, float><<<grid, block, 0, st>>>((const float*)src, (float*)dst, C, HW, src_C);
     else
-        nhwc_to_nchw_kernel<float, __half><<<grid, block, 0, st>>>((const float*)src, (__half*)dst, C, HW);
+        nhwc_to_nchw_kernel<float, __half><<<grid, block, 0, st>>>((const float*)src, (__half*)dst, C, HW, src_C);
     return check_launch("nhwc_to_nchw");
 }
 

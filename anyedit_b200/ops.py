@@ -78,12 +78,12 @@ def nchw_to_nhwc(src, dst, c_off=0):
 
 
 def nhwc_to_nchw(src, dst):
-    """src NHWC f16|f32 [N,H,W,C] -> dst NCHW f32|f16 [N,C,H,W]."""
+    """src NHWC f16|f32 [N,H,W,Cs] (first C channels used) -> dst NCHW f32|f16 [N,C,H,W]."""
     _cuda(src, dst)
     N, Cc, H, W = dst.shape
-    assert src.is_contiguous() and dst.is_contiguous()
-    _lib.check(_lib.load().anysd_nhwc_to_nchw(_ptr(src), _DT[src.dtype], _ptr(dst), _DT[dst.dtype], N, Cc, H, W,
-                                              _stream()), "nhwc_to_nchw")
+    assert src.is_contiguous() and dst.is_contiguous() and src.shape[-1] >= Cc
+    _lib.check(_lib.load().anysd_nhwc_to_nchw(_ptr(src), _DT[src.dtype], src.shape[-1], _ptr(dst), _DT[dst.dtype], N, Cc,
+                                              H, W, _stream()), "nhwc_to_nchw")
     _count()
 
 
@@ -180,7 +180,8 @@ def gemm(A, W, out, bias=None, rowadd=None, rows_per_batch=0, residual=None, act
     _count()
 
 
-def conv3x3(x, W, out, bias=None, rowadd=None, residual=None, stride=1, upsample=0, ld_rowadd=None):
+def conv3x3(x, W, out, bias=None, rowadd=None, residual=None, stride=1, upsample=0, ld_rowadd=None,
+            logical_cin=None, logical_cout=None):
     """x NHWC fp16 [N,H,W,Cin]; W fp16 [Cout, 9*Cin] ((ky,kx,ci) K order); out [N*Ho*Wo, Cout]."""
     _cuda(x, W, out)
     Nimg, H, Wd, Cin = x.shape
@@ -205,7 +206,9 @@ def conv3x3(x, W, out, bias=None, rowadd=None, residual=None, stride=1, upsample
     if upsample:   # scratch for the materialised nearest-x2 input of the tcgen05 path
         ws = torch.empty(Nimg * Hl * Wl * Cin, dtype=torch.float16, device=x.device)
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel() * 2
-    with _Traced("conv3x3", 2.0 * p.M * p.N * p.K):
+    # algorithmic FLOPs (trace only): zero-padded channels do not count
+    fl = 2.0 * p.M * (logical_cout or p.N) * 9 * (logical_cin or Cin)
+    with _Traced("conv3x3", fl):
         _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "conv3x3")
     _count()
     return Ho, Wo

@@ -330,7 +330,9 @@ class UNetModel(nn.Module):
         P["te2_w"], P["te2_b"] = _h(te[2].weight, dev), _f(te[2].bias, dev)
         if self.num_classes is not None:
             P["label"] = _f(self.label_emb.weight, dev)
-        self._cin_pad = (self.in_channels + 7) // 8 * 8
+        # input channels padded to 64 (zeros) so that the input conv runs on the tcgen05 implicit-GEMM kernel
+        # (64-channel k-blocks); the extra MACs are on zero weights and cost ~25 us per forward
+        self._cin_pad = (self.in_channels + 63) // 64 * 64
         P["in_w"] = _pack_conv3(self.input_blocks[0][0].weight, dev, self._cin_pad)
         P["in_b"] = _f(self.input_blocks[0][0].bias, dev)
         emb_w, emb_b, off = [], [], 0
@@ -406,7 +408,14 @@ class UNetModel(nn.Module):
         P["emb_b"] = _f(torch.cat(emb_b, 0), dev)
         P["emb_total"] = off
         P["out_gn_w"], P["out_gn_b"] = _f(self.out[0].weight, dev), _f(self.out[0].bias, dev)
-        P["out_w"], P["out_b"] = _pack_conv3(self.out[2].weight, dev), _f(self.out[2].bias, dev)
+        # output conv: rows padded to a multiple of 8 (zero filters) -> tcgen05 kernel with fp32 output
+        self._cout_pad = (self.out_channels + 7) // 8 * 8
+        ow = _pack_conv3(self.out[2].weight, dev)
+        ob = _f(self.out[2].bias, dev)
+        if self._cout_pad != self.out_channels:
+            ow = torch.cat([ow, ow.new_zeros(self._cout_pad - self.out_channels, ow.shape[1])], 0).contiguous()
+            ob = torch.cat([ob, ob.new_zeros(self._cout_pad - self.out_channels)], 0).contiguous()
+        P["out_w"], P["out_b"] = ow, ob
         self._pack, self._pack_key = P, key
         return P
 
@@ -476,7 +485,7 @@ class UNetModel(nn.Module):
         xin = torch.zeros(N, H, W, self._cin_pad, **f16) if self._cin_pad != Cin else torch.empty(N, H, W, Cin, **f16)
         ops.nchw_to_nhwc(x.contiguous(), xin, 0)
         h = torch.empty(N, H, W, mc, **f16)
-        ops.conv3x3(xin, P["in_w"], h.view(-1, mc), bias=P["in_b"])
+        ops.conv3x3(xin, P["in_w"], h.view(-1, mc), bias=P["in_b"], logical_cin=Cin)
         hs = [h]
         for blk in P["input"]:
             h = self._run(blk, h, None, st)
@@ -488,8 +497,8 @@ class UNetModel(nn.Module):
         Nn, Hh, Ww, C = h.shape
         a = torch.empty_like(h)
         ops.groupnorm(h, P["out_gn_w"], P["out_gn_b"], a, N, Hh * Ww, 1e-5, True, ws)
-        o = torch.empty(N, Hh, Ww, self.out_channels, **f32)
-        ops.conv3x3(a, P["out_w"], o.view(-1, self.out_channels), bias=P["out_b"])
+        o = torch.empty(N, Hh, Ww, self._cout_pad, **f32)
+        ops.conv3x3(a, P["out_w"], o.view(-1, self._cout_pad), bias=P["out_b"], logical_cout=self.out_channels)
         out_dtype = x.dtype if x.dtype in (torch.float32, torch.float16) else torch.float32
         out = torch.empty(N, self.out_channels, Hh, Ww, dtype=out_dtype, device=dev)
         ops.nhwc_to_nchw(o, out)

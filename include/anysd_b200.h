@@ -45,8 +45,9 @@ int anysd_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * [dst_c_off, dst_c_off+C) of an NHWC fp16 tensor with dst_C channels. */
 int anysd_nchw_to_nhwc_f16(const void* src, int src_dtype, void* dst, int N, int C, int H, int W,
                            int dst_C, int dst_c_off, anysd_stream_t stream);
-/* h.type(x.dtype) on the way out (openaimodel.py:782): NHWC (f16|f32) -> NCHW (f32|f16). */
-int anysd_nhwc_to_nchw(const void* src, int src_dtype, void* dst, int dst_dtype, int N, int C, int H, int W,
+/* h.type(x.dtype) on the way out (openaimodel.py:782): NHWC (f16|f32) with src_C channels per pixel (the first C
+ * are converted) -> NCHW (f32|f16). */
+int anysd_nhwc_to_nchw(const void* src, int src_dtype, int src_C, void* dst, int dst_dtype, int N, int C, int H, int W,
                        anysd_stream_t stream);
 /* th.cat([h, hs.pop()], dim=1) (openaimodel.py:780) on NHWC rows: dst[r] = a[r] ++ b[r]. */
 int anysd_concat_channels_f16(const void* a, int Ca, const void* b, int Cb, void* dst, long long rows,
