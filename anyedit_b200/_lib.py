@@ -45,6 +45,7 @@ SIGNATURES = {
     "anysd_version": (_I, []),
     "anysd_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "anysd_nchw_to_nhwc_f16": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "anysd_add_nchw_into_nhwc_f16": (_I, [_VP, _I, _VP, _I, _I, _I, _I, _VP]),
     "anysd_nhwc_to_nchw": (_I, [_VP, _I, _I, _VP, _I, _I, _I, _I, _I, _VP]),
     "anysd_concat_channels_f16": (_I, [_VP, _I, _VP, _I, _VP, _LL, _VP]),
     "anysd_cast_f32_to_f16": (_I, [_VP, _VP, _LL, _VP]),

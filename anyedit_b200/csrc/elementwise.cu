@@ -4,7 +4,7 @@
 namespace anysd {
 
 // ---- NCHW (f32|f16) -> NHWC fp16 channel slice --------------------------------------------
-template <typename T>
+template <typename T, bool ACC>
 __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, __half* __restrict__ dst, int C, int HW,
                                     int dstC, int c_off) {
     __shared__ float tile[32][33];
@@ -19,7 +19,11 @@ __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, __half* __restric
     __half* d = dst + (size_t)n * HW * dstC + c_off;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int hw = hw0 + i, c = c0 + threadIdx.x;
-        if (c < C && hw < HW) d[(size_t)hw * dstC + c] = __float2half_rn(tile[threadIdx.x][i]);
+        if (c < C && hw < HW) {
+            float v = tile[threadIdx.x][i];
+            if (ACC) v += __half2float(d[(size_t)hw * dstC + c]);
+            d[(size_t)hw * dstC + c] = __float2half_rn(v);
+        }
     }
 }
 
@@ -176,12 +180,25 @@ int anysd_nchw_to_nhwc_f16(const void* src, int src_dtype, void* dst, int N, int
     const int HW = H * W;
     dim3 grid(cdiv(HW, 32), cdiv(C, 32), N), block(32, 8);
     if (src_dtype == ANYSD_F32)
-        nchw_to_nhwc_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)src, (__half*)dst, C, HW,
-                                                                            dst_C, dst_c_off);
+        nchw_to_nhwc_kernel<float, false><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)src, (__half*)dst, C, HW,
+                                                                                   dst_C, dst_c_off);
     else
-        nchw_to_nhwc_kernel<__half><<<grid, block, 0, (cudaStream_t)stream>>>((const __half*)src, (__half*)dst, C, HW,
-                                                                             dst_C, dst_c_off);
+        nchw_to_nhwc_kernel<__half, false><<<grid, block, 0, (cudaStream_t)stream>>>((const __half*)src, (__half*)dst, C, HW,
+                                                                                    dst_C, dst_c_off);
     return check_launch("nchw_to_nhwc");
+}
+
+int anysd_add_nchw_into_nhwc_f16(const void* src, int src_dtype, void* dst, int N, int C, int H, int W,
+                                 anysd_stream_t stream) {
+    ANYSD_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0, ANYSD_EINVAL, "add_nchw_into_nhwc: bad args");
+    ANYSD_REQUIRE(src_dtype == ANYSD_F32 || src_dtype == ANYSD_F16, ANYSD_EINVAL, "add_nchw_into_nhwc: bad dtype");
+    const int HW = H * W;
+    dim3 grid(cdiv(HW, 32), cdiv(C, 32), N), block(32, 8);
+    if (src_dtype == ANYSD_F32)
+        nchw_to_nhwc_kernel<float, true><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)src, (__half*)dst, C, HW, C, 0);
+    else
+        nchw_to_nhwc_kernel<__half, true><<<grid, block, 0, (cudaStream_t)stream>>>((const __half*)src, (__half*)dst, C, HW, C, 0);
+    return check_launch("add_nchw_into_nhwc");
 }
 
 int anysd_nhwc_to_nchw(const void* src, int src_dtype, int src_C, void* dst, int dst_dtype, int N, int C, int H, int W,

@@ -228,6 +228,45 @@ class DDIMSampler(object):
         return stepper.step(x.float().contiguous(), index, t, unconditional_guidance_scale, noise)
 
     @torch.no_grad()
+    def encode(self, x0, c, t_enc, use_original_steps=False, return_intermediates=None,
+               unconditional_guidance_scale=1.0, unconditional_conditioning=None, callback=None):
+        """DDIM inversion (ddim.py:253-299).  Same arithmetic and the same quirk as the reference (the model is
+        called with t = loop index i, not with the DDIM timestep); the per-step update
+        x_next = sqrt(a_next/a) x + sqrt(a_next) (sqrt(1/a_next - 1) - sqrt(1/a - 1)) eps runs in the fused kernel."""
+        if use_original_steps:
+            raise NotImplementedError("use_original_steps is not on the AnySD path")
+        num_reference_steps = self.ddim_timesteps.shape[0]
+        assert t_enc <= num_reference_steps
+        num_steps = t_enc
+        alphas_next = torch.as_tensor(self.ddim_alphas[:num_steps], dtype=torch.float32)
+        alphas = torch.tensor(self.ddim_alphas_prev[:num_steps])          # float64, as in the reference
+        x_next = x0.float().contiguous()
+        b = x_next.shape[0]
+        use_cfg = unconditional_guidance_scale != 1.
+        if use_cfg:
+            assert unconditional_conditioning is not None
+        stepper = self._get_stepper(c, unconditional_conditioning, use_cfg, b, tuple(x_next.shape), x_next.device,
+                                    graph=False)
+        intermediates, inter_steps = [], []
+        for i in range(num_steps):
+            c1 = (alphas_next[i] / alphas[i]).sqrt()
+            c2 = alphas_next[i].sqrt() * ((1 / alphas_next[i] - 1).sqrt() - (1 / alphas[i] - 1).sqrt())
+            coef = torch.tensor([0.0, 1.0, float(c1), float(c2), 0.0], dtype=torch.float32, device=x_next.device)
+            x_next, _ = stepper.step(x_next, None, i, unconditional_guidance_scale, None, coef=coef)
+            if return_intermediates and i % (num_steps // return_intermediates) == 0 and i < num_steps - 1:
+                intermediates.append(x_next)
+                inter_steps.append(i)
+            elif return_intermediates and i >= num_steps - 2:
+                intermediates.append(x_next)
+                inter_steps.append(i)
+            if callback:
+                callback(i)
+        out = {"x_encoded": x_next, "intermediate_steps": inter_steps}
+        if return_intermediates:
+            out.update({"intermediates": intermediates})
+        return x_next, out
+
+    @torch.no_grad()
     def stochastic_encode(self, x0, t, use_original_steps=False, noise=None):
         if use_original_steps:
             sac, somac = self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod
@@ -344,7 +383,7 @@ class _Stepper:
         eps = eps.float().contiguous()
         ops.cfg_ddim_step(self.x_buf, eps, self.coef_buf, scale, self.use_cfg, self.x_prev, self.pred_x0, noise)
 
-    def step(self, img, index, t_value, scale, noise):
+    def step(self, img, index, t_value, scale, noise, coef=None):
         s = self.s
         self.x_buf.copy_(img)
         if isinstance(t_value, torch.Tensor):
@@ -352,7 +391,7 @@ class _Stepper:
             self.t_buf.copy_(torch.cat([tv, tv]) if self.use_cfg else tv)
         else:
             self.t_buf.fill_(int(t_value))
-        self.coef_buf.copy_(s.ddim_coef[index], non_blocking=True)
+        self.coef_buf.copy_(s.ddim_coef[index] if coef is None else coef, non_blocking=True)
         if noise is not None:
             if self.noise_buf is None:
                 self.noise_buf = torch.zeros_like(self.x_buf)

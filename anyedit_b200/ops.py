@@ -77,6 +77,16 @@ def nchw_to_nhwc(src, dst, c_off=0):
     _count()
 
 
+def add_nchw_into_nhwc(src, dst):
+    """dst NHWC fp16 [N,H,W,C] += src NCHW f32|f16 [N,C,H,W] (ControlNet residuals)."""
+    _cuda(src, dst)
+    N, Cc, H, W = src.shape
+    assert tuple(dst.shape) == (N, H, W, Cc) and src.is_contiguous() and dst.is_contiguous()
+    _lib.check(_lib.load().anysd_add_nchw_into_nhwc_f16(_ptr(src), _DT[src.dtype], _ptr(dst), N, Cc, H, W, _stream()),
+               "add_nchw_into_nhwc")
+    _count()
+
+
 def nhwc_to_nchw(src, dst):
     """src NHWC f16|f32 [N,H,W,Cs] (first C channels used) -> dst NCHW f32|f16 [N,C,H,W]."""
     _cuda(src, dst)

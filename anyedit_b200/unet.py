@@ -432,7 +432,7 @@ class UNetModel(nn.Module):
         assert (y is not None) == (self.num_classes is not None), \
             "must specify y if and only if the model is class-conditional"
         if control is not None:
-            raise NotImplementedError("ControlNet residual injection is a 'next' row (SURVEY.md 8f rank 3)")
+            control = [c if c.dtype in (torch.float32, torch.float16) else c.float() for c in control]
         P = self.prepare()
         dev = x.device
         if dev.type != "cuda":
@@ -491,8 +491,13 @@ class UNetModel(nn.Module):
             h = self._run(blk, h, None, st)
             hs.append(h)
         h = self._run(P["middle"], h, None, st)
+        if control is not None:                                   # cldm.py:33-34
+            ops.add_nchw_into_nhwc(control.pop().contiguous(), h)
         for blk in P["output"]:
-            h = self._run(blk, h, hs.pop(), st)
+            skip = hs.pop()
+            if control is not None and not only_mid_control:      # cldm.py:36-41
+                ops.add_nchw_into_nhwc(control.pop().contiguous(), skip)
+            h = self._run(blk, h, skip, st)
         # -- head: GN -> SiLU -> conv3x3 (fp32 out), back to NCHW in x.dtype --
         Nn, Hh, Ww, C = h.shape
         a = torch.empty_like(h)

@@ -45,6 +45,10 @@ int anysd_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * [dst_c_off, dst_c_off+C) of an NHWC fp16 tensor with dst_C channels. */
 int anysd_nchw_to_nhwc_f16(const void* src, int src_dtype, void* dst, int N, int C, int H, int W,
                            int dst_C, int dst_c_off, anysd_stream_t stream);
+/* ControlNet residual injection, `h += control.pop()` / `hs.pop() + control.pop()` of ControlledUnetModel.forward
+ * (AnyEdit_Collection/other_modules/cldm/cldm.py:33-41): dst (NHWC fp16 [N,H,W,C]) += src (NCHW f32|f16). */
+int anysd_add_nchw_into_nhwc_f16(const void* src, int src_dtype, void* dst, int N, int C, int H, int W,
+                                 anysd_stream_t stream);
 /* h.type(x.dtype) on the way out (openaimodel.py:782): NHWC (f16|f32) with src_C channels per pixel (the first C
  * are converted) -> NCHW (f32|f16). */
 int anysd_nhwc_to_nchw(const void* src, int src_dtype, int src_C, void* dst, int dst_dtype, int N, int C, int H, int W,
