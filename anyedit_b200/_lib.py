@@ -35,6 +35,7 @@ class AttnParams(C.Structure):
         ("B", C.c_int), ("heads", C.c_int), ("n_q", C.c_int), ("n_kv", C.c_int), ("d", C.c_int),
         ("scale", C.c_float), ("gate", C.c_void_p), ("gate_stride", C.c_int), ("accumulate", C.c_int),
         ("head_stride", C.c_int),
+        ("aux_cols", C.c_int),
     ]
 
 

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .unet import UNetModel, _Param, head_stride_for, pad_heads
+from .unet import UNetModel, _Param, aux_bias, aux_cols_for, head_stride_for, pad_heads
 
 
 class _Adapter(nn.Module):
@@ -87,7 +87,10 @@ class MoE(nn.Module):
             wv = torch.stack([pad_heads(wv[e], heads, dh, hs) for e in range(E)], 0)
             # rows: expert-major, [K_e ; V_e] per expert -> one GEMM gives [.., e*2Cp : e*2Cp+Cp] = K_e
             kv = torch.stack([wk, wv], 1).reshape(E * 2 * cp, -1)
-            P["layers"].append({"c": c, "cp": cp, "kv_w": kv.to(dev, torch.float16).contiguous()})
+            # same operand contract as the UNet's own cross attention (the experts reuse its q): see unet.aux_cols_for
+            kv_b = torch.cat([aux_bias(heads, dh, hs, 2), aux_bias(heads, dh, hs, 1)]).repeat(E).to(dev) \
+                if aux_cols_for(dh) else None
+            P["layers"].append({"c": c, "cp": cp, "kv_w": kv.to(dev, torch.float16).contiguous(), "kv_b": kv_b})
         P["router_w"] = torch.stack([ad.router.weight.detach() for ad in self.adapter_modules], 0).to(
             dev, torch.float16).contiguous()                                   # [L, E, D]
         P["router_b"] = torch.stack([ad.router.bias.detach() for ad in self.adapter_modules], 0).to(
@@ -116,16 +119,16 @@ class MoE(nn.Module):
             gates = torch.empty(N, nl, E, dtype=torch.float32, device=dev)
             ops.router_gate(P["task"], edit_code, P["router_w"], P["router_b"], gates)   # all layers at once
 
-            def experts(layer, q, a, N_, n_q, heads, d, hs):
+            def experts(layer, q, a, N_, n_q, heads, d, hs, aux):
                 L = P["layers"][layer]
                 C, Cp = L["c"], L["cp"]
                 kv = torch.empty(N_ * n_vis, E * 2 * Cp, dtype=torch.float16, device=dev)
-                ops.gemm(v16.view(N_ * n_vis, -1), L["kv_w"], kv)
+                ops.gemm(v16.view(N_ * n_vis, -1), L["kv_w"], kv, bias=L["kv_b"])
                 ld = E * 2 * Cp
                 for e in range(E):
                     ops.attention(q, kv[:, e * 2 * Cp:], kv[:, e * 2 * Cp + Cp:], a, N_, heads, n_q, n_vis, d,
                                   Cp, ld, ld, C, gate=gates[:, layer, e:], gate_stride=nl * E, accumulate=True,
-                                  head_stride=hs)
+                                  head_stride=hs, aux_cols=aux)
 
             hook["experts"] = experts
         return self.unet(noisy_latents, timesteps, context=encoder_hidden_states, anysd=hook)

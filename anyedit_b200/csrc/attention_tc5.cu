@@ -131,7 +131,15 @@ __device__ __forceinline__ uint64_t a_desc_mn(uint32_t addr, uint32_t lbo_bytes)
 // BKV = kv rows per tile.  128: 2 CTAs/SM (TMEM 256 columns each).  64: S + O fit 128 TMEM columns, ~100 registers
 // and 56 KB smem per CTA -> 3 CTAs/SM = 12 softmax warps per SM, which is what the latency-bound exp/max/pack
 // stream of the d = 40, 4096-token level needs (ncu: XU 64 %, issue 46 %, top stall "wait").
-template <int BKV>
+// AUX (needs head stride >= d + 2 and the operand contract of anysd_attn_params::aux_cols): the softmax reference
+// and the denominator move INTO the tensor-core products.  Q carries (-m_hi, -m_lo) in padding columns d, d+1 and K
+// carries 1.0 there, so S arrives as  q.k*scale*log2e - m  and the CUDA cores only take exp2 -- no FFMA; V carries
+// 1.0 in padding column d, so column d of P.V is the softmax denominator, accumulated in fp32 from exactly the fp16 P
+// the numerator uses -- no FADD.  Per pair of scores: 2 MUFU + 1 pack + max tracking instead of 8.5 instructions
+// (the kernel is issue-bound in the softmax warps: every variant that ADDED instructions got slower).  The reference
+// only moves when a tile exceeds it by > 8; the thread then rewrites its two Q columns in smem before it releases
+// S(j), i.e. before the MMA warp may issue S(j+1).
+template <int BKV, bool AUX>
 __global__ void __launch_bounds__(AT_THREADS, BKV == 64 ? 3 : 2)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AtArgs p) {
@@ -247,7 +255,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int lg = warp & 3;
         const int row = lg * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
-        float m_run = -INFINITY, l_run = 0.f;
+        float m_run = AUX ? 0.f : -INFINITY, l_run = 0.f;
         unsigned char* prow = smem + p_off + row * 128;
         for (int j = 0; j < nt; ++j) {
             am_wait(BAR(5), j & 1);
@@ -257,9 +265,11 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
             for (int c = 0; c < BKV / 32; ++c) a_ld32(tmem_S + lane_addr + c * 32, sr + c * 32);
             a_wait_ld();
-            a_fence_before();
-            __syncwarp();
-            if (lane == 0) am_arrive(BAR(6));                 // S(j) consumed: the MMA warp may overwrite it
+            if (!AUX) {
+                a_fence_before();
+                __syncwarp();
+                if (lane == 0) am_arrive(BAR(6));             // S(j) consumed: the MMA warp may overwrite it
+            }
             const int kv_left = p.n_kv - j * AT_BKV;
             float mx = -INFINITY;
             if (kv_left >= AT_BKV) {
@@ -281,26 +291,60 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     mx = fmaxf(mx, v);
                 }
             }
-            mx *= p.scale_log2;
-            // lazy max: only move the reference when the tile max exceeds it by more than 8 (2^8 headroom)
-            const bool upd = mx > m_run + 8.0f;
-            const float m_new = upd ? mx : m_run;
-            const float corr = upd ? a_ex2(m_run - m_new) : 1.0f;    // first tile: ex2(-inf) = 0
-            m_run = m_new;
-            float sum = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+            bool upd;
+            float corr;
             uint32_t pk[BKV / 2];
+            if (AUX) {
+                // S is already relative to the reference held in the Q columns: mx is the excess over it
+                upd = mx > 8.0f;
+                corr = upd ? a_ex2(-mx) : 1.0f;
+                if (upd) {
+                    m_run += mx;
+                    const __half mh = __float2half_rn(-m_run);
+                    const __half ml = __float2half_rn(-m_run - __half2float(mh));
+                    __half2 pair = __halves2half2(mh, ml);
+                    unsigned char* qrow = smem + q_off + row * 128 + ((((p.d >> 3) & 7) ^ (row & 7)) << 4) + (p.d >> 6) * AT_ATOM;
+                    *reinterpret_cast<__half2*>(qrow) = pair;        // columns d, d+1 of this row (d % 8 == 0)
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                }
+                a_fence_before();
+                __syncwarp();
+                if (lane == 0) am_arrive(BAR(6));             // S(j) consumed AND the Q reference is in place
+                if (__any_sync(0xffffffffu, upd)) {
+                    const float sub = upd ? mx : 0.f;
 #pragma unroll
-            for (int i = 0; i < BKV / 2; ++i) {
-                const float p0 = a_ex2(fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, -m_new));
-                const float p1 = a_ex2(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, -m_new));
-                if ((i & 3) == 0) sum += p0 + p1;          // four independent accumulation chains
-                else if ((i & 3) == 1) sum1 += p0 + p1;
-                else if ((i & 3) == 2) sum2 += p0 + p1;
-                else sum3 += p0 + p1;
-                __half2 hh = __floats2half2_rn(p0, p1);
-                pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+                    for (int i = 0; i < BKV / 2; ++i) {
+                        __half2 hh = __floats2half2_rn(a_ex2(__uint_as_float(sr[2 * i]) - sub), a_ex2(__uint_as_float(sr[2 * i + 1]) - sub));
+                        pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < BKV / 2; ++i) {
+                        __half2 hh = __floats2half2_rn(a_ex2(__uint_as_float(sr[2 * i])), a_ex2(__uint_as_float(sr[2 * i + 1])));
+                        pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+                    }
+                }
+            } else {
+                mx *= p.scale_log2;
+                // lazy max: only move the reference when the tile max exceeds it by more than 8 (2^8 headroom)
+                upd = mx > m_run + 8.0f;
+                const float m_new = upd ? mx : m_run;
+                corr = upd ? a_ex2(m_run - m_new) : 1.0f;     // first tile: ex2(-inf) = 0
+                m_run = m_new;
+                float sum = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+                for (int i = 0; i < BKV / 2; ++i) {
+                    const float p0 = a_ex2(fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, -m_new));
+                    const float p1 = a_ex2(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, -m_new));
+                    if ((i & 3) == 0) sum += p0 + p1;          // four independent accumulation chains
+                    else if ((i & 3) == 1) sum1 += p0 + p1;
+                    else if ((i & 3) == 2) sum2 += p0 + p1;
+                    else sum3 += p0 + p1;
+                    __half2 hh = __floats2half2_rn(p0, p1);
+                    pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+                }
+                l_run = l_run * corr + ((sum + sum1) + (sum2 + sum3));
             }
-            l_run = l_run * corr + ((sum + sum1) + (sum2 + sum3));
             // P smem and the O accumulator are free once PV(j-1) has retired
             if (j > 0) {
                 am_wait(BAR(8), (j - 1) & 1);
@@ -332,6 +376,13 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         am_wait(BAR(8), (nt - 1) & 1);
         a_fence_after();
         const float g = p.gate ? p.gate[(size_t)b * p.gate_stride] : 1.0f;
+        if (AUX) {                                         // denominator = column d of the accumulator
+            uint32_t o[16];
+            __syncwarp();
+            a_ld16(tmem_O + lane_addr + (p.d & ~15), o);
+            a_wait_ld();
+            l_run = (p.d & 8) ? __uint_as_float(o[8]) : __uint_as_float(o[0]);
+        }
         const float inv = g / l_run;
         const int qr = q0 + row;
         __half* orow = p.out + (size_t)b * p.obs + (size_t)qr * p.ldo + (size_t)h * p.d;
@@ -399,6 +450,7 @@ bool attention_tc5_supported(const anysd_attn_params* q) {
     const int d_ext = (q->d + 15) / 16 * 16;
     if (d_ext > hs && q->heads > 1) return false;              // K-extent would reach into the next head's columns
     if (q->d % 8 != 0 || d_ext > 160) return false;
+    if (q->aux_cols && (q->d % 16 != 8 || hs < q->d + 8)) return false;
     if (q->ld_q % 8 || q->ld_k % 8 || q->ld_v % 8 || q->ld_o % 8) return false;
     if (((uintptr_t)q->q % 16) || ((uintptr_t)q->k % 16) || ((uintptr_t)q->v % 16) || ((uintptr_t)q->out % 16)) return false;
     // batches must be stacked rows of one matrix (what the UNet produces): batch stride = n * ld
@@ -430,7 +482,8 @@ int launch_attention_tc5(const anysd_attn_params* q, cudaStream_t st) {
     a.scale_log2 = q->scale * 1.4426950408889634f;
     a.gate = q->gate; a.gate_stride = q->gate_stride; a.accumulate = q->accumulate;
     CUtensorMap tmQ, tmK, tmV;
-    const uint64_t width = (uint64_t)(q->heads - 1) * hs + q->d;     // valid columns from the slice pointer
+    // valid columns from the slice pointer (aux_cols: the last head's padding columns are operands too)
+    const uint64_t width = q->aux_cols ? (uint64_t)q->heads * hs : (uint64_t)(q->heads - 1) * hs + q->d;
     bool ok = a_map(&tmQ, q->q, width, (uint64_t)q->B * q->n_q, q->ld_q, 128) &&
               a_map(&tmK, q->k, width, (uint64_t)q->B * q->n_kv, q->ld_k, bkv) &&
               a_map(&tmV, q->v, width, (uint64_t)q->B * q->n_kv, q->ld_v, bkv);
@@ -439,14 +492,15 @@ int launch_attention_tc5(const anysd_attn_params* q, cudaStream_t st) {
         return ANYSD_ECUDA;
     }
     const int smem = a.NA * AT_ATOM + a.stages * 2 * a.NA * bkv * 128 + (bkv / 64) * AT_ATOM + 128;
-    static int attr_set[64][2];
+    static int attr_set[64][4];
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    const int vi = bkv == 64 ? 1 : 0;
+    const int vi = (bkv == 64 ? 1 : 0) + (q->aux_cols ? 2 : 0);
+    const void* fn = bkv == 64 ? (q->aux_cols ? (const void*)attention_tc5_kernel<64, true> : (const void*)attention_tc5_kernel<64, false>)
+                               : (q->aux_cols ? (const void*)attention_tc5_kernel<128, true> : (const void*)attention_tc5_kernel<128, false>);
     if (attr_set[dev][vi] < smem) {
-        cudaError_t e = bkv == 64 ? cudaFuncSetAttribute(attention_tc5_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                                  : cudaFuncSetAttribute(attention_tc5_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             set_error("attention (tcgen05): smem opt-in failed: %s", cudaGetErrorString(e));
             return ANYSD_ECUDA;
@@ -454,10 +508,13 @@ int launch_attention_tc5(const anysd_attn_params* q, cudaStream_t st) {
         attr_set[dev][vi] = smem;
     }
     dim3 grid(cdiv(q->n_q, AT_BQ), q->heads, q->B);
-    if (bkv == 64)
-        attention_tc5_kernel<64><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a);
-    else
-        attention_tc5_kernel<128><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a);
+    if (bkv == 64) {
+        if (q->aux_cols) attention_tc5_kernel<64, true><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a);
+        else attention_tc5_kernel<64, false><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a);
+    } else {
+        if (q->aux_cols) attention_tc5_kernel<128, true><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a);
+        else attention_tc5_kernel<128, false><<<grid, AT_THREADS, smem, st>>>(tmQ, tmK, tmV, a);
+    }
     return check_launch("attention (tcgen05)");
 }
 

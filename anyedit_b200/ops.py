@@ -225,7 +225,7 @@ def conv3x3(x, W, out, bias=None, rowadd=None, residual=None, stride=1, upsample
 
 
 def attention(q, k, v, out, B, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o, q_bs=None, k_bs=None, v_bs=None,
-              o_bs=None, scale=None, gate=None, gate_stride=1, accumulate=False, head_stride=0):
+              o_bs=None, scale=None, gate=None, gate_stride=1, accumulate=False, head_stride=0, aux_cols=False):
     """softmax(q k^T * scale) v per (batch, head); q/k/v may be column slices of fused projections."""
     _cuda(q, k, v, out)
     p = AttnParams()
@@ -241,6 +241,7 @@ def attention(q, k, v, out, B, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o, q_bs
     p.gate_stride = gate_stride
     p.accumulate = int(bool(accumulate))
     p.head_stride = head_stride
+    p.aux_cols = int(bool(aux_cols))
     with _Traced("attention", 4.0 * B * heads * n_q * n_kv * d):
         _lib.check(_lib.load().anysd_attention_f16(C.byref(p), _stream()), "attention")
     _count()

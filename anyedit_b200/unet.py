@@ -175,6 +175,23 @@ def pad_heads(w, heads, d, hs):
     return out.reshape(heads * hs, k)
 
 
+LOG2E = 1.4426950408889634
+
+
+def aux_cols_for(d):
+    """True when the attention operands can carry the softmax bookkeeping (anysd_attn_params::aux_cols): the padded
+    head has at least two spare columns inside the kernel's ceil16(d) contraction extent (d = 40 -> 48)."""
+    return d % 16 == 8
+
+
+def aux_bias(heads, d, hs, ones):
+    """fp32 [heads*hs] projection bias that plants 1.0 in the first `ones` padding columns of every head
+    (to_q/to_k/to_v have no bias of their own, attention.py:152-154)."""
+    b = torch.zeros(heads, hs, dtype=torch.float32)
+    b[:, d:d + ones] = 1.0
+    return b.reshape(-1)
+
+
 def _pack_conv3(w, dev, cin_pad=None):
     """OIHW -> [Cout, 9*Cin_pad] fp16 with K order (ky, kx, ci)."""
     co, ci = w.shape[0], w.shape[1]
@@ -356,12 +373,21 @@ class UNetModel(nn.Module):
 
         def pack_attn(at, self_attn):
             hs = head_stride_for(at.dim_head)
-            d = {"heads": at.heads, "d": at.dim_head, "hs": hs}
+            aux = aux_cols_for(at.dim_head)
+            d = {"heads": at.heads, "d": at.dim_head, "hs": hs, "aux": aux, "qkv_b": None, "kv_b": None}
             ph = lambda w: pad_heads(w.detach(), at.heads, at.dim_head, hs)
+            wq = at.to_q.weight.detach()
+            if aux:
+                # softmax scale and log2(e) folded into Wq; K gets 1.0 in two padding columns, V in one: the kernel
+                # keeps its running reference in q's padding and reads the denominator from column d of P.V
+                wq = wq.float() * (at.dim_head ** -0.5 * LOG2E)
+                ab = lambda n: aux_bias(at.heads, at.dim_head, hs, n)
+                d["qkv_b"] = torch.cat([ab(0), ab(2), ab(1)]).to(dev)
+                d["kv_b"] = torch.cat([ab(2), ab(1)]).to(dev)
             if self_attn:
-                d["qkv_w"] = _h(torch.cat([ph(at.to_q.weight), ph(at.to_k.weight), ph(at.to_v.weight)], 0), dev)
+                d["qkv_w"] = _h(torch.cat([ph(wq).float(), ph(at.to_k.weight).float(), ph(at.to_v.weight).float()], 0), dev)
             else:
-                d["q_w"] = _h(ph(at.to_q.weight), dev)
+                d["q_w"] = _h(ph(wq), dev)
                 d["kv_w"] = _h(torch.cat([ph(at.to_k.weight), ph(at.to_v.weight)], 0), dev)
             d["o_w"], d["o_b"] = _h(at.to_out[0].weight, dev), _f(at.to_out[0].bias, dev)
             return d
@@ -565,18 +591,19 @@ class UNetModel(nn.Module):
         a = torch.empty(N * n_q, C, dtype=torch.float16, device=dev)
         if self_attn:
             qkv = torch.empty(N * n_q, 3 * Cp, dtype=torch.float16, device=dev)
-            ops.gemm(xq, ad["qkv_w"], qkv)
+            ops.gemm(xq, ad["qkv_w"], qkv, bias=ad["qkv_b"])
             ops.attention(qkv, qkv[:, Cp:], qkv[:, 2 * Cp:], a, N, ad["heads"], n_q, n_q, ad["d"],
-                          3 * Cp, 3 * Cp, 3 * Cp, C, head_stride=hs)
+                          3 * Cp, 3 * Cp, 3 * Cp, C, head_stride=hs, aux_cols=ad["aux"])
         else:
             L = ctx.shape[1]
             q = torch.empty(N * n_q, Cp, dtype=torch.float16, device=dev)
             ops.gemm(xq, ad["q_w"], q)
             kv = torch.empty(N * L, 2 * Cp, dtype=torch.float16, device=dev)
-            ops.gemm(ctx.view(N * L, -1), ad["kv_w"], kv)
-            ops.attention(q, kv, kv[:, Cp:], a, N, ad["heads"], n_q, L, ad["d"], Cp, 2 * Cp, 2 * Cp, C, head_stride=hs)
+            ops.gemm(ctx.view(N * L, -1), ad["kv_w"], kv, bias=ad["kv_b"])
+            ops.attention(q, kv, kv[:, Cp:], a, N, ad["heads"], n_q, L, ad["d"], Cp, 2 * Cp, 2 * Cp, C, head_stride=hs,
+                          aux_cols=ad["aux"])
             if expert and st["anysd"] is not None and st["anysd"].get("experts") is not None:
-                st["anysd"]["experts"](st["layer"], q, a, N, n_q, ad["heads"], ad["d"], hs)
+                st["anysd"]["experts"](st["layer"], q, a, N, n_q, ad["heads"], ad["d"], hs, ad["aux"])
             if expert:
                 st["layer"] += 1
         ops.gemm(a, ad["o_w"], out, bias=ad["o_b"], residual=residual)

@@ -137,6 +137,14 @@ typedef struct {
     int accumulate;
     int head_stride;        /* elements between consecutive heads inside a q/k/v row; 0 = d.  The tcgen05 kernel
                                needs head_stride >= ceil16(d) with zero padding columns when d % 16 != 0 */
+    int aux_cols;           /* 1 = "operands carry the softmax bookkeeping" (tcgen05 kernel only; needs d % 16 == 8,
+                               head_stride >= d + 8, EUNSUPPORTED otherwise).  Contract, per head:
+                                 q: columns [0,d) hold q * scale * log2(e) (the caller folds both into Wq; `scale` is
+                                    ignored), columns d.. are zero;
+                                 k: columns d and d+1 hold 1.0;    v: column d holds 1.0;   other padding zero.
+                               The kernel writes its running reference into q's padding inside shared memory, so the
+                               scores leave the tensor core already shifted (exp2 only) and the softmax denominator is
+                               column d of P.V.  Same result as aux_cols = 0 up to fp32 rounding. */
 } anysd_attn_params;
 int anysd_attention_f16(const anysd_attn_params* p, anysd_stream_t stream);
 

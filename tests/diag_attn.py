@@ -11,6 +11,7 @@ from anyedit_b200.unet import head_stride_for  # noqa: E402
 
 
 def run(B, heads, n, nkv, d, check=True):
+    aux = "--aux" in sys.argv and d % 16 == 8
     hs = head_stride_for(d)
     C, Cp = heads * d, heads * hs
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -19,8 +20,13 @@ def run(B, heads, n, nkv, d, check=True):
         t[..., :d] = torch.randn(B, rows, heads, d, device="cuda", generator=g).half()
         return t.reshape(B, rows, Cp)
     q, k, v = mk(n), mk(nkv), mk(nkv)
+    qa = q
+    if aux:                                  # operand contract of anysd_attn_params::aux_cols
+        qa = (q.float() * (d ** -0.5 * 1.4426950408889634)).half()
+        k.view(B, nkv, heads, hs)[..., d:d + 2] = 1.0
+        v.view(B, nkv, heads, hs)[..., d] = 1.0
     out = torch.empty(B, n, C, dtype=torch.float16, device="cuda")
-    fn = lambda: ops.attention(q, k, v, out, B, heads, n, nkv, d, Cp, Cp, Cp, C, head_stride=hs)
+    fn = lambda: ops.attention(qa, k, v, out, B, heads, n, nkv, d, Cp, Cp, Cp, C, head_stride=hs, aux_cols=aux)
     fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -39,7 +45,7 @@ def run(B, heads, n, nkv, d, check=True):
         ref = ref.permute(0, 2, 1, 3).reshape(1, n, C)
         err = float((out[:1].float() - ref).norm() / ref.norm())
     fl = 4.0 * B * heads * n * nkv * d
-    print(f"attn B={B} h={heads} n={n} kv={nkv} d={d}: {t * 1e6:9.1f} us {fl / t / 1e12:7.1f} TFLOP/s rel={err:.2e}", flush=True)
+    print(f"attn aux={int(aux)} B={B} h={heads} n={n} kv={nkv} d={d}: {t * 1e6:9.1f} us {fl / t / 1e12:7.1f} TFLOP/s rel={err:.2e}", flush=True)
 
 
 if __name__ == "__main__":

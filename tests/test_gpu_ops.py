@@ -331,3 +331,52 @@ def test_attention_padded_heads(ops, B, heads, nq, nkv, d):
     ops.attention(pad(q16), pad(k16), pad(v16), out, B, heads, nq, nkv, d, Cp, Cp, Cp, C, head_stride=hs)
     e = rel(out, ref)
     assert e < 2e-3, e
+
+
+@pytest.mark.parametrize("B,heads,nq,nkv,d,amp", [(1, 8, 256, 256, 40, 1.0), (2, 8, 300, 300, 40, 1.0), (2, 8, 100, 77, 40, 1.0),
+                                                  (1, 8, 1024, 1024, 40, 6.0), (1, 3, 130, 513, 24, 3.0),
+                                                  (1, 2, 128, 2048, 40, 12.0)])
+def test_attention_aux_cols(ops, B, heads, nq, nkv, d, amp):
+    """anysd_attn_params::aux_cols -- q pre-scaled by scale*log2(e), K carrying 1.0 in padding columns d, d+1 and V
+    in column d (what anyedit_b200.unet packs for d = 40): same softmax(q k^T scale) v as the plain contract.  `amp`
+    widens the score range so the in-kernel reference moves many times (rewrites of q's padding columns); keys are
+    sorted by growing norm in the last case so the maximum keeps rising tile after tile."""
+    from anyedit_b200.unet import LOG2E, aux_cols_for, head_stride_for
+    from oracle import unet_oracle
+    assert aux_cols_for(d)
+    hs = head_stride_for(d)
+    C, Cp = heads * d, heads * hs
+    q, k, v = randn(191, B, nq, C) * amp, randn(192, B, nkv, C), randn(193, B, nkv, C)
+    if amp >= 12.0:
+        k = k * torch.linspace(0.05, 2.0, nkv).view(1, nkv, 1)
+    scale = d ** -0.5
+    qs16 = (q * (scale * LOG2E)).half()                      # the operand the kernel sees
+    k16, v16 = k.half(), v.half()
+
+    def split(t):
+        return t.float().reshape(B, t.shape[1], heads, d).permute(0, 2, 1, 3).reshape(B * heads, t.shape[1], d)
+
+    def pad(t, ones):
+        o = torch.zeros(B, t.shape[1], heads, hs, dtype=torch.float16)
+        o[..., :d] = t.reshape(B, t.shape[1], heads, d)
+        o[..., d:d + ones] = 1.0
+        return o.reshape(B, t.shape[1], Cp).cuda().contiguous()
+
+    # reference on exactly the fp16 operands: softmax(q16' k16^T ln2) v16  ==  softmax over base-2 exponent
+    ref = unet_oracle.attention_bhnd(split(qs16) / (scale * LOG2E), split(k16), split(v16))
+    ref = ref.reshape(B, heads, nq, d).permute(0, 2, 1, 3).reshape(B, nq, C)
+    out = torch.empty(B, nq, C, dtype=torch.float16, device="cuda")
+    ops.attention(pad(qs16, 0), pad(k16, 2), pad(v16, 1), out, B, heads, nq, nkv, d, Cp, Cp, Cp, C, head_stride=hs,
+                  aux_cols=True)
+    assert torch.isfinite(out).all()
+    e = rel(out, ref)
+    assert e < 2e-3, e
+
+
+def test_attention_aux_cols_unsupported_is_loud(ops):
+    """aux_cols with a head that has no spare columns (d = 64) must fail, not silently fall back."""
+    B, heads, n, d = 1, 2, 128, 64
+    t = torch.zeros(B, n, heads * d, dtype=torch.float16, device="cuda")
+    out = torch.empty_like(t)
+    with pytest.raises(Exception):
+        ops.attention(t, t, t, out, B, heads, n, n, d, heads * d, heads * d, heads * d, heads * d, aux_cols=True)
