@@ -38,13 +38,13 @@ def _count(n=1):
 
 # Optional per-launch tracing for bench.py's roofline leg: when ``trace`` is a list, the tensor-core
 # wrappers bracket their launch with CUDA events on the launching stream and append
-# (kind, algorithmic_flops, start_event, end_event).  None (default) adds no work.
+# (kind, algorithmic_flops, start_event, end_event, tag).  None (default) adds no work.
 trace = None
 
 
 class _Traced:
-    def __init__(self, kind, flops):
-        self.kind, self.flops = kind, flops
+    def __init__(self, kind, flops, tag=""):
+        self.kind, self.flops, self.tag = kind, flops, tag
 
     def __enter__(self):
         if trace is not None:
@@ -56,7 +56,7 @@ class _Traced:
     def __exit__(self, *exc):
         if trace is not None:
             self.e1.record()
-            trace.append((self.kind, self.flops, self.e0, self.e1))
+            trace.append((self.kind, self.flops, self.e0, self.e1, self.tag))
         return False
 
 
@@ -149,9 +149,10 @@ def groupnorm(x1, gamma, beta, y, N, HW, eps, silu, ws, x2=None, G=32):
     _cuda(x1, y, ws)
     C1 = x1.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
-    _lib.check(_lib.load().anysd_groupnorm_nhwc_f16(_ptr(x1), C1, _ptr(x2), C2, _ptr(gamma), _ptr(beta), _ptr(y), N,
-                                                    HW, G, float(eps), int(bool(silu)), _ptr(ws), ws.numel() * 4,
-                                                    _stream()), "groupnorm")
+    with _Traced("groupnorm", 0.0, f"N={N} HW={HW} C={C1}+{C2}"):
+        _lib.check(_lib.load().anysd_groupnorm_nhwc_f16(_ptr(x1), C1, _ptr(x2), C2, _ptr(gamma), _ptr(beta), _ptr(y), N,
+                                                        HW, G, float(eps), int(bool(silu)), _ptr(ws), ws.numel() * 4,
+                                                        _stream()), "groupnorm")
     _count(2)
 
 
@@ -159,8 +160,9 @@ def layernorm(x, gamma, beta, y, eps=1e-5):
     _cuda(x, y)
     Cc = x.shape[-1]
     M = x.numel() // Cc
-    _lib.check(_lib.load().anysd_layernorm_f16(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), M, Cc, float(eps),
-                                               _stream()), "layernorm")
+    with _Traced("layernorm", 0.0, f"M={M} C={Cc}"):
+        _lib.check(_lib.load().anysd_layernorm_f16(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), M, Cc, float(eps),
+                                                   _stream()), "layernorm")
     _count()
 
 
@@ -185,7 +187,7 @@ def gemm(A, W, out, bias=None, rowadd=None, rows_per_batch=0, residual=None, act
     p.act = act
     p.out_dtype = _DT[out.dtype]
     p.conv = 0
-    with _Traced("gemm", 2.0 * p.M * p.N * p.K):
+    with _Traced("gemm", 2.0 * p.M * p.N * p.K, f"M={p.M} N={p.N} K={p.K} act={p.act} res={int(residual is not None)}"):
         _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "gemm")
     _count()
 
@@ -218,7 +220,7 @@ def conv3x3(x, W, out, bias=None, rowadd=None, residual=None, stride=1, upsample
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel() * 2
     # algorithmic FLOPs (trace only): zero-padded channels do not count
     fl = 2.0 * p.M * (logical_cout or p.N) * 9 * (logical_cin or Cin)
-    with _Traced("conv3x3", fl):
+    with _Traced("conv3x3", fl, f"N={p.Nimg} {p.H}x{p.Wd} {p.Cin}->{p.N} s={p.stride} up={p.upsample} res={int(residual is not None)}"):
         _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "conv3x3")
     _count()
     return Ho, Wo
@@ -242,7 +244,7 @@ def attention(q, k, v, out, B, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o, q_bs
     p.accumulate = int(bool(accumulate))
     p.head_stride = head_stride
     p.aux_cols = int(bool(aux_cols))
-    with _Traced("attention", 4.0 * B * heads * n_q * n_kv * d):
+    with _Traced("attention", 4.0 * B * heads * n_q * n_kv * d, f"B={B} h={heads} nq={n_q} nkv={n_kv} d={d}"):
         _lib.check(_lib.load().anysd_attention_f16(C.byref(p), _stream()), "attention")
     _count()
 

@@ -273,7 +273,7 @@ def main():
             model.apply_model(x_in, tt, cond2)       # eager (no graph): events around every contraction launch
         torch.cuda.synchronize()
         agg = {}
-        for kind, fl, e0, e1 in ops.trace:
+        for kind, fl, e0, e1, _tag in ops.trace:
             a = agg.setdefault(kind, [0.0, 0.0, 0])
             a[0] += fl
             a[1] += e0.elapsed_time(e1) * 1e-3

@@ -39,17 +39,26 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         agg = {}
-        for kind, fl, a, b in ops.trace:
+        shapes = {}
+        for kind, fl, a, b, tag in ops.trace:
             d = agg.setdefault(kind, [0.0, 0.0, 0])
+            ms = a.elapsed_time(b)
             d[0] += fl
-            d[1] += a.elapsed_time(b)
+            d[1] += ms
             d[2] += 1
+            s = shapes.setdefault((kind, tag), [0.0, 0.0, 0])
+            s[0] += fl
+            s[1] += ms
+            s[2] += 1
         ops.trace = None
         tot = e0.elapsed_time(e1)
         print(f"forward total {tot:.2f} ms (eager, with events)")
         for k, v in agg.items():
             print(f"  {k:10s} {v[2]:4d} launches {v[1]:8.2f} ms {v[0] / v[1] / 1e9:8.1f} TFLOP/s")
         print(f"  other      {tot - sum(v[1] for v in agg.values()):8.2f} ms")
+        if "--shapes" in sys.argv:
+            for (kind, tag), v in sorted(shapes.items(), key=lambda kv: -kv[1][1]):
+                print(f"    {v[1]:7.3f} ms {v[2]:3d}x {v[1] / v[2] * 1e3:8.1f} us {v[0] / v[1] / 1e9:8.1f} TF  {kind} {tag}")
         # plain timing without events
         e0.record()
         for _ in range(3):

@@ -17,11 +17,15 @@ rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
 hs, heads, n, d = 48, 8, 4096, 40
 qkv = torch.zeros(B, n, 3, heads, hs, dtype=torch.float16, device="cuda")
 qkv[..., :d] = rn(B, n, 3, heads, d).half()
+qkv[:, :, 0, :, :d] *= d ** -0.5 * 1.4426950408889634      # aux_cols contract: q pre-scaled, ones in K/V padding
+qkv[:, :, 1, :, d:d + 2] = 1.0
+qkv[:, :, 2, :, d] = 1.0
 qkv = qkv.view(B * n, 3 * heads * hs)
 Cp = heads * hs
 out = torch.empty(B * n, heads * d, dtype=torch.float16, device="cuda")
 for _ in range(2):
-    ops.attention(qkv, qkv[:, Cp:], qkv[:, 2 * Cp:], out, B, heads, n, n, d, 3 * Cp, 3 * Cp, 3 * Cp, heads * d, head_stride=hs)
+    ops.attention(qkv, qkv[:, Cp:], qkv[:, 2 * Cp:], out, B, heads, n, n, d, 3 * Cp, 3 * Cp, 3 * Cp, heads * d, head_stride=hs,
+                  aux_cols=True)
 # 2. conv3x3 320 -> 320 @ 64x64 with time-embedding row add and residual
 x = rn(B, 64, 64, 320).half()
 w = (rn(320, 9 * 320) * (2880 ** -0.5)).half()
