@@ -260,90 +260,133 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int j = 0; j < nt; ++j) {
             am_wait(BAR(5), j & 1);
             a_fence_after();
-            uint32_t sr[BKV];
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < BKV / 32; ++c) a_ld32(tmem_S + lane_addr + c * 32, sr + c * 32);
-            a_wait_ld();
-            if (!AUX) {
-                a_fence_before();
-                __syncwarp();
-                if (lane == 0) am_arrive(BAR(6));             // S(j) consumed: the MMA warp may overwrite it
-            }
             const int kv_left = p.n_kv - j * AT_BKV;
-            float mx = -INFINITY;
-            if (kv_left >= AT_BKV) {
-                // four independent chains (a single running max is a 128-deep dependent chain)
+            bool upd = false;
+            float corr = 1.0f;
+            uint32_t pk[BKV / 2];
+            bool done = false;
+            if (AUX && kv_left >= AT_BKV) {
+                // Streamed tile: with the reference inside the product the exponentials do not wait for the row
+                // maximum, so chunk c+1 (32 columns) travels TMEM -> registers while chunk c goes through the XU.
+                // The tile maximum is complete before the LAST chunk's exponentials; if no row of the warp moves its
+                // reference (the common case) S(j) is released there and S(j+1) runs under the remaining work.
+                // Otherwise nothing is released and the tile is redone from TMEM on the general path below.
+                constexpr int NC = BKV / 32;
+                uint32_t cb[2][32];
                 float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+                __syncwarp();
+                a_ld32(tmem_S + lane_addr, cb[0]);
+                a_wait_ld();
 #pragma unroll
-                for (int i = 0; i < BKV; i += 8) {
-                    m0 = fmaxf(m0, fmaxf(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])));
-                    m1 = fmaxf(m1, fmaxf(__uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3])));
-                    m2 = fmaxf(m2, fmaxf(__uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5])));
-                    m3 = fmaxf(m3, fmaxf(__uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7])));
-                }
-                mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-            } else {
+                for (int c = 0; c < NC; ++c) {
+                    if (c + 1 < NC) a_ld32(tmem_S + lane_addr + (c + 1) * 32, cb[(c + 1) & 1]);
+                    const uint32_t* cur = cb[c & 1];
 #pragma unroll
-                for (int i = 0; i < BKV; ++i) {
-                    float v = (i < kv_left) ? __uint_as_float(sr[i]) : -INFINITY;
-                    sr[i] = __float_as_uint(v);
-                    mx = fmaxf(mx, v);
+                    for (int i = 0; i < 32; i += 8) {
+                        m0 = fmaxf(m0, fmaxf(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])));
+                        m1 = fmaxf(m1, fmaxf(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])));
+                        m2 = fmaxf(m2, fmaxf(__uint_as_float(cur[i + 4]), __uint_as_float(cur[i + 5])));
+                        m3 = fmaxf(m3, fmaxf(__uint_as_float(cur[i + 6]), __uint_as_float(cur[i + 7])));
+                    }
+                    if (c == NC - 1) {
+                        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                        if (!__any_sync(0xffffffffu, mx > 8.0f)) {
+                            a_fence_before();
+                            __syncwarp();
+                            if (lane == 0) am_arrive(BAR(6));     // S(j) consumed, reference unchanged
+                            done = true;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        __half2 hh = __floats2half2_rn(a_ex2(__uint_as_float(cur[2 * i])), a_ex2(__uint_as_float(cur[2 * i + 1])));
+                        pk[c * 16 + i] = *reinterpret_cast<uint32_t*>(&hh);
+                    }
+                    if (c + 1 < NC) a_wait_ld();
                 }
             }
-            bool upd;
-            float corr;
-            uint32_t pk[BKV / 2];
-            if (AUX) {
-                // S is already relative to the reference held in the Q columns: mx is the excess over it
-                upd = mx > 8.0f;
-                corr = upd ? a_ex2(-mx) : 1.0f;
-                if (upd) {
-                    m_run += mx;
-                    const __half mh = __float2half_rn(-m_run);
-                    const __half ml = __float2half_rn(-m_run - __half2float(mh));
-                    __half2 pair = __halves2half2(mh, ml);
-                    unsigned char* qrow = smem + q_off + row * 128 + ((((p.d >> 3) & 7) ^ (row & 7)) << 4) + (p.d >> 6) * AT_ATOM;
-                    *reinterpret_cast<__half2*>(qrow) = pair;        // columns d, d+1 of this row (d % 8 == 0)
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                }
-                a_fence_before();
+            if (!done) {
+                uint32_t sr[BKV];
                 __syncwarp();
-                if (lane == 0) am_arrive(BAR(6));             // S(j) consumed AND the Q reference is in place
-                if (__any_sync(0xffffffffu, upd)) {
-                    const float sub = upd ? mx : 0.f;
-#pragma unroll
-                    for (int i = 0; i < BKV / 2; ++i) {
-                        __half2 hh = __floats2half2_rn(a_ex2(__uint_as_float(sr[2 * i]) - sub), a_ex2(__uint_as_float(sr[2 * i + 1]) - sub));
-                        pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+    #pragma unroll
+                for (int c = 0; c < BKV / 32; ++c) a_ld32(tmem_S + lane_addr + c * 32, sr + c * 32);
+                a_wait_ld();
+                if (!AUX) {
+                    a_fence_before();
+                    __syncwarp();
+                    if (lane == 0) am_arrive(BAR(6));             // S(j) consumed: the MMA warp may overwrite it
+                }
+                float mx = -INFINITY;
+                if (kv_left >= AT_BKV) {
+                    // four independent chains (a single running max is a 128-deep dependent chain)
+                    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+    #pragma unroll
+                    for (int i = 0; i < BKV; i += 8) {
+                        m0 = fmaxf(m0, fmaxf(__uint_as_float(sr[i]), __uint_as_float(sr[i + 1])));
+                        m1 = fmaxf(m1, fmaxf(__uint_as_float(sr[i + 2]), __uint_as_float(sr[i + 3])));
+                        m2 = fmaxf(m2, fmaxf(__uint_as_float(sr[i + 4]), __uint_as_float(sr[i + 5])));
+                        m3 = fmaxf(m3, fmaxf(__uint_as_float(sr[i + 6]), __uint_as_float(sr[i + 7])));
+                    }
+                    mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                } else {
+    #pragma unroll
+                    for (int i = 0; i < BKV; ++i) {
+                        float v = (i < kv_left) ? __uint_as_float(sr[i]) : -INFINITY;
+                        sr[i] = __float_as_uint(v);
+                        mx = fmaxf(mx, v);
+                    }
+                }
+                if (AUX) {
+                    // S is already relative to the reference held in the Q columns: mx is the excess over it
+                    upd = mx > 8.0f;
+                    corr = upd ? a_ex2(-mx) : 1.0f;
+                    if (upd) {
+                        m_run += mx;
+                        const __half mh = __float2half_rn(-m_run);
+                        const __half ml = __float2half_rn(-m_run - __half2float(mh));
+                        __half2 pair = __halves2half2(mh, ml);
+                        unsigned char* qrow = smem + q_off + row * 128 + ((((p.d >> 3) & 7) ^ (row & 7)) << 4) + (p.d >> 6) * AT_ATOM;
+                        *reinterpret_cast<__half2*>(qrow) = pair;        // columns d, d+1 of this row (d % 8 == 0)
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    }
+                    a_fence_before();
+                    __syncwarp();
+                    if (lane == 0) am_arrive(BAR(6));             // S(j) consumed AND the Q reference is in place
+                    if (__any_sync(0xffffffffu, upd)) {
+                        const float sub = upd ? mx : 0.f;
+    #pragma unroll
+                        for (int i = 0; i < BKV / 2; ++i) {
+                            __half2 hh = __floats2half2_rn(a_ex2(__uint_as_float(sr[2 * i]) - sub), a_ex2(__uint_as_float(sr[2 * i + 1]) - sub));
+                            pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+                        }
+                    } else {
+    #pragma unroll
+                        for (int i = 0; i < BKV / 2; ++i) {
+                            __half2 hh = __floats2half2_rn(a_ex2(__uint_as_float(sr[2 * i])), a_ex2(__uint_as_float(sr[2 * i + 1])));
+                            pk[i] = *reinterpret_cast<uint32_t*>(&hh);
+                        }
                     }
                 } else {
-#pragma unroll
+                    mx *= p.scale_log2;
+                    // lazy max: only move the reference when the tile max exceeds it by more than 8 (2^8 headroom)
+                    upd = mx > m_run + 8.0f;
+                    const float m_new = upd ? mx : m_run;
+                    corr = upd ? a_ex2(m_run - m_new) : 1.0f;     // first tile: ex2(-inf) = 0
+                    m_run = m_new;
+                    float sum = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+    #pragma unroll
                     for (int i = 0; i < BKV / 2; ++i) {
-                        __half2 hh = __floats2half2_rn(a_ex2(__uint_as_float(sr[2 * i])), a_ex2(__uint_as_float(sr[2 * i + 1])));
+                        const float p0 = a_ex2(fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, -m_new));
+                        const float p1 = a_ex2(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, -m_new));
+                        if ((i & 3) == 0) sum += p0 + p1;          // four independent accumulation chains
+                        else if ((i & 3) == 1) sum1 += p0 + p1;
+                        else if ((i & 3) == 2) sum2 += p0 + p1;
+                        else sum3 += p0 + p1;
+                        __half2 hh = __floats2half2_rn(p0, p1);
                         pk[i] = *reinterpret_cast<uint32_t*>(&hh);
                     }
+                    l_run = l_run * corr + ((sum + sum1) + (sum2 + sum3));
                 }
-            } else {
-                mx *= p.scale_log2;
-                // lazy max: only move the reference when the tile max exceeds it by more than 8 (2^8 headroom)
-                upd = mx > m_run + 8.0f;
-                const float m_new = upd ? mx : m_run;
-                corr = upd ? a_ex2(m_run - m_new) : 1.0f;     // first tile: ex2(-inf) = 0
-                m_run = m_new;
-                float sum = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-#pragma unroll
-                for (int i = 0; i < BKV / 2; ++i) {
-                    const float p0 = a_ex2(fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, -m_new));
-                    const float p1 = a_ex2(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, -m_new));
-                    if ((i & 3) == 0) sum += p0 + p1;          // four independent accumulation chains
-                    else if ((i & 3) == 1) sum1 += p0 + p1;
-                    else if ((i & 3) == 2) sum2 += p0 + p1;
-                    else sum3 += p0 + p1;
-                    __half2 hh = __floats2half2_rn(p0, p1);
-                    pk[i] = *reinterpret_cast<uint32_t*>(&hh);
-                }
-                l_run = l_run * corr + ((sum + sum1) + (sum2 + sum3));
             }
             // P smem and the O accumulator are free once PV(j-1) has retired
             if (j > 0) {
