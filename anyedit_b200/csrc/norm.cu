@@ -13,6 +13,10 @@
 namespace anysd {
 
 constexpr int GN_MAX_SPLITS = 64;
+constexpr int GN_U = 8;            // 16-byte loads a thread keeps in flight
+
+// x * sigmoid(x) with two MUFU ops (ex2, rcp) instead of an IEEE division: ~1e-7 relative, far below the fp16 store
+__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 struct GnGeom {
     int CV;    // 8-channel vectors per row (C/8)
@@ -31,11 +35,10 @@ static GnGeom gn_geom(int C1, int C2) {
     return g;
 }
 
-__global__ void gn_stats_kernel(const uint4* __restrict__ x1, const uint4* __restrict__ x2, int CV, int CV1, int R,
-                                int HW, int rows_per_block, int G, int cpg, float eps, float* __restrict__ partials,
-                                float* __restrict__ meanrstd, unsigned int* __restrict__ counters) {
-    extern __shared__ float sm[];  // [R][CV*8] sums, then [R][CV*8] squares
-    const int n = blockIdx.y, s = blockIdx.x;
+// partial {sum, sumsq} of logical chunk (n, s) -> partials[((n * S + s) * G + g) * 2]; all threads of the block take part
+__device__ __forceinline__ void gn_stats_block(const uint4* __restrict__ x1, const uint4* __restrict__ x2, int CV, int CV1, int R,
+                                               int HW, int rows_per_block, int S, int G, int cpg, int n, int s,
+                                               float* __restrict__ partials, float* sm) {
     const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
     const int C = CV * 8;
     const int row0 = s * rows_per_block;
@@ -49,25 +52,26 @@ __global__ void gn_stats_kernel(const uint4* __restrict__ x1, const uint4* __res
     float sum[8], sq[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
-    int row = row0 + r;
-    // 4 independent 16-byte loads in flight per thread
-    for (; row + 3 * R < row1; row += 4 * R) {
-        uint4 v0 = __ldg(base + (size_t)row * stride);
-        uint4 v1 = __ldg(base + (size_t)(row + R) * stride);
-        uint4 v2 = __ldg(base + (size_t)(row + 2 * R) * stride);
-        uint4 v3 = __ldg(base + (size_t)(row + 3 * R) * stride);
-        float f[8];
-#define ANYSD_ACC(v)                        \
-        unpack8(v, f);                          \
-        _Pragma("unroll") for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] += f[j] * f[j]; }
-        ANYSD_ACC(v0) ANYSD_ACC(v1) ANYSD_ACC(v2) ANYSD_ACC(v3)
+    // GN_U independent 16-byte loads in flight per thread, predicated: a chunk is normally ONE such batch (the host
+    // sizes rows_per_block = GN_U * R), so a thread never chains dependent memory latencies.
+    for (int row = row0 + r; row < row1; row += GN_U * R) {
+        uint4 v[GN_U];
+#pragma unroll
+        for (int u = 0; u < GN_U; ++u) {
+            const int rr = row + u * R;
+            v[u] = rr < row1 ? __ldg(base + (size_t)rr * stride) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < GN_U; ++u) {
+            float f[8];
+            unpack8(v[u], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                sum[j] += f[j];
+                sq[j] += f[j] * f[j];
+            }
+        }
     }
-    for (; row < row1; row += R) {
-        uint4 v0 = __ldg(base + (size_t)row * stride);
-        float f[8];
-        ANYSD_ACC(v0)
-    }
-#undef ANYSD_ACC
     float* ssum = sm;
     float* ssq = sm + (size_t)R * C;
 #pragma unroll
@@ -95,12 +99,37 @@ __global__ void gn_stats_kernel(const uint4* __restrict__ x1, const uint4* __res
             a += ssum[idx];
             b += ssq[idx];
         }
-        float* p = partials + (((size_t)n * gridDim.x + s) * G + g) * 2;
+        float* p = partials + (((size_t)n * S + s) * G + g) * 2;
         p[0] = a;
         p[1] = b;
     }
-    // The last block of image n to finish folds the S partials (fixed order, in double: deterministic and
-    // independent of which block happens to be last) into mean / rstd, so the apply pass starts streaming at once.
+}
+
+// The S partials of image n folded in a fixed order, in double: deterministic, independent of which block runs it.
+__device__ __forceinline__ void gn_fold(const float* __restrict__ partials, int n, int S, int G, int g, int HW, int cpg, float eps,
+                                        float& mean_out, float& rstd_out) {
+    double a = 0.0, b = 0.0;
+    const float* p = partials + ((size_t)n * S * G + g) * 2;
+    for (int i = 0; i < S; ++i) {
+        a += (double)__ldcg(p + (size_t)i * G * 2);
+        b += (double)__ldcg(p + (size_t)i * G * 2 + 1);
+    }
+    const double cnt = (double)HW * cpg;
+    const double mean = a / cnt;
+    double var = b / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean_out = (float)mean;
+    rstd_out = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void __launch_bounds__(512, 2) gn_stats_kernel(const uint4* __restrict__ x1, const uint4* __restrict__ x2, int CV, int CV1, int R,
+                                int HW, int rows_per_block, int G, int cpg, float eps, float* __restrict__ partials,
+                                float* __restrict__ meanrstd, unsigned int* __restrict__ counters) {
+    extern __shared__ float sm[];  // [R][CV*8] sums, then [R][CV*8] squares
+    const int n = blockIdx.y;
+    gn_stats_block(x1, x2, CV, CV1, R, HW, rows_per_block, gridDim.x, G, cpg, n, blockIdx.x, partials, sm);
+    // The last block of image n to finish folds the S partials into mean / rstd, so the apply pass starts streaming
+    // at once.
     __shared__ bool is_last;
     __threadfence();
     __syncthreads();
@@ -113,42 +142,34 @@ __global__ void gn_stats_kernel(const uint4* __restrict__ x1, const uint4* __res
     if (is_last) {
         __threadfence();
         for (int g = threadIdx.x; g < G; g += blockDim.x) {
-            double a = 0.0, b = 0.0;
-            const float* p = partials + ((size_t)n * gridDim.x * G + g) * 2;
-            for (int i = 0; i < (int)gridDim.x; ++i) {
-                a += (double)__ldcg(p + (size_t)i * G * 2);
-                b += (double)__ldcg(p + (size_t)i * G * 2 + 1);
-            }
-            const double cnt = (double)HW * cpg;
-            const double mean = a / cnt;
-            double var = b / cnt - mean * mean;
-            if (var < 0.0) var = 0.0;
-            meanrstd[((size_t)n * G + g) * 2] = (float)mean;
-            meanrstd[((size_t)n * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+            float m, rs;
+            gn_fold(partials, n, gridDim.x, G, g, HW, cpg, eps, m, rs);
+            meanrstd[((size_t)n * G + g) * 2] = m;
+            meanrstd[((size_t)n * G + g) * 2 + 1] = rs;
         }
     }
 }
 
-__global__ void gn_apply_kernel(const uint4* __restrict__ x1, const uint4* __restrict__ x2, int CV, int CV1, int R,
-                                int HW, int rows_per_block, int G, int cpg, const float* __restrict__ meanrstd,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int fuse_silu,
-                                uint4* __restrict__ y) {
-    __shared__ float s_mean[64], s_rstd[64];
-    const int n = blockIdx.y, s = blockIdx.x;
-    if (threadIdx.x < G) {
-        s_mean[threadIdx.x] = meanrstd[((size_t)n * G + threadIdx.x) * 2];
-        s_rstd[threadIdx.x] = meanrstd[((size_t)n * G + threadIdx.x) * 2 + 1];
-    }
-    __syncthreads();
+// y = [silu](x * a + b) over the rows of logical chunk (n, s); s_mean / s_rstd: this image's statistics in smem
+// COEF_SMEM: per-channel a = rstd*gamma, b = beta - mean*a were staged in shared memory (coef[0..C) = a, coef[C..2C) = b)
+// by the caller and are read per use (frees 16 registers for loads in flight); otherwise they are built here.
+template <bool COEF_SMEM>
+__device__ __forceinline__ void gn_apply_block(const uint4* __restrict__ x1, const uint4* __restrict__ x2, int CV, int CV1, int R,
+                                               int HW, int rows_per_block, int cpg, int n, int s, const float* s_mean,
+                                               const float* s_rstd, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, int fuse_silu, uint4* __restrict__ y,
+                                               const float* coef) {
     const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
     float ca[8], cb[8];
+    if (!COEF_SMEM) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = cv * 8 + j;
-        const int g = c / cpg;
-        const float a = s_rstd[g] * gamma[c];
-        ca[j] = a;
-        cb[j] = beta[c] - s_mean[g] * a;
+        for (int j = 0; j < 8; ++j) {
+            const int c = cv * 8 + j;
+            const int g = c / cpg;
+            const float a = s_rstd[g] * gamma[c];
+            ca[j] = a;
+            cb[j] = beta[c] - s_mean[g] * a;
+        }
     }
     const int row0 = s * rows_per_block;
     int row1 = row0 + rows_per_block;
@@ -158,48 +179,108 @@ __global__ void gn_apply_kernel(const uint4* __restrict__ x1, const uint4* __res
     const uint4* base = first ? (x1 + (size_t)n * HW * CV1 + cv) : (x2 + (size_t)n * HW * CV2 + (cv - CV1));
     const int stride = first ? CV1 : CV2;
     uint4* out = y + (size_t)n * HW * CV + cv;
-    int row = row0 + r;
-    for (; row + 3 * R < row1; row += 4 * R) {      // 4 independent 16-byte loads in flight per thread
-        uint4 v[4];
+    for (int row = row0 + r; row < row1; row += GN_U * R) {      // GN_U independent 16-byte loads in flight per thread
+        uint4 v[GN_U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = __ldg(base + (size_t)(row + u * R) * stride);
+        for (int u = 0; u < GN_U; ++u) {
+            const int rr = row + u * R;
+            v[u] = rr < row1 ? __ldg(base + (size_t)rr * stride) : make_uint4(0u, 0u, 0u, 0u);
+        }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < GN_U; ++u) {
+            const int rr = row + u * R;
             float f[8];
             unpack8(v[u], f);
+            if (COEF_SMEM) {
+                const float4* a4 = reinterpret_cast<const float4*>(coef + cv * 8);
+                const float4* b4 = reinterpret_cast<const float4*>(coef + CV * 8 + cv * 8);
+                const float4 a0 = a4[0], a1 = a4[1], b0 = b4[0], b1 = b4[1];
+                ca[0] = a0.x; ca[1] = a0.y; ca[2] = a0.z; ca[3] = a0.w; ca[4] = a1.x; ca[5] = a1.y; ca[6] = a1.z; ca[7] = a1.w;
+                cb[0] = b0.x; cb[1] = b0.y; cb[2] = b0.z; cb[3] = b0.w; cb[4] = b1.x; cb[5] = b1.y; cb[6] = b1.z; cb[7] = b1.w;
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float t = f[j] * ca[j] + cb[j];
-                f[j] = fuse_silu ? silu_f(t) : t;
+                const float t = fmaf(f[j], ca[j], cb[j]);
+                f[j] = fuse_silu ? silu_fast(t) : t;
             }
-            out[(size_t)(row + u * R) * CV] = pack8(f);
+            if (rr < row1) out[(size_t)rr * CV] = pack8(f);
         }
     }
-    for (; row + R < row1; row += 2 * R) {
-        uint4 v0 = __ldg(base + (size_t)row * stride);
-        uint4 v1 = __ldg(base + (size_t)(row + R) * stride);
-        float f0[8], f1[8];
-        unpack8(v0, f0);
-        unpack8(v1, f1);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float t0 = f0[j] * ca[j] + cb[j], t1 = f1[j] * ca[j] + cb[j];
-            f0[j] = fuse_silu ? silu_f(t0) : t0;
-            f1[j] = fuse_silu ? silu_f(t1) : t1;
-        }
-        out[(size_t)row * CV] = pack8(f0);
-        out[(size_t)(row + R) * CV] = pack8(f1);
+}
+
+__global__ void __launch_bounds__(512, 2) gn_apply_kernel(const uint4* __restrict__ x1, const uint4* __restrict__ x2, int CV, int CV1, int R,
+                                int HW, int rows_per_block, int G, int cpg, const float* __restrict__ meanrstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int fuse_silu,
+                                uint4* __restrict__ y) {
+    __shared__ float s_mean[64], s_rstd[64];
+    const int n = blockIdx.y;
+    if (threadIdx.x < G) {
+        s_mean[threadIdx.x] = meanrstd[((size_t)n * G + threadIdx.x) * 2];
+        s_rstd[threadIdx.x] = meanrstd[((size_t)n * G + threadIdx.x) * 2 + 1];
     }
-    for (; row < row1; row += R) {
-        uint4 v0 = __ldg(base + (size_t)row * stride);
-        float f0[8];
-        unpack8(v0, f0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float t0 = f0[j] * ca[j] + cb[j];
-            f0[j] = fuse_silu ? silu_f(t0) : t0;
+    __syncthreads();
+    gn_apply_block<false>(x1, x2, CV, CV1, R, HW, rows_per_block, cpg, n, blockIdx.x, s_mean, s_rstd, gamma, beta, fuse_silu, y, nullptr);
+}
+
+// One launch instead of two (cooperative: every CTA resident).  The N*S logical chunks -- the SAME chunks, thread
+// mapping and fold order as the two-kernel path, so every output bit is identical and independent of the batch size
+// and of the physical grid -- are dealt round-robin to the CTAs: phase 1 writes chunk partials, a sense-reversing
+// grid barrier (bar[0] arrivals, bar[1] generation) separates the phases, phase 2 folds the image statistics and
+// streams y; its reads of x hit L2 (the whole activation was read moments ago: <= 63 MB at the bench shapes).
+struct GnFusedArgs {
+    const uint4* x1; const uint4* x2;
+    int CV, CV1, R, HW, rows_per_block, S, N, G, cpg;
+    float eps;
+    float* partials;
+    const float* gamma; const float* beta;
+    int fuse_silu;
+    uint4* y;
+    unsigned int* bar;
+};
+
+__global__ void __launch_bounds__(512, 2) gn_fused_kernel(const GnFusedArgs a) {
+    extern __shared__ float sm[];
+    __shared__ float s_mean[64], s_rstd[64];
+    const int chunks = a.N * a.S;
+    for (int ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        gn_stats_block(a.x1, a.x2, a.CV, a.CV1, a.R, a.HW, a.rows_per_block, a.S, a.G, a.cpg, ch / a.S, ch % a.S, a.partials, sm);
+        __syncthreads();                                  // sm is reused by the next chunk
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned int* gen = a.bar + 1;
+        const unsigned int g0 = *gen;
+        __threadfence();
+        if (atomicAdd(a.bar, 1u) == gridDim.x - 1) {
+            a.bar[0] = 0;                                 // re-arm (the next launch is stream-ordered behind this one)
+            __threadfence();
+            atomicAdd(a.bar + 1, 1u);
+        } else {
+            while (*gen == g0) __nanosleep(32);
         }
-        out[(size_t)row * CV] = pack8(f0);
+        __threadfence();
+    }
+    __syncthreads();
+    int cur_n = -1;
+    for (int ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const int n = ch / a.S;
+        if (n != cur_n) {
+            __syncthreads();                              // previous chunk's readers of s_mean / s_rstd are done
+            if (threadIdx.x < a.G) gn_fold(a.partials, n, a.S, a.G, threadIdx.x, a.HW, a.cpg, a.eps, s_mean[threadIdx.x], s_rstd[threadIdx.x]);
+            __syncthreads();
+            const int C = a.CV * 8;
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {      // sm (the stats scratch) now holds a[0..C) | b[0..C)
+                const int g = c / a.cpg;
+                const float ca = s_rstd[g] * a.gamma[c];
+                sm[c] = ca;
+                sm[C + c] = a.beta[c] - s_mean[g] * ca;
+            }
+            __syncthreads();
+            cur_n = n;
+        }
+        gn_apply_block<true>(a.x1, a.x2, a.CV, a.CV1, a.R, a.HW, a.rows_per_block, a.cpg, n, ch % a.S, s_mean, s_rstd, a.gamma, a.beta,
+                             a.fuse_silu, a.y, sm);
     }
 }
 
@@ -277,7 +358,9 @@ size_t anysd_groupnorm_workspace_bytes(int N, int G, int C) {
     if (N <= 0 || G <= 0) return 0;
     // partials [N, 64, G, 2] | mean/rstd [N, G, 2] | per-image completion counters [N] (must be zero on first use:
     // the caller zero-fills the workspace once; every launch re-arms them)
-    return (size_t)N * GN_MAX_SPLITS * G * 2 * sizeof(float) + (size_t)N * G * 2 * sizeof(float) + (size_t)N * sizeof(unsigned int);
+    // | grid barrier of the one-launch path {arrivals, generation}
+    return (size_t)N * GN_MAX_SPLITS * G * 2 * sizeof(float) + (size_t)N * G * 2 * sizeof(float) + (size_t)N * sizeof(unsigned int) +
+           2 * sizeof(unsigned int);
 }
 
 int anysd_groupnorm_nhwc_f16(const void* x1, int C1, const void* x2, int C2, const float* gamma, const float* beta,
@@ -296,11 +379,10 @@ int anysd_groupnorm_nhwc_f16(const void* x1, int C1, const void* x2, int C2, con
     const int cpg = C / G;
     // The spatial split depends on the image geometry only (never on N): the summation order, and hence
     // every output bit, is independent of how many samples share the batch.  >= 8 row-steps per block.
-    int S = HW / (8 * g.R);
-    if (S > 32) S = 32;
-    if (S < 1) S = 1;
-    const int rpb = cdiv(HW, S);
-    S = cdiv(HW, rpb);
+    // A chunk is one batch of GN_U row-steps per thread (more only when that would exceed GN_MAX_SPLITS chunks).
+    const int batch = GN_U * g.R;
+    const int rpb = batch * cdiv(HW, (long long)batch * GN_MAX_SPLITS);
+    const int S = cdiv(HW, rpb);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)2 * g.R * C * sizeof(float);
     if (smem > 48 * 1024) {
@@ -310,6 +392,33 @@ int anysd_groupnorm_nhwc_f16(const void* x1, int C1, const void* x2, int C2, con
     float* partials = (float*)workspace;
     float* meanrstd = partials + (size_t)N * GN_MAX_SPLITS * G * 2;
     unsigned int* counters = (unsigned int*)(meanrstd + (size_t)N * G * 2);
+    // One cooperative launch when the device can hold a useful grid (ANYSD_GN_FUSED=0 forces the two-kernel path,
+    // which produces the same bits).
+    static const char* fused_env = getenv("ANYSD_GN_FUSED");
+    if (!(fused_env && fused_env[0] == '0')) {
+        static thread_local int occ_T = -1, occ_smem = -1, occ = 0, occ_dev = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (occ_T != g.T || occ_smem != (int)smem || occ_dev != dev) {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_fused_kernel, g.T, smem) != cudaSuccess) occ = 0;
+            occ_T = g.T; occ_smem = (int)smem; occ_dev = dev;
+        }
+        long long P = (long long)occ * sm_count();
+        if (P > (long long)N * S) P = (long long)N * S;
+        if (P >= 1) {
+            GnFusedArgs fa;
+            fa.x1 = (const uint4*)x1; fa.x2 = (const uint4*)x2;
+            fa.CV = g.CV; fa.CV1 = g.CV1; fa.R = g.R; fa.HW = HW; fa.rows_per_block = rpb; fa.S = S; fa.N = N; fa.G = G; fa.cpg = cpg;
+            fa.eps = eps; fa.partials = partials; fa.gamma = gamma; fa.beta = beta; fa.fuse_silu = fuse_silu; fa.y = (uint4*)y;
+            fa.bar = counters + N;
+            void* kargs[] = {(void*)&fa};
+            cudaError_t e = cudaLaunchCooperativeKernel((const void*)gn_fused_kernel, dim3((unsigned)P), dim3(g.T), kargs, smem, st);
+            ANYSD_REQUIRE(e == cudaSuccess, ANYSD_ECUDA, "groupnorm (fused): launch failed: %s", cudaGetErrorString(e));
+            return check_launch("groupnorm (fused)");
+        }
+    }
     gn_stats_kernel<<<dim3(S, N), g.T, smem, st>>>((const uint4*)x1, (const uint4*)x2, g.CV, g.CV1, g.R, HW, rpb, G, cpg, eps,
                                                    partials, meanrstd, counters);
     int rc = check_launch("groupnorm stats");

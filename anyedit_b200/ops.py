@@ -4,6 +4,7 @@ PyTorch is plumbing here: device memory, the current CUDA stream, nothing else. 
 launches hand-written sm_100a kernels from ``libanysd_b200.so`` on ``torch.cuda.current_stream()``
 and raises on failure.  Tensors are NHWC / token-major fp16 unless stated.
 """
+import os
 import ctypes as C
 
 import torch
@@ -140,6 +141,9 @@ def router_gate(table, idx, W, bias, gate):
     _count()
 
 
+_GN_FUSED = os.environ.get("ANYSD_GN_FUSED", "1")[:1] != "0"     # one cooperative launch (default) or stats + apply
+
+
 def groupnorm_workspace(N, G=32, C=0, device="cuda"):
     nbytes = _lib.load().anysd_groupnorm_workspace_bytes(N, G, C)
     return torch.zeros(nbytes // 4, dtype=torch.float32, device=device)   # completion counters start at zero
@@ -153,7 +157,7 @@ def groupnorm(x1, gamma, beta, y, N, HW, eps, silu, ws, x2=None, G=32):
         _lib.check(_lib.load().anysd_groupnorm_nhwc_f16(_ptr(x1), C1, _ptr(x2), C2, _ptr(gamma), _ptr(beta), _ptr(y), N,
                                                         HW, G, float(eps), int(bool(silu)), _ptr(ws), ws.numel() * 4,
                                                         _stream()), "groupnorm")
-    _count(2)
+    _count(1 if _GN_FUSED else 2)
 
 
 def layernorm(x, gamma, beta, y, eps=1e-5):
