@@ -91,3 +91,54 @@ def test_ddim_loop_golden():
         assert e2 < 1e-5
         e3 = (inter["x_inter"][1] - f(f"x_inter_1_S{S}")).norm() / f(f"x_inter_1_S{S}").norm()
         assert e3 < 1e-5
+
+
+def test_training_step_gradients_golden():
+    """a24: autograd through the oracle forward == autograd through the reference UNet (tests/golden/make_golden_train.py):
+    q_sample, loss value, and d loss / d {class-embedding table, cross-attention K/V weights, context tokens}."""
+    import torch.nn.functional as F
+    from oracle import train_oracle
+    g = _load("train_tiny_b.npz")
+    meta = _keys("tiny_b_keys.json")
+    shapes = {k: tuple(v) for k, v in meta["keys"].items()}
+    sd = weights.make_state_dict(shapes, int(g["seed"]))
+    assert weights.checksum(sd) == pytest.approx(float(g["wsum"]), rel=1e-12)
+    sched = ddim_oracle.register_schedule("linear", 1000, 0.00085, 0.012)
+    t = torch.tensor(g["t"])
+    noisy = train_oracle.q_sample(torch.tensor(g["x0"]), torch.tensor(g["noise"]), t, sched["alphas_cumprod"])
+    assert np.abs(noisy.numpy() - g["noisy"]).max() < 1e-6
+    gkeys = [k[len("grad__"):] for k in g.files if k.startswith("grad__")]
+    leaves = dict(sd)
+    for k in gkeys:
+        leaves[k] = sd[k].clone().requires_grad_(True)
+    ctx = torch.tensor(g["ctx"]).requires_grad_(True)
+    cfg = meta["config"]
+    with torch.enable_grad():
+        pred = unet_oracle.unet_forward(leaves, noisy, t, ctx, torch.tensor(g["y"]), num_heads=cfg.get("num_heads", -1),
+                                        num_head_channels=cfg.get("num_head_channels", -1))
+        loss = F.mse_loss(pred.float(), torch.tensor(g["noise"]), reduction="mean")
+        loss.backward()
+    assert np.abs(pred.detach().numpy() - g["pred"]).max() < 5e-6
+    assert float(loss.detach()) == pytest.approx(float(g["loss"]), rel=1e-6)
+    for k in gkeys:
+        ref = g["grad__" + k]
+        err = np.abs(leaves[k].grad.numpy() - ref).max() / np.abs(ref).max()
+        assert err < 2e-5, (k, err)
+    err = np.abs(ctx.grad.numpy() - g["grad_ctx"]).max() / np.abs(g["grad_ctx"]).max()
+    assert err < 2e-5, err
+
+
+def test_adamw_restatement_matches_torch():
+    """oracle/train_oracle.adamw_step == torch.optim.AdamW (the optimizer of train.py:486-492), 3 steps."""
+    from oracle import train_oracle
+    gen = torch.Generator().manual_seed(5)
+    p0 = torch.randn(37, 11, generator=gen)
+    grads = [torch.randn(37, 11, generator=gen) * 0.1 for _ in range(3)]
+    p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    q, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    for i, gr in enumerate(grads, 1):
+        p.grad = gr.clone()
+        opt.step()
+        q, m, v = train_oracle.adamw_step(q, gr, m, v, i, 1e-3, 0.9, 0.999, 1e-8, 1e-2)
+        assert torch.allclose(q, p.detach(), rtol=1e-6, atol=1e-7), i
