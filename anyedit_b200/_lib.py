@@ -39,6 +39,20 @@ class AttnParams(C.Structure):
     ]
 
 
+class AttnBwdParams(C.Structure):          # mirrors anysd_attn_bwd_params field for field
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("d_out", C.c_void_p),
+                ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+                ("q_batch_stride", C.c_longlong), ("k_batch_stride", C.c_longlong), ("v_batch_stride", C.c_longlong),
+                ("do_batch_stride", C.c_longlong), ("dq_batch_stride", C.c_longlong), ("dk_batch_stride", C.c_longlong),
+                ("dv_batch_stride", C.c_longlong),
+                ("ld_q", C.c_int), ("ld_k", C.c_int), ("ld_v", C.c_int), ("ld_do", C.c_int), ("ld_dq", C.c_int),
+                ("ld_dk", C.c_int), ("ld_dv", C.c_int),
+                ("B", C.c_int), ("heads", C.c_int), ("n_q", C.c_int), ("n_kv", C.c_int), ("d", C.c_int),
+                ("head_stride", C.c_int), ("qk_scale", C.c_float),
+                ("gate", C.c_void_p), ("gate_stride", C.c_int), ("d_gate", C.c_void_p),
+                ("accumulate_dq", C.c_int), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
 # name -> (restype, argtypes); mirrors include/anysd_b200.h one to one
 _VP, _I, _LL, _F, _SZ = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 SIGNATURES = {
@@ -59,6 +73,26 @@ SIGNATURES = {
     "anysd_gemm_f16": (_I, [C.POINTER(GemmParams), _VP]),
     "anysd_attention_f16": (_I, [C.POINTER(AttnParams), _VP]),
     "anysd_cfg_ddim_step_f32": (_I, [_VP, _VP, _VP, _VP, _F, _I, _VP, _VP, _LL, _I, _VP]),
+    # ---- training step ----
+    "anysd_q_sample_f32": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _LL, _VP]),
+    "anysd_mse_workspace_bytes": (_SZ, []),
+    "anysd_mse_loss_f32": (_I, [_VP, _VP, _I, _I, _I, _I, _F, _VP, _VP, _VP, _SZ, _VP]),
+    "anysd_geglu_f16": (_I, [_VP, _VP, _LL, _I, _VP]),
+    "anysd_geglu_bwd_f16": (_I, [_VP, _VP, _VP, _LL, _I, _VP]),
+    "anysd_silu_bwd_f32": (_I, [_VP, _VP, _VP, _LL, _VP]),
+    "anysd_groupnorm_bwd_nhwc_f16": (_I, [_VP, _I, _VP, _I, _VP, _VP, _VP, _VP, _I, _I, _I, _F, _I, _VP]),
+    "anysd_layernorm_bwd_f16": (_I, [_VP, _VP, _VP, _VP, _LL, _I, _F, _VP]),
+    "anysd_attention_bwd_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "anysd_attention_bwd_f16": (_I, [C.POINTER(AttnBwdParams), _VP]),
+    "anysd_colsum_f16": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "anysd_add_f16": (_I, [_VP, _VP, _LL, _VP]),
+    "anysd_split_channels_f16": (_I, [_VP, _VP, _I, _VP, _I, _LL, _VP]),
+    "anysd_zero_insert2x_f16": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
+    "anysd_sumpool2x_f16": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
+    "anysd_gemm_tn_f32": (_I, [_VP, _I, _I, _I, _VP, _I, _VP, _I, _I, _I, _I, _F, _I, _VP]),
+    "anysd_router_bwd_f32": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _F, _VP, _VP, _VP, _VP]),
+    "anysd_scatter_add_rows_f32": (_I, [_VP, _VP, _I, _I, _I, _F, _VP, _VP]),
+    "anysd_adamw_f32": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _F, _VP]),
 }
 
 _lib = None

@@ -1,0 +1,428 @@
+// Attention backward (the training step back-propagates through CrossAttention.forward,
+// attention.py:163-194, to reach the adapter experts).  First-generation tensor-core path: mma.sync m16n8k16,
+// flash-style recomputation -- the n x n probabilities are never stored; the forward keeps nothing but q, k, v.
+//
+//   s_ij = c (q_i . k_j)          c = qk_scale (natural-log units; the caller passes scale, or ln 2 when q is
+//   p_ij = exp(s_ij - lse_i)          already multiplied by scale*log2(e) -- the aux_cols packing)
+//   dp_ij = g_b (dO_i . v_j)      g_b = optional per-sample gate of the forward (expert sum)
+//   D_i  = sum_j p_ij dp_ij       (= dO_i . O_i without needing O)
+//   ds_ij = c p_ij (dp_ij - D_i)
+//   dq_i = sum_j ds_ij k_j ;  dk_j = sum_i ds_ij q_i ;  dv_j = g_b sum_i p_ij dO_i ;  dg_b = sum_ij p_ij (dO_i . v_j)
+//
+// Two kernels, no cross-CTA reduction:
+//   attn_bwd_dq_kernel : CTA = 64 query rows; pass 0 row max / sum -> lse, pass 1 D, pass 2 dq.  Writes lse (base 2)
+//                        and D to the workspace.
+//   attn_bwd_dkv_kernel: CTA = 64 key rows; every product is formed transposed (S^T = K Q^T, dP^T = V dO^T) so that
+//                        key rows are the M dimension of every mma and P^T / dS^T are A operands straight from
+//                        registers.  Head dims above 96 accumulate dk/dv in two column halves (register budget).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace anysd {
+
+constexpr int AB_T = 64, AB_THREADS = 128;
+
+struct BwdArgs {
+    const __half* q; const __half* k; const __half* v; const __half* dout;
+    __half* dq; __half* dk; __half* dv;
+    long long qbs, kbs, vbs, dobs, dqbs, dkbs, dvbs;
+    int ldq, ldk, ldv, lddo, lddq, lddk, lddv;
+    int n_q, n_kv, d, hs, heads;
+    float c_nat, c_log2;                 // qk_scale, qk_scale * log2(e)
+    const float* gate; int gate_stride; float* dgate;
+    int accumulate_dq;
+    float* lse; float* D;                // [B, heads, n_q]
+};
+
+__device__ __forceinline__ float b_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// rows [row0, row0 + AB_T) x DP columns of a head slice -> smem (zero fill outside nrows / d)
+template <int DP>
+__device__ __forceinline__ void b_load_tile(const __half* g, int ld, int row0, int nrows, int dch, __half* s) {
+    constexpr int LDS = DP + 8, CH = DP / 8;
+    for (int i = threadIdx.x; i < AB_T * CH; i += AB_THREADS) {
+        const int r = i / CH, c = i - r * CH;
+        const bool ok = (row0 + r) < nrows && c < dch;
+        const __half* src = g + (size_t)(ok ? (row0 + r) : 0) * ld + (ok ? c * 8 : 0);
+        cp_async16(smem_u32(s + r * LDS + c * 8), src, ok);
+    }
+}
+
+// acc[T/8][4] (16 x T) = A(16 x DP, rows a_row0.. of sA) * B^T, B = T rows of sB (both K-contiguous, "row.col")
+template <int DP, int T>
+__device__ __forceinline__ void b_mma_nt(float (*acc)[4], const __half* sA, int a_row0, const __half* sB, int lane) {
+    constexpr int LDS = DP + 8;
+#pragma unroll
+    for (int j = 0; j < T / 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < DP / 16; ++ks) {
+        uint32_t af[4];
+        ldmatrix_x4(af[0], af[1], af[2], af[3], smem_u32(sA + (a_row0 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8));
+#pragma unroll
+        for (int j = 0; j < T / 16; ++j) {
+            uint32_t b0, b1, b2, b3;
+            const __half* a = sB + (j * 16 + (lane & 7) + ((lane >> 4) << 3)) * LDS + ks * 16 + ((lane >> 3) & 1) * 8;
+            ldmatrix_x4(b0, b1, b2, b3, smem_u32(a));
+            mma_16816(acc[2 * j], af, b0, b1);
+            mma_16816(acc[2 * j + 1], af, b2, b3);
+        }
+    }
+}
+
+// acc[NC/8][4] (16 x NC) += A(16 x T, register fragments af[T/16][4]) * B, B = T rows x NC columns of sB starting at col0
+template <int DP, int T, int NC>
+__device__ __forceinline__ void b_mma_nn(float (*acc)[4], const uint32_t (*af)[4], const __half* sB, int col0, int lane) {
+    constexpr int LDS = DP + 8;
+#pragma unroll
+    for (int kk = 0; kk < T / 16; ++kk) {
+#pragma unroll
+        for (int dn = 0; dn < NC / 16; ++dn) {
+            uint32_t b0, b1, b2, b3;
+            const __half* a = sB + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + col0 + dn * 16 + (lane >> 4) * 8;
+            ldmatrix_x4_trans(b0, b1, b2, b3, smem_u32(a));
+            mma_16816(acc[2 * dn], af[kk], b0, b1);
+            mma_16816(acc[2 * dn + 1], af[kk], b2, b3);
+        }
+    }
+}
+
+template <int DP>
+__global__ void __launch_bounds__(AB_THREADS) attn_bwd_dq_kernel(const BwdArgs p) {
+    constexpr int LDS = DP + 8, TILE = AB_T * LDS;
+    extern __shared__ __align__(128) __half ab_smem[];
+    __half* sQ = ab_smem;
+    __half* sdO = sQ + TILE;
+    __half* sK = sdO + TILE;
+    __half* sV = sK + TILE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AB_T;
+    const int dch = p.d / 8;
+    const __half* qg = p.q + (size_t)b * p.qbs + (size_t)h * p.hs;
+    const __half* kg = p.k + (size_t)b * p.kbs + (size_t)h * p.hs;
+    const __half* vg = p.v + (size_t)b * p.vbs + (size_t)h * p.hs;
+    const __half* og = p.dout + (size_t)b * p.dobs + (size_t)h * p.d;
+    const float g = p.gate ? p.gate[(size_t)b * p.gate_stride] : 1.0f;
+    const int nt = (p.n_kv + AB_T - 1) / AB_T;
+
+    b_load_tile<DP>(qg, p.ldq, q0, p.n_q, dch, sQ);
+    b_load_tile<DP>(og, p.lddo, q0, p.n_q, dch, sdO);
+    cp_async_commit();
+
+    // ---- pass 0: log-sum-exp (base 2) of every row ----
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    for (int t = 0; t < nt; ++t) {
+        __syncthreads();
+        b_load_tile<DP>(kg, p.ldk, t * AB_T, p.n_kv, dch, sK);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        float s[AB_T / 8][4];
+        b_mma_nt<DP, AB_T>(s, sQ, warp * 16, sK, lane);
+        const int kv_left = p.n_kv - t * AB_T;
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < AB_T / 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int col = j * 8 + (lane & 3) * 2 + (e & 1);
+                const float v = col < kv_left ? s[j][e] * p.c_log2 : -INFINITY;
+                s[j][e] = v;
+                mx[e >> 1] = fmaxf(mx[e >> 1], v);
+            }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float m_new = fmaxf(m_run[r], mx[r]);
+            l_run[r] *= b_ex2(m_run[r] - m_new);
+            m_run[r] = m_new;
+        }
+#pragma unroll
+        for (int j = 0; j < AB_T / 8; ++j) {
+            l_run[0] += b_ex2(s[j][0] - m_run[0]) + b_ex2(s[j][1] - m_run[0]);
+            l_run[1] += b_ex2(s[j][2] - m_run[1]) + b_ex2(s[j][3] - m_run[1]);
+        }
+    }
+    float lse[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        float l = l_run[r];
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        lse[r] = m_run[r] + log2f(l);
+    }
+
+    // ---- pass 1: D_raw_i = sum_j p_ij (dO_i . v_j) ----
+    float d_raw[2] = {0.f, 0.f};
+    for (int t = 0; t < nt; ++t) {
+        __syncthreads();
+        b_load_tile<DP>(kg, p.ldk, t * AB_T, p.n_kv, dch, sK);
+        b_load_tile<DP>(vg, p.ldv, t * AB_T, p.n_kv, dch, sV);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        float s[AB_T / 8][4], dp[AB_T / 8][4];
+        b_mma_nt<DP, AB_T>(s, sQ, warp * 16, sK, lane);
+        b_mma_nt<DP, AB_T>(dp, sdO, warp * 16, sV, lane);
+        const int kv_left = p.n_kv - t * AB_T;
+#pragma unroll
+        for (int j = 0; j < AB_T / 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int col = j * 8 + (lane & 3) * 2 + (e & 1);
+                const float pr = col < kv_left ? b_ex2(s[j][e] * p.c_log2 - lse[e >> 1]) : 0.f;
+                d_raw[e >> 1] += pr * dp[j][e];
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        d_raw[r] += __shfl_xor_sync(0xffffffffu, d_raw[r], 1);
+        d_raw[r] += __shfl_xor_sync(0xffffffffu, d_raw[r], 2);
+    }
+    const float Dg[2] = {g * d_raw[0], g * d_raw[1]};
+    {
+        const size_t base = ((size_t)b * p.heads + h) * p.n_q;
+        float dg_part = 0.f;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = q0 + warp * 16 + (lane >> 2) + r * 8;
+            if (row < p.n_q) {
+                if ((lane & 3) == 0) {
+                    p.lse[base + row] = lse[r];
+                    p.D[base + row] = Dg[r];
+                    dg_part += d_raw[r];
+                }
+            }
+        }
+        if (p.dgate) {
+            dg_part = warp_sum(dg_part);
+            if (lane == 0 && dg_part != 0.f) atomicAdd(p.dgate + (size_t)b * p.gate_stride, dg_part);
+        }
+    }
+
+    // ---- pass 2: dq_i = sum_j ds_ij k_j ----
+    float dq[DP / 8][4];
+#pragma unroll
+    for (int i = 0; i < DP / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+    for (int t = 0; t < nt; ++t) {
+        __syncthreads();
+        b_load_tile<DP>(kg, p.ldk, t * AB_T, p.n_kv, dch, sK);
+        b_load_tile<DP>(vg, p.ldv, t * AB_T, p.n_kv, dch, sV);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        float s[AB_T / 8][4], dp[AB_T / 8][4];
+        b_mma_nt<DP, AB_T>(s, sQ, warp * 16, sK, lane);
+        b_mma_nt<DP, AB_T>(dp, sdO, warp * 16, sV, lane);
+        const int kv_left = p.n_kv - t * AB_T;
+        uint32_t dsf[AB_T / 16][4];
+#pragma unroll
+        for (int j = 0; j < AB_T / 8; ++j) {
+            float ds[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int col = j * 8 + (lane & 3) * 2 + (e & 1);
+                const float pr = col < kv_left ? b_ex2(s[j][e] * p.c_log2 - lse[e >> 1]) : 0.f;
+                ds[e] = p.c_nat * pr * (g * dp[j][e] - Dg[e >> 1]);
+            }
+            dsf[j >> 1][(j & 1) * 2 + 0] = pack_h2(ds[0], ds[1]);
+            dsf[j >> 1][(j & 1) * 2 + 1] = pack_h2(ds[2], ds[3]);
+        }
+        b_mma_nn<DP, AB_T, DP>(dq, dsf, sK, 0, lane);
+    }
+    __half* dqg = p.dq + (size_t)b * p.dqbs + (size_t)h * p.hs;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int row = q0 + warp * 16 + (lane >> 2) + r * 8;
+        if (row >= p.n_q) continue;
+#pragma unroll
+        for (int i = 0; i < DP / 8; ++i) {
+            const int col = i * 8 + (lane & 3) * 2;
+            if (col >= p.hs) continue;
+            float v0 = dq[i][r * 2], v1 = dq[i][r * 2 + 1];
+            if (col >= p.d) v0 = v1 = 0.f;                     // padding columns of the head stay exact zeros
+            __half2* dst = reinterpret_cast<__half2*>(dqg + (size_t)row * p.lddq + col);
+            if (p.accumulate_dq) {
+                const float2 prev = __half22float2(*dst);
+                v0 += prev.x;
+                v1 += prev.y;
+            }
+            *dst = __floats2half2_rn(v0, v1);
+        }
+    }
+}
+
+template <int DP, int DC>
+__global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const BwdArgs p) {
+    constexpr int LDS = DP + 8, TILE = AB_T * LDS;
+    extern __shared__ __align__(128) __half ab_smem[];
+    __half* sK = ab_smem;
+    __half* sV = sK + TILE;
+    __half* sQ = sV + TILE;
+    __half* sdO = sQ + TILE;
+    float* s_lse = reinterpret_cast<float*>(sdO + TILE);
+    float* s_D = s_lse + AB_T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * AB_T;
+    const int dch = p.d / 8;
+    const __half* qg = p.q + (size_t)b * p.qbs + (size_t)h * p.hs;
+    const __half* kg = p.k + (size_t)b * p.kbs + (size_t)h * p.hs;
+    const __half* vg = p.v + (size_t)b * p.vbs + (size_t)h * p.hs;
+    const __half* og = p.dout + (size_t)b * p.dobs + (size_t)h * p.d;
+    const float g = p.gate ? p.gate[(size_t)b * p.gate_stride] : 1.0f;
+    const size_t sbase = ((size_t)b * p.heads + h) * p.n_q;
+    const int nqt = (p.n_q + AB_T - 1) / AB_T;
+
+    b_load_tile<DP>(kg, p.ldk, k0, p.n_kv, dch, sK);
+    b_load_tile<DP>(vg, p.ldv, k0, p.n_kv, dch, sV);
+    cp_async_commit();
+
+    for (int c0 = 0; c0 < DP; c0 += DC) {
+        float dk[DC / 8][4], dv[DC / 8][4];
+#pragma unroll
+        for (int i = 0; i < DC / 8; ++i) {
+            dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+            dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+        }
+        for (int t = 0; t < nqt; ++t) {
+            __syncthreads();
+            b_load_tile<DP>(qg, p.ldq, t * AB_T, p.n_q, dch, sQ);
+            b_load_tile<DP>(og, p.lddo, t * AB_T, p.n_q, dch, sdO);
+            cp_async_commit();
+            if (tid < AB_T) {
+                const int row = t * AB_T + tid;
+                s_lse[tid] = row < p.n_q ? p.lse[sbase + row] : INFINITY;     // exp2(x - inf) = 0: padded queries vanish
+                s_D[tid] = row < p.n_q ? p.D[sbase + row] : 0.f;
+            }
+            cp_async_wait<0>();
+            __syncthreads();
+            float st[AB_T / 8][4], dpt[AB_T / 8][4];
+            b_mma_nt<DP, AB_T>(st, sK, warp * 16, sQ, lane);        // S^T: key rows x query columns
+            b_mma_nt<DP, AB_T>(dpt, sV, warp * 16, sdO, lane);      // dP^T (without the gate)
+            uint32_t pf[AB_T / 16][4], dsf[AB_T / 16][4];
+#pragma unroll
+            for (int j = 0; j < AB_T / 8; ++j) {
+                float pr[4], ds[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = j * 8 + (lane & 3) * 2 + (e & 1);
+                    pr[e] = b_ex2(st[j][e] * p.c_log2 - s_lse[col]);
+                    ds[e] = p.c_nat * pr[e] * (g * dpt[j][e] - s_D[col]);
+                }
+                pf[j >> 1][(j & 1) * 2 + 0] = pack_h2(pr[0], pr[1]);
+                pf[j >> 1][(j & 1) * 2 + 1] = pack_h2(pr[2], pr[3]);
+                dsf[j >> 1][(j & 1) * 2 + 0] = pack_h2(ds[0], ds[1]);
+                dsf[j >> 1][(j & 1) * 2 + 1] = pack_h2(ds[2], ds[3]);
+            }
+            b_mma_nn<DP, AB_T, DC>(dv, pf, sdO, c0, lane);          // dv += P^T dO
+            b_mma_nn<DP, AB_T, DC>(dk, dsf, sQ, c0, lane);          // dk += dS^T Q
+        }
+        __half* dkg = p.dk + (size_t)b * p.dkbs + (size_t)h * p.hs;
+        __half* dvg = p.dv + (size_t)b * p.dvbs + (size_t)h * p.hs;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = k0 + warp * 16 + (lane >> 2) + r * 8;
+            if (row >= p.n_kv) continue;
+#pragma unroll
+            for (int i = 0; i < DC / 8; ++i) {
+                const int col = c0 + i * 8 + (lane & 3) * 2;
+                if (col >= p.hs) continue;
+                const bool real = col < p.d;
+                *reinterpret_cast<__half2*>(dkg + (size_t)row * p.lddk + col) =
+                    __floats2half2_rn(real ? dk[i][r * 2] : 0.f, real ? dk[i][r * 2 + 1] : 0.f);
+                *reinterpret_cast<__half2*>(dvg + (size_t)row * p.lddv + col) =
+                    __floats2half2_rn(real ? g * dv[i][r * 2] : 0.f, real ? g * dv[i][r * 2 + 1] : 0.f);
+            }
+        }
+    }
+}
+
+template <int DP>
+static int launch_bwd(const BwdArgs& a, int B, cudaStream_t st, bool need_dkv) {
+    constexpr int LDS = DP + 8;
+    constexpr int DC = DP > 96 ? DP / 2 : DP;
+    const int smem = 4 * AB_T * LDS * (int)sizeof(__half) + 2 * AB_T * (int)sizeof(float);
+    static bool done[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!done[dev]) {
+        cudaFuncSetAttribute(attn_bwd_dq_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(attn_bwd_dkv_kernel<DP, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        done[dev] = true;
+    }
+    attn_bwd_dq_kernel<DP><<<dim3(cdiv(a.n_q, AB_T), a.heads, B), AB_THREADS, smem, st>>>(a);
+    int rc = check_launch("attention backward (dq)");
+    if (rc || !need_dkv) return rc;
+    attn_bwd_dkv_kernel<DP, DC><<<dim3(cdiv(a.n_kv, AB_T), a.heads, B), AB_THREADS, smem, st>>>(a);
+    return check_launch("attention backward (dk, dv)");
+}
+
+}  // namespace anysd
+
+using namespace anysd;
+
+extern "C" size_t anysd_attention_bwd_workspace_bytes(int B, int heads, int n_q) {
+    if (B <= 0 || heads <= 0 || n_q <= 0) return 0;
+    return (size_t)2 * B * heads * n_q * sizeof(float);
+}
+
+extern "C" int anysd_attention_bwd_f16(const anysd_attn_bwd_params* p, anysd_stream_t stream) {
+    ANYSD_REQUIRE(p != nullptr, ANYSD_EINVAL, "attention_bwd: null params");
+    ANYSD_REQUIRE(p->q && p->k && p->v && p->d_out && p->dq && p->workspace, ANYSD_EINVAL, "attention_bwd: null pointer");
+    ANYSD_REQUIRE((p->dk == nullptr) == (p->dv == nullptr), ANYSD_EINVAL, "attention_bwd: dk and dv go together");
+    ANYSD_REQUIRE(p->B > 0 && p->heads > 0 && p->n_q > 0 && p->n_kv > 0, ANYSD_EINVAL, "attention_bwd: bad sizes");
+    ANYSD_REQUIRE(p->d > 0 && p->d % 8 == 0 && p->d <= 160, ANYSD_EUNSUPPORTED,
+                  "attention_bwd: head dim %d must be a multiple of 8, at most 160", p->d);
+    const int hs = p->head_stride > 0 ? p->head_stride : p->d;
+    const int dp = (p->d + 15) / 16 * 16;
+    ANYSD_REQUIRE(hs % 8 == 0 && hs >= p->d && hs <= dp, ANYSD_EINVAL,
+                  "attention_bwd: head_stride %d must be a multiple of 8 in [d, ceil16(d)]", hs);
+    ANYSD_REQUIRE(p->ld_q % 8 == 0 && p->ld_k % 8 == 0 && p->ld_v % 8 == 0 && p->ld_do % 8 == 0 && p->ld_dq % 2 == 0 &&
+                      (!p->dk || (p->ld_dk % 2 == 0 && p->ld_dv % 2 == 0)),
+                  ANYSD_EINVAL, "attention_bwd: leading dims must be multiples of 8 (inputs) / 2 (outputs)");
+    ANYSD_REQUIRE(p->q_batch_stride % 8 == 0 && p->k_batch_stride % 8 == 0 && p->v_batch_stride % 8 == 0 &&
+                      p->do_batch_stride % 8 == 0,
+                  ANYSD_EINVAL, "attention_bwd: batch strides must be multiples of 8");
+    ANYSD_REQUIRE(((uintptr_t)p->q % 16) == 0 && ((uintptr_t)p->k % 16) == 0 && ((uintptr_t)p->v % 16) == 0 &&
+                      ((uintptr_t)p->d_out % 16) == 0 && ((uintptr_t)p->dq % 4) == 0,
+                  ANYSD_EINVAL, "attention_bwd: pointers must be 16-byte aligned");
+    ANYSD_REQUIRE(p->workspace_bytes >= anysd_attention_bwd_workspace_bytes(p->B, p->heads, p->n_q), ANYSD_EINVAL,
+                  "attention_bwd: workspace too small");
+    ANYSD_REQUIRE(p->heads <= 65535 && p->B <= 65535, ANYSD_EINVAL, "attention_bwd: grid too large");
+    BwdArgs a;
+    a.q = (const __half*)p->q; a.k = (const __half*)p->k; a.v = (const __half*)p->v; a.dout = (const __half*)p->d_out;
+    a.dq = (__half*)p->dq; a.dk = (__half*)p->dk; a.dv = (__half*)p->dv;
+    a.qbs = p->q_batch_stride; a.kbs = p->k_batch_stride; a.vbs = p->v_batch_stride; a.dobs = p->do_batch_stride;
+    a.dqbs = p->dq_batch_stride; a.dkbs = p->dk_batch_stride; a.dvbs = p->dv_batch_stride;
+    a.ldq = p->ld_q; a.ldk = p->ld_k; a.ldv = p->ld_v; a.lddo = p->ld_do; a.lddq = p->ld_dq; a.lddk = p->ld_dk; a.lddv = p->ld_dv;
+    a.n_q = p->n_q; a.n_kv = p->n_kv; a.d = p->d; a.hs = hs; a.heads = p->heads;
+    a.c_nat = p->qk_scale; a.c_log2 = p->qk_scale * 1.4426950408889634f;
+    a.gate = p->gate; a.gate_stride = p->gate_stride; a.dgate = p->d_gate;
+    a.accumulate_dq = p->accumulate_dq;
+    a.lse = (float*)p->workspace; a.D = a.lse + (size_t)p->B * p->heads * p->n_q;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool need = p->dk != nullptr;
+    switch (dp) {
+        case 16: return launch_bwd<16>(a, p->B, st, need);
+        case 32: return launch_bwd<32>(a, p->B, st, need);
+        case 48: return launch_bwd<48>(a, p->B, st, need);
+        case 64: return launch_bwd<64>(a, p->B, st, need);
+        case 80: return launch_bwd<80>(a, p->B, st, need);
+        case 96: return launch_bwd<96>(a, p->B, st, need);
+        case 128: return launch_bwd<128>(a, p->B, st, need);
+        case 160: return launch_bwd<160>(a, p->B, st, need);
+        default:
+            set_error("attention_bwd: head dim %d not supported", p->d);
+            return ANYSD_EUNSUPPORTED;
+    }
+}

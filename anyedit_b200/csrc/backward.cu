@@ -1,0 +1,574 @@
+// Backward / training-step kernels (train.py:629-710).  First correct generation: simple, HBM- or
+// latency-bound elementwise and reduction kernels; every contraction of the backward pass reuses anysd_gemm_f16 with
+// transposed / rotated weight packs (host side), attention has its own file (attention_bwd.cu).
+// Activation gradients are fp16 (the caller scales the loss), statistics and parameter gradients fp32.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace anysd {
+
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.0f / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu_grad_f(float z) {                 // d/dz z*sigmoid(z)
+    const float s = sigmoid_f(z);
+    return s * (1.0f + z * (1.0f - s));
+}
+
+// ---- GEGLU (attention.py:49-56), pre = interleaved (a_j, gate_j) ------------------------------------------------
+__global__ void geglu_fwd_kernel(const uint4* __restrict__ pre, uint4* __restrict__ out, long long nvec) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        float f0[8], f1[8], o[8];
+        unpack8(__ldg(pre + 2 * i), f0);
+        unpack8(__ldg(pre + 2 * i + 1), f1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            o[j] = f0[2 * j] * gelu_erf_f(f0[2 * j + 1]);
+            o[4 + j] = f1[2 * j] * gelu_erf_f(f1[2 * j + 1]);
+        }
+        out[i] = pack8(o);
+    }
+}
+__device__ __forceinline__ void geglu_grad(float a, float g, float dy, float& da, float& dg) {
+    const float cdf = 0.5f * (1.0f + erff(g * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * g * g);
+    da = dy * g * cdf;
+    dg = dy * a * (cdf + g * pdf);
+}
+__global__ void geglu_bwd_kernel(const uint4* __restrict__ pre, const uint4* __restrict__ dout, uint4* __restrict__ dpre,
+                                 long long nvec) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        float f0[8], f1[8], dy[8], d0[8], d1[8];
+        unpack8(__ldg(pre + 2 * i), f0);
+        unpack8(__ldg(pre + 2 * i + 1), f1);
+        unpack8(__ldg(dout + i), dy);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            geglu_grad(f0[2 * j], f0[2 * j + 1], dy[j], d0[2 * j], d0[2 * j + 1]);
+            geglu_grad(f1[2 * j], f1[2 * j + 1], dy[4 + j], d1[2 * j], d1[2 * j + 1]);
+        }
+        dpre[2 * i] = pack8(d0);
+        dpre[2 * i + 1] = pack8(d1);
+    }
+}
+
+__global__ void silu_bwd_f32_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dx[i] = dy[i] * silu_grad_f(x[i]);
+}
+
+// ---- GroupNorm(+SiLU) backward: one CTA per (image, group) -----------------------------------------------------
+// y = [silu](z), z = xhat * gamma + beta, xhat = (x - mean) * rstd over the group's HW x cpg elements:
+//   dz = dy * silu'(z);  w = dz * gamma;  dx = rstd * (w - mean(w) - xhat * mean(w * xhat))
+__global__ void __launch_bounds__(256) gn_bwd_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     const __half* __restrict__ dy, __half* __restrict__ dx, int HW, int G,
+                                                     float eps, int fuse_silu) {
+    const int n = blockIdx.y, g = blockIdx.x;
+    const int C = C1 + C2, cpg = C / G, c0 = g * cpg;
+    const int total = HW * cpg;
+    __shared__ float red[2][8];
+    __shared__ float bc[4];
+    auto X = [&](int row, int c) -> float {
+        return c < C1 ? __half2float(x1[((size_t)n * HW + row) * C1 + c]) : __half2float(x2[((size_t)n * HW + row) * C2 + (c - C1)]);
+    };
+    auto block_sum2 = [&](float a, float b, float& oa, float& ob) {
+        a = warp_sum(a);
+        b = warp_sum(b);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) {
+            red[0][threadIdx.x >> 5] = a;
+            red[1][threadIdx.x >> 5] = b;
+        }
+        __syncthreads();
+        float ta = 0.f, tb = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            ta += red[0][w];
+            tb += red[1][w];
+        }
+        oa = ta;
+        ob = tb;
+    };
+    float s = 0.f, q = 0.f;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const float v = X(i / cpg, c0 + i % cpg);
+        s += v;
+        q += v * v;
+    }
+    float S, Q;
+    block_sum2(s, q, S, Q);
+    const float mean = S / total;
+    float var = Q / total - mean * mean;
+    var = var < 0.f ? 0.f : var;
+    const float rstd = rsqrtf(var + eps);
+    float a = 0.f, b = 0.f;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int row = i / cpg, c = c0 + i % cpg;
+        const float xh = (X(row, c) - mean) * rstd;
+        float d = __half2float(dy[((size_t)n * HW + row) * C + c]);
+        if (fuse_silu) d *= silu_grad_f(xh * gamma[c] + beta[c]);
+        const float w = d * gamma[c];
+        a += w;
+        b += w * xh;
+    }
+    float A, Bq;
+    block_sum2(a, b, A, Bq);
+    const float mw = A / total, mwx = Bq / total;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int row = i / cpg, c = c0 + i % cpg;
+        const float xh = (X(row, c) - mean) * rstd;
+        float d = __half2float(dy[((size_t)n * HW + row) * C + c]);
+        if (fuse_silu) d *= silu_grad_f(xh * gamma[c] + beta[c]);
+        const float w = d * gamma[c];
+        dx[((size_t)n * HW + row) * C + c] = __float2half_rn(rstd * (w - mw - xh * mwx));
+    }
+    (void)bc;
+}
+
+// ---- LayerNorm backward: one warp per token row ----------------------------------------------------------------
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
+                                                     const uint4* __restrict__ dy, uint4* __restrict__ dx, long long M, int CV,
+                                                     float eps) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    const uint4* xr = x + row * CV;
+    const uint4* dr = dy + row * CV;
+    const float inv_c = 1.0f / (CV * 8);
+    float s = 0.f;
+    for (int v = lane; v < CV; v += 32) {
+        float f[8];
+        unpack8(__ldg(xr + v), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[j];
+    }
+    const float mean = warp_sum(s) * inv_c;
+    float q = 0.f;
+    for (int v = lane; v < CV; v += 32) {
+        float f[8];
+        unpack8(__ldg(xr + v), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q += (f[j] - mean) * (f[j] - mean);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
+    float a = 0.f, b = 0.f;
+    for (int v = lane; v < CV; v += 32) {
+        float f[8], d[8];
+        unpack8(__ldg(xr + v), f);
+        unpack8(__ldg(dr + v), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float w = d[j] * gamma[v * 8 + j];
+            a += w;
+            b += w * (f[j] - mean) * rstd;
+        }
+    }
+    const float mw = warp_sum(a) * inv_c, mwx = warp_sum(b) * inv_c;
+    for (int v = lane; v < CV; v += 32) {
+        float f[8], d[8], o[8];
+        unpack8(__ldg(xr + v), f);
+        unpack8(__ldg(dr + v), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xh = (f[j] - mean) * rstd;
+            o[j] = rstd * (d[j] * gamma[v * 8 + j] - mw - xh * mwx);
+        }
+        dx[row * CV + v] = pack8(o);
+    }
+}
+
+// ---- per-image column sums: x [N, rows, C] fp16 -> out [N, ld_out] fp32 (time-embedding row add backward) ---------
+__global__ void __launch_bounds__(256) colsum_kernel(const uint4* __restrict__ x, float* __restrict__ out, int rows, int CV, int ld_out,
+                                                     int accumulate) {
+    __shared__ float sm[32][8 * 8 + 1];
+    const int n = blockIdx.y;
+    const int cvl = threadIdx.x & 7, rl = threadIdx.x >> 3;       // 8 vector columns x 32 row lanes
+    const int cv = blockIdx.x * 8 + cvl;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (cv < CV) {
+        for (int r = rl; r < rows; r += 32) {
+            float f[8];
+            unpack8(__ldg(x + ((size_t)n * rows + r) * CV + cv), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[rl][cvl * 8 + j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float t = 0.f;
+        for (int r = 0; r < 32; ++r) t += sm[r][threadIdx.x];
+        const int c = blockIdx.x * 64 + threadIdx.x;
+        if (c < CV * 8) {
+            float* o = out + (size_t)n * ld_out + c;
+            *o = accumulate ? *o + t : t;
+        }
+    }
+}
+
+__global__ void add_f16_kernel(uint4* __restrict__ y, const uint4* __restrict__ x, long long nvec) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        float a[8], b[8];
+        unpack8(y[i], a);
+        unpack8(__ldg(x + i), b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += b[j];
+        y[i] = pack8(a);
+    }
+}
+
+__global__ void split_kernel(const uint4* __restrict__ src, uint4* __restrict__ a, int ca, uint4* __restrict__ b, int cb, long long total) {
+    const int cv = ca + cb;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / cv;
+        const int c = (int)(i - row * cv);
+        const uint4 v = __ldg(src + i);
+        if (c < ca) a[row * ca + c] = v;
+        else b[row * cb + (c - ca)] = v;
+    }
+}
+
+// dst [N, 2H, 2W, C]: dst[2y, 2x] = src[y, x], zero elsewhere (backward of a stride-2 conv = conv over this)
+__global__ void zero_insert2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int H, int W, int CV, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % CV);
+        long long t = i / CV;
+        const int x = (int)(t % (2 * W));
+        t /= 2 * W;
+        const int y = (int)(t % (2 * H));
+        const long long n = t / (2 * H);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (!(x & 1) && !(y & 1)) v = __ldg(src + ((n * H + (y >> 1)) * W + (x >> 1)) * CV + c);
+        dst[i] = v;
+    }
+}
+// dst [N, H, W, C] = sum of the 2x2 block of src [N, 2H, 2W, C] (backward of nearest x2)
+__global__ void sumpool2x_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int H, int W, int CV, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % CV);
+        long long t = i / CV;
+        const int x = (int)(t % W);
+        t /= W;
+        const int y = (int)(t % H);
+        const long long n = t / H;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                float f[8];
+                unpack8(__ldg(src + ((n * 2 * H + 2 * y + dy) * (2 * W) + 2 * x + dx) * CV + c), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+        dst[i] = pack8(acc);
+    }
+}
+
+// ---- loss (train.py:696) ----------------------------------------------------------------------------------------
+// pred, target fp32 NCHW [N, C, HW]; loss += mean((pred - target)^2); dpred NHWC fp16 [N, HW, Cpad] =
+// grad_scale * 2 (pred - target) / numel, zero in the padding channels.  Two-stage deterministic sum: partial[blk].
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, int N, int C, int HW,
+                                                  int Cpad, float grad_scale, __half* __restrict__ dpred, float* __restrict__ partial) {
+    const long long numel = (long long)N * C * HW;
+    const float k = grad_scale * 2.0f / (float)numel;
+    float acc = 0.f;
+    const long long pix = (long long)N * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pix; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / HW, hw = i - n * HW;
+        for (int c = 0; c < Cpad; ++c) {
+            float d = 0.f;
+            if (c < C) {
+                const long long idx = (n * C + c) * HW + hw;
+                d = pred[idx] - target[idx];
+                acc += d * d;
+            }
+            dpred[i * Cpad + c] = __float2half_rn(k * d);
+        }
+    }
+    __shared__ float red[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        partial[blockIdx.x] = t / (float)numel;
+    }
+}
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < n; ++i) t += (double)partial[i];
+        *out = (float)t;
+    }
+}
+
+// noisy = sqrt(acp[t]) x0 + sqrt(1 - acp[t]) noise (train.py:641; ddpm.py:356-359), fp32 NCHW, tables on the device
+__global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const long long* __restrict__ t,
+                                const float* __restrict__ sqrt_acp, const float* __restrict__ sqrt_1m_acp, float* __restrict__ out,
+                                long long n_per, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / n_per;
+        const long long tt = t[b];
+        out[i] = sqrt_acp[tt] * x0[i] + sqrt_1m_acp[tt] * noise[i];
+    }
+}
+
+// torch.optim.AdamW single-tensor step (train.py:486-492): grad is multiplied by grad_scale (1 / loss scale) first
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                             float grad_scale) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gr = g[i] * grad_scale;
+        float w = p[i] * (1.0f - lr * wd);
+        const float mi = b1 * m[i] + (1.0f - b1) * gr;
+        const float vi = b2 * v[i] + (1.0f - b2) * gr * gr;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        w -= (lr / bc1) * mi / denom;
+        p[i] = w;
+    }
+}
+
+// ---- small-M weight gradient: out[ka, kb] (+)= alpha * sum_m A[m, col(ka)] * B[m, kb] -----------------------------
+// A [M, lda] fp16 with optional head padding (logical column ka lives at (ka / head_d) * head_stride + ka % head_d),
+// B [M, ldb] fp16, out fp32 [Ka, ldo].  32 x 32 output tile per CTA, 16 x 16 threads, 2 x 2 outputs each.
+__global__ void __launch_bounds__(256) gemm_tn_kernel(const __half* __restrict__ A, int lda, int head_d, int head_stride,
+                                                      const __half* __restrict__ B, int ldb, float* __restrict__ out, int ldo,
+                                                      int M, int Ka, int Kb, float alpha, int accumulate) {
+    __shared__ float sA[32][33], sB[32][33];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    for (int m0 = 0; m0 < M; m0 += 32) {
+        for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+            const int mm = i >> 5, cc = i & 31;
+            const int m = m0 + mm;
+            float va = 0.f, vb = 0.f;
+            if (m < M) {
+                const int ka = a0 + cc;
+                if (ka < Ka) {
+                    const int col = head_d > 0 ? (ka / head_d) * head_stride + ka % head_d : ka;
+                    va = __half2float(A[(size_t)m * lda + col]);
+                }
+                const int kb = b0 + cc;
+                if (kb < Kb) vb = __half2float(B[(size_t)m * ldb + kb]);
+            }
+            sA[mm][cc] = va;
+            sB[mm][cc] = vb;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int mm = 0; mm < 32; ++mm) {
+            const float x0 = sA[mm][ty * 2], x1 = sA[mm][ty * 2 + 1];
+            const float y0 = sB[mm][tx * 2], y1 = sB[mm][tx * 2 + 1];
+            acc[0][0] += x0 * y0; acc[0][1] += x0 * y1;
+            acc[1][0] += x1 * y0; acc[1][1] += x1 * y1;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int ka = a0 + ty * 2 + i, kb = b0 + tx * 2 + j;
+            if (ka < Ka && kb < Kb) {
+                float* o = out + (size_t)ka * ldo + kb;
+                *o = (accumulate ? *o : 0.f) + alpha * acc[i][j];
+            }
+        }
+}
+
+// ---- router backward (restated spec, oracle/anysd_oracle.py): g = softmax(W te + b) per (sample, layer) -----------
+// dlogit = g * (dg - sum_e g dg);  dW[l] += dlogit^T te;  db[l] += sum_n dlogit;  dte[n] += sum_l dlogit W[l]
+// grid = L, block = 256.  gates / dgates [N, L, E] fp32; te [N, D] fp32 (gathered task embeddings); W [L, E, D] fp16.
+__global__ void __launch_bounds__(256) router_bwd_kernel(const float* __restrict__ gates, const float* __restrict__ dgates,
+                                                         const float* __restrict__ te, const __half* __restrict__ W, int N, int L, int E,
+                                                         int D, float alpha, float* __restrict__ dW, float* __restrict__ db,
+                                                         float* __restrict__ dte) {
+    extern __shared__ float dl[];                 // [N, E]
+    const int l = blockIdx.x;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const float* g = gates + ((size_t)n * L + l) * E;
+        const float* dg = dgates + ((size_t)n * L + l) * E;
+        float dot = 0.f;
+        for (int e = 0; e < E; ++e) dot += g[e] * dg[e];
+        for (int e = 0; e < E; ++e) dl[n * E + e] = alpha * g[e] * (dg[e] - dot);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < E * D; i += blockDim.x) {
+        const int e = i / D, d = i - e * D;
+        float t = 0.f;
+        for (int n = 0; n < N; ++n) t += dl[n * E + e] * te[(size_t)n * D + d];
+        dW[((size_t)l * E + e) * D + d] += t;
+    }
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        float t = 0.f;
+        for (int n = 0; n < N; ++n) t += dl[n * E + e];
+        db[(size_t)l * E + e] += t;
+    }
+    for (int i = threadIdx.x; i < N * D; i += blockDim.x) {
+        const int n = i / D, d = i - n * D;
+        float t = 0.f;
+        for (int e = 0; e < E; ++e) t += dl[n * E + e] * __half2float(W[((size_t)l * E + e) * D + d]);
+        atomicAdd(dte + (size_t)n * D + d, t);
+    }
+}
+
+// table_grad[idx[n]] += alpha * src[n]   (task-embedding gather backward)
+__global__ void scatter_add_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, int rows, int D, int table_rows,
+                                        float alpha, float* __restrict__ table_grad) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * D; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i / D), d = (int)(i - (long long)n * D);
+        const long long r = idx[n];
+        if (r >= 0 && r < table_rows) atomicAdd(table_grad + r * D + d, alpha * src[i]);
+    }
+}
+
+static int grid_for(long long n, int block = 256, int per_sm = 8) {
+    long long g = (n + block - 1) / block;
+    const long long cap = (long long)sm_count() * per_sm;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace anysd
+
+using namespace anysd;
+
+extern "C" {
+
+int anysd_geglu_f16(const void* pre, void* out, long long M, int inner, anysd_stream_t stream) {
+    ANYSD_REQUIRE(pre && out && M > 0 && inner > 0 && inner % 8 == 0, ANYSD_EINVAL, "geglu: bad args (inner %% 8 == 0)");
+    const long long nvec = M * inner / 8;
+    geglu_fwd_kernel<<<grid_for(nvec), 256, 0, (cudaStream_t)stream>>>((const uint4*)pre, (uint4*)out, nvec);
+    return check_launch("geglu");
+}
+
+int anysd_geglu_bwd_f16(const void* pre, const void* d_out, void* d_pre, long long M, int inner, anysd_stream_t stream) {
+    ANYSD_REQUIRE(pre && d_out && d_pre && M > 0 && inner > 0 && inner % 8 == 0, ANYSD_EINVAL, "geglu_bwd: bad args");
+    const long long nvec = M * inner / 8;
+    geglu_bwd_kernel<<<grid_for(nvec), 256, 0, (cudaStream_t)stream>>>((const uint4*)pre, (const uint4*)d_out, (uint4*)d_pre, nvec);
+    return check_launch("geglu_bwd");
+}
+
+int anysd_silu_bwd_f32(const float* x, const float* dy, float* dx, long long n, anysd_stream_t stream) {
+    ANYSD_REQUIRE(x && dy && dx && n > 0, ANYSD_EINVAL, "silu_bwd: bad args");
+    silu_bwd_f32_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, n);
+    return check_launch("silu_bwd");
+}
+
+int anysd_groupnorm_bwd_nhwc_f16(const void* x1, int C1, const void* x2, int C2, const float* gamma, const float* beta,
+                                 const void* dy, void* dx, int N, int HW, int G, float eps, int fuse_silu,
+                                 anysd_stream_t stream) {
+    ANYSD_REQUIRE(x1 && gamma && beta && dy && dx, ANYSD_EINVAL, "groupnorm_bwd: null pointer");
+    if (x2 == nullptr) C2 = 0;
+    const int C = C1 + C2;
+    ANYSD_REQUIRE(N > 0 && HW > 0 && G > 0 && C1 > 0 && C2 >= 0 && C % G == 0 && N <= 65535, ANYSD_EINVAL, "groupnorm_bwd: bad shape");
+    gn_bwd_kernel<<<dim3(G, N), 256, 0, (cudaStream_t)stream>>>((const __half*)x1, C1, (const __half*)x2, C2, gamma, beta,
+                                                               (const __half*)dy, (__half*)dx, HW, G, eps, fuse_silu);
+    return check_launch("groupnorm_bwd");
+}
+
+int anysd_layernorm_bwd_f16(const void* x, const float* gamma, const void* dy, void* dx, long long M, int C, float eps,
+                            anysd_stream_t stream) {
+    ANYSD_REQUIRE(x && gamma && dy && dx && M > 0 && C > 0 && C % 8 == 0, ANYSD_EINVAL, "layernorm_bwd: bad args (C %% 8 == 0)");
+    ln_bwd_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, gamma, (const uint4*)dy, (uint4*)dx, M, C / 8, eps);
+    return check_launch("layernorm_bwd");
+}
+
+int anysd_colsum_f16(const void* x, float* out, int N, int rows, int C, int ld_out, int accumulate, anysd_stream_t stream) {
+    ANYSD_REQUIRE(x && out && N > 0 && rows > 0 && C > 0 && C % 8 == 0 && ld_out >= C && N <= 65535, ANYSD_EINVAL, "colsum: bad args");
+    colsum_kernel<<<dim3(cdiv(C, 64), N), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, out, rows, C / 8, ld_out, accumulate);
+    return check_launch("colsum");
+}
+
+int anysd_add_f16(void* y, const void* x, long long n, anysd_stream_t stream) {
+    ANYSD_REQUIRE(y && x && n > 0 && n % 8 == 0, ANYSD_EINVAL, "add: bad args (n %% 8 == 0)");
+    add_f16_kernel<<<grid_for(n / 8), 256, 0, (cudaStream_t)stream>>>((uint4*)y, (const uint4*)x, n / 8);
+    return check_launch("add");
+}
+
+int anysd_split_channels_f16(const void* src, void* a, int Ca, void* b, int Cb, long long rows, anysd_stream_t stream) {
+    ANYSD_REQUIRE(src && a && b && rows > 0 && Ca > 0 && Cb > 0 && Ca % 8 == 0 && Cb % 8 == 0, ANYSD_EINVAL, "split: bad args");
+    const long long total = rows * ((Ca + Cb) / 8);
+    split_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)a, Ca / 8, (uint4*)b, Cb / 8, total);
+    return check_launch("split");
+}
+
+int anysd_zero_insert2x_f16(const void* src, void* dst, int N, int H, int W, int C, anysd_stream_t stream) {
+    ANYSD_REQUIRE(src && dst && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, ANYSD_EINVAL, "zero_insert2x: bad args");
+    const long long total = (long long)N * 2 * H * 2 * W * (C / 8);
+    zero_insert2x_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)dst, H, W, C / 8, total);
+    return check_launch("zero_insert2x");
+}
+
+int anysd_sumpool2x_f16(const void* src, void* dst, int N, int H, int W, int C, anysd_stream_t stream) {
+    ANYSD_REQUIRE(src && dst && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, ANYSD_EINVAL, "sumpool2x: bad args");
+    const long long total = (long long)N * H * W * (C / 8);
+    sumpool2x_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)dst, H, W, C / 8, total);
+    return check_launch("sumpool2x");
+}
+
+size_t anysd_mse_workspace_bytes(void) { return (size_t)1024 * sizeof(float); }
+
+int anysd_mse_loss_f32(const float* pred, const float* target, int N, int C, int HW, int Cpad, float grad_scale, void* d_pred,
+                       float* loss, void* workspace, size_t workspace_bytes, anysd_stream_t stream) {
+    ANYSD_REQUIRE(pred && target && d_pred && loss && workspace, ANYSD_EINVAL, "mse_loss: null pointer");
+    ANYSD_REQUIRE(N > 0 && C > 0 && HW > 0 && Cpad >= C && workspace_bytes >= anysd_mse_workspace_bytes(), ANYSD_EINVAL, "mse_loss: bad args");
+    int grid = grid_for((long long)N * HW, 256, 4);
+    if (grid > 1024) grid = 1024;
+    mse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, target, N, C, HW, Cpad, grad_scale, (__half*)d_pred, (float*)workspace);
+    int rc = check_launch("mse_loss");
+    if (rc) return rc;
+    sum_partials_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const float*)workspace, grid, loss);
+    return check_launch("mse_loss (sum)");
+}
+
+int anysd_q_sample_f32(const float* x0, const float* noise, const long long* t, const float* sqrt_acp, const float* sqrt_1m_acp,
+                       float* out, int B, long long n_per, anysd_stream_t stream) {
+    ANYSD_REQUIRE(x0 && noise && t && sqrt_acp && sqrt_1m_acp && out && B > 0 && n_per > 0, ANYSD_EINVAL, "q_sample: bad args");
+    const long long total = (long long)B * n_per;
+    q_sample_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x0, noise, t, sqrt_acp, sqrt_1m_acp, out, n_per, total);
+    return check_launch("q_sample");
+}
+
+int anysd_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float grad_scale, anysd_stream_t stream) {
+    ANYSD_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, ANYSD_EINVAL, "adamw: bad args (step counts from 1)");
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2s = sqrtf(1.0f - powf(beta2, (float)step));
+    adamw_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                              weight_decay, bc1, bc2s, grad_scale);
+    return check_launch("adamw");
+}
+
+int anysd_gemm_tn_f32(const void* A, int lda, int head_d, int head_stride, const void* B, int ldb, float* out, int ldo, int M,
+                      int Ka, int Kb, float alpha, int accumulate, anysd_stream_t stream) {
+    ANYSD_REQUIRE(A && B && out && M > 0 && Ka > 0 && Kb > 0 && lda > 0 && ldb >= Kb && ldo >= Kb, ANYSD_EINVAL, "gemm_tn: bad args");
+    ANYSD_REQUIRE(head_d == 0 || (head_d > 0 && head_stride >= head_d), ANYSD_EINVAL, "gemm_tn: bad head mapping");
+    gemm_tn_kernel<<<dim3(cdiv(Kb, 32), cdiv(Ka, 32)), 256, 0, (cudaStream_t)stream>>>((const __half*)A, lda, head_d, head_stride,
+                                                                                     (const __half*)B, ldb, out, ldo, M, Ka, Kb, alpha,
+                                                                                     accumulate);
+    return check_launch("gemm_tn");
+}
+
+int anysd_router_bwd_f32(const float* gates, const float* d_gates, const float* te, const void* W, int N, int L, int E, int D,
+                         float alpha, float* dW, float* db, float* d_te, anysd_stream_t stream) {
+    ANYSD_REQUIRE(gates && d_gates && te && W && dW && db && d_te, ANYSD_EINVAL, "router_bwd: null pointer");
+    ANYSD_REQUIRE(N > 0 && L > 0 && E > 0 && D > 0 && (size_t)N * E * sizeof(float) <= 48 * 1024, ANYSD_EINVAL, "router_bwd: bad sizes");
+    router_bwd_kernel<<<L, 256, (size_t)N * E * sizeof(float), (cudaStream_t)stream>>>(gates, d_gates, te, (const __half*)W, N, L, E, D,
+                                                                                     alpha, dW, db, d_te);
+    return check_launch("router_bwd");
+}
+
+int anysd_scatter_add_rows_f32(const float* src, const long long* idx, int rows, int D, int table_rows, float alpha, float* table_grad,
+                               anysd_stream_t stream) {
+    ANYSD_REQUIRE(src && idx && table_grad && rows > 0 && D > 0 && table_rows > 0, ANYSD_EINVAL, "scatter_add_rows: bad args");
+    scatter_add_rows_kernel<<<grid_for((long long)rows * D), 256, 0, (cudaStream_t)stream>>>(src, idx, rows, D, table_rows, alpha, table_grad);
+    return check_launch("scatter_add_rows");
+}
+}

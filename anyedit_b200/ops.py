@@ -263,3 +263,153 @@ def cfg_ddim_step(x, eps, coef, scale, cfg, x_prev, pred_x0=None, noise=None):
                                                    int(bool(cfg)), _ptr(x_prev), _ptr(pred_x0), n_per, B, _stream()),
                "cfg_ddim_step")
     _count()
+
+
+# ---- training step: thin wrappers, same conventions as above -------------------------------------
+def q_sample(x0, noise, t, sqrt_acp, sqrt_1m_acp, out):
+    _cuda(x0, noise, t, out)
+    B = x0.shape[0]
+    _lib.check(_lib.load().anysd_q_sample_f32(_ptr(x0), _ptr(noise), _ptr(t), _ptr(sqrt_acp), _ptr(sqrt_1m_acp), _ptr(out), B,
+                                              x0.numel() // B, _stream()), "q_sample")
+    _count()
+
+
+def mse_loss(pred, target, d_pred, loss, grad_scale=1.0):
+    """pred/target fp32 NCHW; d_pred fp16 [N, HW, Cpad]; loss: 1-element fp32 tensor."""
+    _cuda(pred, target, d_pred, loss)
+    N, Cc = pred.shape[0], pred.shape[1]
+    HW = pred.numel() // (N * Cc)
+    ws = torch.empty(_lib.load().anysd_mse_workspace_bytes() // 4, dtype=torch.float32, device=pred.device)
+    _lib.check(_lib.load().anysd_mse_loss_f32(_ptr(pred), _ptr(target), N, Cc, HW, d_pred.shape[-1], float(grad_scale), _ptr(d_pred),
+                                              _ptr(loss), _ptr(ws), ws.numel() * 4, _stream()), "mse_loss")
+    _count(2)
+
+
+def geglu(pre, out):
+    _cuda(pre, out)
+    inner = out.shape[-1]
+    _lib.check(_lib.load().anysd_geglu_f16(_ptr(pre), _ptr(out), out.numel() // inner, inner, _stream()), "geglu")
+    _count()
+
+
+def geglu_bwd(pre, d_out, d_pre):
+    _cuda(pre, d_out, d_pre)
+    inner = d_out.shape[-1]
+    _lib.check(_lib.load().anysd_geglu_bwd_f16(_ptr(pre), _ptr(d_out), _ptr(d_pre), d_out.numel() // inner, inner, _stream()), "geglu_bwd")
+    _count()
+
+
+def silu_bwd_f32(x, dy, dx):
+    _cuda(x, dy, dx)
+    _lib.check(_lib.load().anysd_silu_bwd_f32(_ptr(x), _ptr(dy), _ptr(dx), x.numel(), _stream()), "silu_bwd")
+    _count()
+
+
+def groupnorm_bwd(x1, gamma, beta, dy, dx, N, HW, eps, silu, x2=None, G=32):
+    _cuda(x1, dy, dx)
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    _lib.check(_lib.load().anysd_groupnorm_bwd_nhwc_f16(_ptr(x1), C1, _ptr(x2), C2, _ptr(gamma), _ptr(beta), _ptr(dy), _ptr(dx), N, HW,
+                                                        G, float(eps), int(bool(silu)), _stream()), "groupnorm_bwd")
+    _count()
+
+
+def layernorm_bwd(x, gamma, dy, dx, eps=1e-5):
+    _cuda(x, dy, dx)
+    Cc = x.shape[-1]
+    _lib.check(_lib.load().anysd_layernorm_bwd_f16(_ptr(x), _ptr(gamma), _ptr(dy), _ptr(dx), x.numel() // Cc, Cc, float(eps), _stream()),
+               "layernorm_bwd")
+    _count()
+
+
+def attention_bwd(q, k, v, d_out, dq, dk, dv, B, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk=0, ld_dv=0,
+                  qk_scale=None, gate=None, gate_stride=1, d_gate=None, accumulate_dq=False, head_stride=0):
+    """Backward of `attention` (recomputing the probabilities).  dk/dv None: frozen K/V."""
+    _cuda(q, k, v, d_out, dq)
+    p = _lib.AttnBwdParams()
+    p.q, p.k, p.v, p.d_out, p.dq = q.data_ptr(), k.data_ptr(), v.data_ptr(), d_out.data_ptr(), dq.data_ptr()
+    p.dk = dk.data_ptr() if dk is not None else None
+    p.dv = dv.data_ptr() if dv is not None else None
+    p.q_batch_stride, p.k_batch_stride, p.v_batch_stride = n_q * ld_q, n_kv * ld_k, n_kv * ld_v
+    p.do_batch_stride, p.dq_batch_stride = n_q * ld_do, n_q * ld_dq
+    p.dk_batch_stride, p.dv_batch_stride = n_kv * ld_dk, n_kv * ld_dv
+    p.ld_q, p.ld_k, p.ld_v, p.ld_do, p.ld_dq, p.ld_dk, p.ld_dv = ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk, ld_dv
+    p.B, p.heads, p.n_q, p.n_kv, p.d, p.head_stride = B, heads, n_q, n_kv, d, head_stride
+    p.qk_scale = float(qk_scale if qk_scale is not None else d ** -0.5)
+    p.gate = gate.data_ptr() if gate is not None else None
+    p.gate_stride = gate_stride
+    p.d_gate = d_gate.data_ptr() if d_gate is not None else None
+    p.accumulate_dq = int(bool(accumulate_dq))
+    nbytes = _lib.load().anysd_attention_bwd_workspace_bytes(B, heads, n_q)
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=q.device)
+    p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
+    _lib.check(_lib.load().anysd_attention_bwd_f16(C.byref(p), _stream()), "attention_bwd")
+    _count(2 if dk is not None else 1)
+
+
+def colsum(x, out, N, rows, accumulate=False):
+    """x [N, rows, C] fp16 -> out[:N, :C] (fp32, row stride out.stride(0))."""
+    _cuda(x, out)
+    _lib.check(_lib.load().anysd_colsum_f16(_ptr(x), _ptr(out), N, rows, x.shape[-1], out.stride(0), int(bool(accumulate)), _stream()),
+               "colsum")
+    _count()
+
+
+def add_(y, x):
+    _cuda(y, x)
+    assert y.numel() == x.numel() and y.is_contiguous() and x.is_contiguous()
+    _lib.check(_lib.load().anysd_add_f16(_ptr(y), _ptr(x), y.numel(), _stream()), "add")
+    _count()
+
+
+def split_channels(src, a, b):
+    _cuda(src, a, b)
+    _lib.check(_lib.load().anysd_split_channels_f16(_ptr(src), _ptr(a), a.shape[-1], _ptr(b), b.shape[-1],
+                                                    src.numel() // src.shape[-1], _stream()), "split_channels")
+    _count()
+
+
+def zero_insert2x(src, dst):
+    _cuda(src, dst)
+    N, H, W, Cc = src.shape
+    _lib.check(_lib.load().anysd_zero_insert2x_f16(_ptr(src), _ptr(dst), N, H, W, Cc, _stream()), "zero_insert2x")
+    _count()
+
+
+def sumpool2x(src, dst):
+    _cuda(src, dst)
+    N, H, W, Cc = dst.shape
+    _lib.check(_lib.load().anysd_sumpool2x_f16(_ptr(src), _ptr(dst), N, H, W, Cc, _stream()), "sumpool2x")
+    _count()
+
+
+def gemm_tn(A, B, out, M, Ka, Kb, lda=None, ldb=None, alpha=1.0, accumulate=False, head_d=0, head_stride=0):
+    """out[ka, kb] (+)= alpha * sum_m A[m, col(ka)] * B[m, kb]; A, B fp16, out fp32."""
+    _cuda(A, B, out)
+    _lib.check(_lib.load().anysd_gemm_tn_f32(_ptr(A), lda if lda is not None else A.stride(0), head_d, head_stride, _ptr(B),
+                                             ldb if ldb is not None else B.stride(0), _ptr(out), out.stride(0), M, Ka, Kb, float(alpha),
+                                             int(bool(accumulate)), _stream()), "gemm_tn")
+    _count()
+
+
+def router_bwd(gates, d_gates, te, W, dW, db, d_te, alpha=1.0):
+    _cuda(gates, d_gates, te, W, dW, db, d_te)
+    N, L, E = gates.shape
+    _lib.check(_lib.load().anysd_router_bwd_f32(_ptr(gates), _ptr(d_gates), _ptr(te), _ptr(W), N, L, E, te.shape[-1], float(alpha),
+                                                _ptr(dW), _ptr(db), _ptr(d_te), _stream()), "router_bwd")
+    _count()
+
+
+def scatter_add_rows(src, idx, table_grad, alpha=1.0):
+    _cuda(src, idx, table_grad)
+    _lib.check(_lib.load().anysd_scatter_add_rows_f32(_ptr(src), _ptr(idx), src.shape[0], src.shape[1], table_grad.shape[0], float(alpha),
+                                                      _ptr(table_grad), _stream()), "scatter_add_rows")
+    _count()
+
+
+def adamw_(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
+    _cuda(param, grad, exp_avg, exp_avg_sq)
+    _lib.check(_lib.load().anysd_adamw_f32(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr),
+                                           float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale),
+                                           _stream()), "adamw")
+    _count()

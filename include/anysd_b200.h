@@ -159,6 +159,95 @@ int anysd_cfg_ddim_step_f32(const float* x, const float* eps, const float* noise
                             float guidance_scale, int cfg, float* x_prev, float* pred_x0, long long n_per_batch,
                             int B, anysd_stream_t stream);
 
+/* ==== training step (train.py:629-710) =====================================================
+ * The reference back-propagates mse_loss(MoE(...), noise) through the frozen UNet with torch autograd
+ * (train.py:694-703); trainables are the adapter experts, the router and the task-embedding table
+ * (train.py:486-492).  Below: every non-contraction backward op of the path.  dX of linears / convs reuses
+ * anysd_gemm_f16 with transposed / 180-degree-rotated weight packs (anyedit_b200/training.py).
+ * Activation gradients are fp16 (the caller scales the loss), statistics and parameter gradients fp32. */
+
+/* noisy = sqrt(acp[t]) x0 + sqrt(1 - acp[t]) noise  (train.py:641 add_noise == ddpm.py:356-359); fp32 NCHW,
+ * t int64 [B], tables fp32 [T] on the device. */
+int anysd_q_sample_f32(const float* x0, const float* noise, const long long* t, const float* sqrt_acp,
+                       const float* sqrt_1m_acp, float* out, int B, long long n_per_batch, anysd_stream_t stream);
+
+/* F.mse_loss(pred.float(), target.float(), "mean") (train.py:696) and its gradient.  pred/target fp32 NCHW
+ * [N, C, HW]; *loss = mean; d_pred fp16 NHWC [N, HW, Cpad] = grad_scale * 2 (pred - target) / numel with zero
+ * padding channels (the layout the output conv's backward contraction consumes).  Deterministic two-stage sum. */
+size_t anysd_mse_workspace_bytes(void);
+int anysd_mse_loss_f32(const float* pred, const float* target, int N, int C, int HW, int Cpad, float grad_scale,
+                       void* d_pred, float* loss, void* workspace, size_t workspace_bytes, anysd_stream_t stream);
+
+/* GEGLU (attention.py:49-56) un-fused for training: pre [M, 2*inner] fp16 with (a_j, gate_j) interleaved (the
+ * packing of anysd_gemm_f16 act = 2), out[m, j] = a_j * gelu(gate_j); backward writes d_pre in the same layout. */
+int anysd_geglu_f16(const void* pre, void* out, long long M, int inner, anysd_stream_t stream);
+int anysd_geglu_bwd_f16(const void* pre, const void* d_out, void* d_pre, long long M, int inner, anysd_stream_t stream);
+
+/* dx = dy * silu'(x), fp32 (time-embedding path, openaimodel.py:217-223, 526-530) */
+int anysd_silu_bwd_f32(const float* x, const float* dy, float* dx, long long n, anysd_stream_t stream);
+
+/* Backward of anysd_groupnorm_nhwc_f16 (util.py:202-219): x = channel concat of x1 [N,HW,C1] and x2 [N,HW,C2]
+ * (x2 may be NULL), dy and dx dense [N, HW, C1+C2] fp16; statistics are recomputed. */
+int anysd_groupnorm_bwd_nhwc_f16(const void* x1, int C1, const void* x2, int C2, const float* gamma, const float* beta,
+                                 const void* dy, void* dx, int N, int HW, int G, float eps, int fuse_silu,
+                                 anysd_stream_t stream);
+
+/* Backward of anysd_layernorm_f16 w.r.t. x (attention.py:262-264); x, dy, dx [M, C] fp16. */
+int anysd_layernorm_bwd_f16(const void* x, const float* gamma, const void* dy, void* dx, long long M, int C, float eps,
+                            anysd_stream_t stream);
+
+/* Backward of anysd_attention_f16 (CrossAttention.forward, attention.py:163-194), recomputing the probabilities
+ * from q, k, v (nothing saved by the forward).  Natural-log score = qk_scale * (q . k): pass the softmax scale, or
+ * ln(2) when q was packed with scale*log2(e) (aux_cols).  d_out [B, n_q, ld_do] with head h at columns
+ * [h*d, (h+1)*d); q/k/v and dq/dk/dv use head_stride (padding columns of dq/dk/dv are written as zeros).
+ * gate: forward's per-sample factor; d_gate[b*gate_stride] += sum(dO . attn) (atomic, fp32) when not NULL.
+ * dk/dv may both be NULL (frozen text K/V).  workspace >= anysd_attention_bwd_workspace_bytes(B, heads, n_q). */
+typedef struct {
+    const void* q; const void* k; const void* v; const void* d_out;
+    void* dq; void* dk; void* dv;
+    long long q_batch_stride, k_batch_stride, v_batch_stride, do_batch_stride, dq_batch_stride, dk_batch_stride,
+        dv_batch_stride;                                                       /* elements */
+    int ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk, ld_dv;
+    int B, heads, n_q, n_kv, d, head_stride;
+    float qk_scale;
+    const float* gate; int gate_stride; float* d_gate;
+    int accumulate_dq;      /* 1: dq += (the experts share the text attention's q) */
+    void* workspace; size_t workspace_bytes;
+} anysd_attn_bwd_params;
+size_t anysd_attention_bwd_workspace_bytes(int B, int heads, int n_q);
+int anysd_attention_bwd_f16(const anysd_attn_bwd_params* p, anysd_stream_t stream);
+
+/* out[n, c] (+)= sum_rows x[n, r, c]: gradient of the per-image time-embedding row add (openaimodel.py:262-263) */
+int anysd_colsum_f16(const void* x, float* out, int N, int rows, int C, int ld_out, int accumulate, anysd_stream_t stream);
+/* y += x (gradient accumulation where a tensor feeds two consumers: residual / skip connections) */
+int anysd_add_f16(void* y, const void* x, long long n, anysd_stream_t stream);
+/* backward of anysd_concat_channels_f16 (th.cat([h, hs.pop()], 1), openaimodel.py:780) */
+int anysd_split_channels_f16(const void* src, void* a, int Ca, void* b, int Cb, long long rows, anysd_stream_t stream);
+/* Downsample (conv stride 2, openaimodel.py:148-150) backward = rotated conv over the zero-inserted gradient */
+int anysd_zero_insert2x_f16(const void* src, void* dst, int N, int H, int W, int C, anysd_stream_t stream);
+/* Upsample (nearest x2, openaimodel.py:110-115) backward = 2x2 sum pooling */
+int anysd_sumpool2x_f16(const void* src, void* dst, int N, int H, int W, int C, anysd_stream_t stream);
+
+/* Weight gradient with few rows: out[ka, kb] (+)= alpha * sum_m A[m, col(ka)] B[m, kb]; A, B fp16, out fp32.
+ * head_d > 0: A has padded heads, logical column ka sits at (ka / head_d) * head_stride + ka % head_d.
+ * (dW of to_k_ip / to_v_ip: A = dK_e / dV_e, B = visual tokens; ip_adapter/attention_processor.py:160-166) */
+int anysd_gemm_tn_f32(const void* A, int lda, int head_d, int head_stride, const void* B, int ldb, float* out, int ldo,
+                      int M, int Ka, int Kb, float alpha, int accumulate, anysd_stream_t stream);
+
+/* Router backward (restated spec, oracle/anysd_oracle.py): gates = softmax(W te + b) per (sample, layer);
+ * dW [L,E,D] +=, db [L,E] +=, d_te [N,D] += (atomic).  gates/d_gates fp32 [N,L,E], te fp32 [N,D], W fp16 [L,E,D]. */
+int anysd_router_bwd_f32(const float* gates, const float* d_gates, const float* te, const void* W, int N, int L, int E,
+                         int D, float alpha, float* dW, float* db, float* d_te, anysd_stream_t stream);
+/* table_grad[idx[n], :] += alpha * src[n, :] (backward of the task-embedding gather, openaimodel.py:770-772 slot) */
+int anysd_scatter_add_rows_f32(const float* src, const long long* idx, int rows, int D, int table_rows, float alpha,
+                               float* table_grad, anysd_stream_t stream);
+
+/* torch.optim.AdamW single-tensor step (train.py:486-492), step counted from 1; grad is multiplied by grad_scale
+ * (1 / loss scale) before use. */
+int anysd_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                    anysd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

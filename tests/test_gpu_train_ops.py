@@ -1,0 +1,268 @@
+"""Per-op parity of the training-step kernels against torch autograd on fp32 CPU copies of the same
+fp16-rounded operands.  Called through the C ABI (anyedit_b200.ops)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from anyedit_b200 import ops as o
+    return o
+
+
+def randn(seed, *shape, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def h16(t):
+    return t.half().float()
+
+
+@pytest.mark.parametrize("B,heads,nq,nkv,d,self_attn,gated,ln2", [
+    (2, 3, 100, 77, 40, False, True, False), (1, 2, 130, 130, 64, True, False, False), (2, 2, 70, 70, 160, True, False, False),
+    (1, 3, 65, 16, 24, False, True, True), (2, 8, 256, 256, 40, True, False, True), (1, 2, 200, 300, 80, False, False, False)])
+def test_attention_backward(ops, B, heads, nq, nkv, d, self_attn, gated, ln2):
+    """dq, dk, dv and the gate gradient of softmax(c q k^T) v * gate vs autograd; padded head stride; ln2 = the
+    aux_cols packing where q already carries scale*log2(e) and the natural-log factor is ln 2."""
+    from anyedit_b200.unet import head_stride_for
+    hs = head_stride_for(d)
+    C, Cp = heads * d, heads * hs
+    scale = d ** -0.5
+    q, k, v = h16(randn(1, B, nq, heads, d)), h16(randn(2, B, nkv, heads, d)), h16(randn(3, B, nkv, heads, d))
+    if ln2:
+        q = h16(q * scale * math.log2(math.e))
+    c = math.log(2.0) if ln2 else scale
+    dO = h16(randn(4, B, nq, heads, d) * 0.1)
+    gate = torch.rand(B, generator=torch.Generator().manual_seed(5)) + 0.25 if gated else None
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    gr = gate.clone().requires_grad_(True) if gated else None
+    s = torch.einsum("bihd,bjhd->bhij", qr, kr) * c
+    o = torch.einsum("bhij,bjhd->bihd", s.softmax(-1), vr)
+    if gated:
+        o = o * gr.view(B, 1, 1, 1)
+    o.backward(dO)
+
+    def pad(t):
+        out = torch.zeros(B, t.shape[1], heads, hs, dtype=torch.float16)
+        out[..., :d] = t
+        return out.reshape(B, t.shape[1], Cp).cuda().contiguous()
+
+    q16, k16, v16 = pad(q), pad(k), pad(v)
+    dO16 = dO.reshape(B, nq, C).half().cuda().contiguous()
+    dq = torch.full((B, nq, Cp), float("nan"), dtype=torch.float16, device="cuda")
+    dk = torch.full((B, nkv, Cp), float("nan"), dtype=torch.float16, device="cuda")
+    dv = torch.full((B, nkv, Cp), float("nan"), dtype=torch.float16, device="cuda")
+    g_dev = gate.cuda() if gated else None
+    dg = torch.zeros(B, device="cuda") if gated else None
+    ops.attention_bwd(q16, k16, v16, dO16, dq, dk, dv, B, heads, nq, nkv, d, Cp, Cp, Cp, C, Cp, Cp, Cp, qk_scale=c, gate=g_dev,
+                      d_gate=dg, head_stride=hs)
+    torch.cuda.synchronize()
+    unpad = lambda t, n: t.float().cpu().reshape(B, n, heads, hs)
+    for name, got, ref, n in (("dq", dq, qr.grad, nq), ("dk", dk, kr.grad, nkv), ("dv", dv, vr.grad, nkv)):
+        g4 = unpad(got, n)
+        assert torch.isfinite(g4).all(), name
+        assert float(g4[..., d:].abs().max()) == 0.0 if hs > d else True, name       # padding columns stay zero
+        e = rel(g4[..., :d], ref)
+        assert e < 4e-3, (name, e)
+    if gated:
+        e = rel(dg, gr.grad)
+        assert e < 4e-3, ("d_gate", e)
+    # frozen K/V (text cross-attention): dq only, accumulated onto an existing gradient
+    dq2 = dq.clone()
+    ops.attention_bwd(q16, k16, v16, dO16, dq2, None, None, B, heads, nq, nkv, d, Cp, Cp, Cp, C, Cp, qk_scale=c, gate=g_dev,
+                      head_stride=hs, accumulate_dq=True)
+    e = rel(unpad(dq2, nq)[..., :d], 2 * qr.grad)
+    assert e < 4e-3, ("dq accumulate", e)
+
+
+@pytest.mark.parametrize("N,HW,C1,C2,silu", [(2, 60, 64, 0, True), (3, 35, 96, 32, True), (2, 16, 320, 0, False), (1, 100, 64, 128, False)])
+def test_groupnorm_backward(ops, N, HW, C1, C2, silu):
+    C = C1 + C2
+    x = h16(randn(11, N, HW, C) * 1.5 + 0.3)
+    gamma, beta = randn(12, C) * 0.5 + 1.0, randn(13, C) * 0.2
+    dy = h16(randn(14, N, HW, C) * 0.1)
+    xr = x.clone().requires_grad_(True)
+    y = F.group_norm(xr.permute(0, 2, 1), 32, gamma, beta, eps=1e-5)
+    if silu:
+        y = F.silu(y)
+    y.backward(dy.permute(0, 2, 1))
+    x1 = x[..., :C1].contiguous().half().cuda()
+    x2 = x[..., C1:].contiguous().half().cuda() if C2 else None
+    dx = torch.empty(N, HW, C, dtype=torch.float16, device="cuda")
+    ops.groupnorm_bwd(x1, gamma.cuda(), beta.cuda(), dy.half().cuda(), dx, N, HW, 1e-5, silu, x2=x2)
+    e = rel(dx, xr.grad)
+    assert e < 3e-3, e
+
+
+@pytest.mark.parametrize("M,C", [(50, 64), (33, 320), (9, 1280)])
+def test_layernorm_backward(ops, M, C):
+    x = h16(randn(21, M, C) * 2.0 + 0.5)
+    gamma = randn(22, C) * 0.5 + 1.0
+    dy = h16(randn(23, M, C) * 0.1)
+    xr = x.clone().requires_grad_(True)
+    F.layer_norm(xr, (C,), gamma, torch.zeros(C), 1e-5).backward(dy)
+    dx = torch.empty(M, C, dtype=torch.float16, device="cuda")
+    ops.layernorm_bwd(x.half().cuda(), gamma.cuda(), dy.half().cuda(), dx)
+    e = rel(dx, xr.grad)
+    assert e < 3e-3, e
+
+
+def test_geglu_forward_backward(ops):
+    M, inner = 37, 64
+    pre = h16(randn(31, M, inner, 2) * 1.5)                    # [..., 0] = a, [..., 1] = gate (interleaved columns)
+    dy = h16(randn(32, M, inner) * 0.1)
+    pr = pre.clone().requires_grad_(True)
+    out = pr[..., 0] * F.gelu(pr[..., 1])
+    out.backward(dy)
+    pre16 = pre.reshape(M, 2 * inner).half().cuda()
+    o = torch.empty(M, inner, dtype=torch.float16, device="cuda")
+    ops.geglu(pre16, o)
+    assert rel(o, out.detach()) < 1e-3
+    dpre = torch.empty(M, 2 * inner, dtype=torch.float16, device="cuda")
+    ops.geglu_bwd(pre16, dy.half().cuda(), dpre)
+    assert rel(dpre.view(M, inner, 2), pr.grad) < 2e-3
+
+
+def test_conv_and_linear_input_gradients_reuse_the_forward_contraction(ops):
+    """dX of conv3x3 (stride 1, stride 2 via zero insertion, after nearest x2 via sum pooling) and of a linear layer are
+    anysd_gemm_f16 launches on rotated / transposed weight packs (anyedit_b200.training)."""
+    from anyedit_b200 import training as T
+    N, H, W, Ci, Co = 2, 8, 12, 64, 128
+    x = h16(randn(41, N, Ci, H, W))
+    w = h16(randn(42, Co, Ci, 3, 3) * (9 * Ci) ** -0.5)
+    to_nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().half().cuda()
+    from_nhwc = lambda t, n, h, ww: t.float().cpu().view(n, h, ww, -1).permute(0, 3, 1, 2)
+    wb = T.pack_conv3_dx(w, "cuda")
+    # stride 1
+    xr = x.clone().requires_grad_(True)
+    y = F.conv2d(xr, w, padding=1)
+    dy = h16(randn(43, *y.shape) * 0.1)
+    y.backward(dy)
+    dx = torch.empty(N * H * W, Ci, dtype=torch.float16, device="cuda")
+    ops.conv3x3(to_nhwc(dy), wb, dx)
+    assert rel(from_nhwc(dx, N, H, W), xr.grad) < 2e-3
+    # stride 2 (Downsample)
+    xr = x.clone().requires_grad_(True)
+    y = F.conv2d(xr, w, padding=1, stride=2)
+    dy = h16(randn(44, *y.shape) * 0.1)
+    y.backward(dy)
+    up = torch.empty(N, H, W, Co, dtype=torch.float16, device="cuda")
+    ops.zero_insert2x(to_nhwc(dy), up)
+    ops.conv3x3(up, wb, dx)
+    assert rel(from_nhwc(dx, N, H, W), xr.grad) < 2e-3
+    # nearest x2 then conv (Upsample)
+    xr = x.clone().requires_grad_(True)
+    y = F.conv2d(F.interpolate(xr, scale_factor=2, mode="nearest"), w, padding=1)
+    dy = h16(randn(45, *y.shape) * 0.1)
+    y.backward(dy)
+    dbig = torch.empty(N * 2 * H * 2 * W, Ci, dtype=torch.float16, device="cuda")
+    ops.conv3x3(to_nhwc(dy), wb, dbig)
+    dsm = torch.empty(N, H, W, Ci, dtype=torch.float16, device="cuda")
+    ops.sumpool2x(dbig.view(N, 2 * H, 2 * W, Ci), dsm)
+    assert rel(from_nhwc(dsm, N, H, W), xr.grad) < 2e-3
+    # linear
+    M, K, Nn = 70, 96, 160
+    a, wl = h16(randn(46, M, K)), h16(randn(47, Nn, K) * K ** -0.5)
+    ar = a.clone().requires_grad_(True)
+    dyl = h16(randn(48, M, Nn) * 0.1)
+    F.linear(ar, wl).backward(dyl)
+    dxl = torch.empty(M, K, dtype=torch.float16, device="cuda")
+    ops.gemm(dyl.half().cuda(), T.pack_linear_dx(wl, "cuda"), dxl)
+    assert rel(dxl, ar.grad) < 2e-3
+
+
+def test_small_training_kernels(ops):
+    from oracle import ddim_oracle, train_oracle
+    # q_sample
+    sched = ddim_oracle.register_schedule("linear", 1000, 0.00085, 0.012)
+    x0, noise = randn(51, 3, 4, 8, 8), randn(52, 3, 4, 8, 8)
+    t = torch.tensor([0, 500, 999])
+    out = torch.empty(3, 4, 8, 8, device="cuda")
+    ops.q_sample(x0.cuda(), noise.cuda(), t.cuda(), sched["sqrt_alphas_cumprod"].cuda(), sched["sqrt_one_minus_alphas_cumprod"].cuda(), out)
+    ref = train_oracle.q_sample(x0, noise, t, sched["alphas_cumprod"])
+    assert float((out.cpu() - ref).abs().max()) < 1e-6
+    # mse loss + gradient in the padded NHWC layout
+    pred, target = randn(53, 2, 4, 6, 5), randn(54, 2, 4, 6, 5)
+    pr = pred.clone().requires_grad_(True)
+    loss_ref = F.mse_loss(pr, target)
+    loss_ref.backward()
+    dp = torch.empty(2, 30, 64, dtype=torch.float16, device="cuda")
+    loss = torch.zeros(1, device="cuda")
+    ops.mse_loss(pred.cuda(), target.cuda(), dp, loss, grad_scale=256.0)
+    assert float(loss) == pytest.approx(float(loss_ref), rel=1e-5)
+    got = dp.float().cpu().view(2, 6, 5, 64)
+    assert float(got[..., 4:].abs().max()) == 0.0
+    assert rel(got[..., :4].permute(0, 3, 1, 2) / 256.0, pr.grad) < 1e-3
+    # colsum / add / split
+    x = h16(randn(55, 3, 50, 72))
+    cs = torch.zeros(3, 100, device="cuda")
+    ops.colsum(x.half().cuda(), cs, 3, 50)
+    assert rel(cs[:, :72], x.sum(1)) < 1e-5 and float(cs[:, 72:].abs().max()) == 0.0
+    ops.colsum(x.half().cuda(), cs, 3, 50, accumulate=True)
+    assert rel(cs[:, :72], 2 * x.sum(1)) < 1e-5
+    y = h16(randn(56, 40, 64))
+    yy = y.half().cuda()
+    ops.add_(yy, y.half().cuda())
+    assert torch.equal(yy.cpu(), (2 * y).half())
+    src = h16(randn(57, 33, 24 + 40)).half().cuda()
+    a, b = torch.empty(33, 24, dtype=torch.float16, device="cuda"), torch.empty(33, 40, dtype=torch.float16, device="cuda")
+    ops.split_channels(src, a, b)
+    assert torch.equal(torch.cat([a, b], 1), src)
+    # silu backward (fp32)
+    xs, ds = randn(58, 5, 64), randn(59, 5, 64)
+    xr = xs.clone().requires_grad_(True)
+    F.silu(xr).backward(ds)
+    dxs = torch.empty(5, 64, device="cuda")
+    ops.silu_bwd_f32(xs.cuda(), ds.cuda(), dxs)
+    assert rel(dxs, xr.grad) < 1e-5
+    # weight gradient with padded heads
+    M, heads, d, hs, Kb = 48, 3, 24, 32, 40
+    A = h16(randn(60, M, heads, d))
+    Bm = h16(randn(61, M, Kb))
+    Ap = torch.zeros(M, heads, hs)
+    Ap[..., :d] = A
+    outw = torch.zeros(heads * d, Kb, device="cuda")
+    ops.gemm_tn(Ap.reshape(M, heads * hs).half().cuda(), Bm.half().cuda(), outw, M, heads * d, Kb, alpha=0.5, head_d=d, head_stride=hs)
+    assert rel(outw, 0.5 * A.reshape(M, heads * d).t() @ Bm) < 1e-5
+    # AdamW
+    p0, g0 = randn(62, 1000), randn(63, 1000) * 0.1
+    p, m, v = p0.clone().cuda(), torch.zeros(1000, device="cuda"), torch.zeros(1000, device="cuda")
+    q, mq, vq = p0.clone(), torch.zeros(1000), torch.zeros(1000)
+    for step in (1, 2, 3):
+        ops.adamw_(p, (g0 * 128).cuda(), m, v, step, 1e-3, 0.9, 0.999, 1e-8, 1e-2, grad_scale=1 / 128)
+        q, mq, vq = train_oracle.adamw_step(q, g0, mq, vq, step, 1e-3, 0.9, 0.999, 1e-8, 1e-2)
+    assert float((p.cpu() - q).abs().max()) < 1e-6
+
+
+def test_router_backward_and_scatter(ops):
+    N, L, E, D, T = 5, 3, 4, 64, 7
+    table = randn(71, T, D)
+    idx = torch.tensor([0, 3, 3, 6, 1])
+    W = h16(randn(72, L, E, D) * 0.2)
+    b = randn(73, L, E) * 0.1
+    dg = randn(74, N, L, E)
+    tr = table.clone().requires_grad_(True)
+    Wr, br = W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    te = tr[idx]
+    gates = torch.einsum("led,nd->nle", Wr, te) + br
+    gates = gates.softmax(-1)
+    gates.backward(dg)
+    dW, db, dte = torch.zeros(L, E, D, device="cuda"), torch.zeros(L, E, device="cuda"), torch.zeros(N, D, device="cuda")
+    ops.router_bwd(gates.detach().cuda(), dg.cuda(), table[idx].cuda(), W.half().cuda(), dW, db, dte)
+    assert rel(dW, Wr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+    dtab = torch.zeros(T, D, device="cuda")
+    ops.scatter_add_rows(dte, idx.cuda(), dtab)
+    assert rel(dtab, tr.grad) < 1e-4
