@@ -356,7 +356,7 @@ class UNetModel(nn.Module):
 
         def pack_res(rb):
             nonlocal off
-            d = {"cin": rb.channels, "cout": rb.out_channels}
+            d = {"cin": rb.channels, "cout": rb.out_channels, "_mod": rb}     # _mod: source module (training.py packs dX weights from it)
             d["gn1_w"], d["gn1_b"] = _f(rb.in_layers[0].weight, dev), _f(rb.in_layers[0].bias, dev)
             d["c1_w"], d["c1_b"] = _pack_conv3(rb.in_layers[2].weight, dev), _f(rb.in_layers[2].bias, dev)
             emb_w.append(rb.emb_layers[1].weight)
@@ -374,7 +374,7 @@ class UNetModel(nn.Module):
         def pack_attn(at, self_attn):
             hs = head_stride_for(at.dim_head)
             aux = aux_cols_for(at.dim_head)
-            d = {"heads": at.heads, "d": at.dim_head, "hs": hs, "aux": aux, "qkv_b": None, "kv_b": None}
+            d = {"heads": at.heads, "d": at.dim_head, "hs": hs, "aux": aux, "qkv_b": None, "kv_b": None, "_mod": at}
             ph = lambda w: pad_heads(w.detach(), at.heads, at.dim_head, hs)
             wq = at.to_q.weight.detach()
             if aux:
@@ -393,7 +393,7 @@ class UNetModel(nn.Module):
             return d
 
         def pack_st(st):
-            d = {"ch": st.in_channels, "inner": st.inner}
+            d = {"ch": st.in_channels, "inner": st.inner, "_mod": st}
             d["gn_w"], d["gn_b"] = _f(st.norm.weight, dev), _f(st.norm.bias, dev)
             d["pin_w"] = _h(st.proj_in.weight.reshape(st.proj_in.weight.shape[0], -1), dev)
             d["pin_b"] = _f(st.proj_in.bias, dev)
@@ -402,7 +402,7 @@ class UNetModel(nn.Module):
             d["blocks"] = []
             for tb in st.transformer_blocks:
                 b = {"attn1": pack_attn(tb.attn1, not tb.disable_self_attn), "attn2": pack_attn(tb.attn2, False),
-                     "self": not tb.disable_self_attn}
+                     "self": not tb.disable_self_attn, "_mod": tb}
                 for i, nm in enumerate((tb.norm1, tb.norm2, tb.norm3), 1):
                     b[f"ln{i}_w"], b[f"ln{i}_b"] = _f(nm.weight, dev), _f(nm.bias, dev)
                 gw, gb = tb.ff.net[0].proj.weight, tb.ff.net[0].proj.bias
@@ -422,9 +422,9 @@ class UNetModel(nn.Module):
                 elif isinstance(m, _SpatialTransformer):
                     out.append(("st", pack_st(m)))
                 elif isinstance(m, _Downsample):
-                    out.append(("down", {"w": _pack_conv3(m.op.weight, dev), "b": _f(m.op.bias, dev)}))
+                    out.append(("down", {"w": _pack_conv3(m.op.weight, dev), "b": _f(m.op.bias, dev), "_mod": m}))
                 elif isinstance(m, _Upsample):
-                    out.append(("up", {"w": _pack_conv3(m.conv.weight, dev), "b": _f(m.conv.bias, dev)}))
+                    out.append(("up", {"w": _pack_conv3(m.conv.weight, dev), "b": _f(m.conv.bias, dev), "_mod": m}))
             return out
 
         P["input"] = [pack_block(b) for b in list(self.input_blocks)[1:]]
