@@ -146,3 +146,32 @@ def test_training_step_linear_projection_geometry():
     print("[training step, linear-projection geometry] worst relative L2 per gradient kind:", {k: f"{v:.2e}" for k, v in worst.items()})
     for k, v in worst.items():
         assert v < (ROUTER_TOL if k.startswith("router") else GRAD_TOL), (k, v)
+
+
+def test_c4_training_step_sd15_geometry():
+    """BASELINE config 4 flavour at a size the CPU oracle's autograd finishes in about a minute: SD-1.5 geometry
+    (8 heads, d = 40 at level 0 -> the padded-head / aux_cols packing and its ln 2 score factor in the backward,
+    d = 160 two-pass dk/dv), 11 experts, 16 visual tokens, 2 requests at 16x16 latent."""
+    from anyedit_b200.training import AdapterTrainer
+    from oracle import cpu, train_oracle
+    moe, sd, asd, cfg, b, acp = _setup("sd15", 3, E=11, T=20, B=2, hw=16, n_vis=16, gain=1.5)
+    tr = AdapterTrainer(moe, loss_scale=1024.0)
+    c = _cuda(b)
+    loss, pred, grads = tr.loss_and_grads(c["latents"], c["noise"], c["t"], c["image_latent"], c["text"], c["vis"], c["code"])
+    torch.cuda.synchronize()
+    torch.set_num_threads(cpu.usable_cores())
+    loss_ref, pred_ref, g_ref = train_oracle.train_step_grads(sd, asd, b["latents"], b["noise"], b["t"], b["image_latent"], b["text"],
+                                                              b["code"], b["vis"], acp, num_heads=cfg["num_heads"])
+    assert rel(pred, pred_ref) < 4e-3
+    assert abs(float(loss) - float(loss_ref)) < LOSS_TOL * float(loss_ref)
+    worst = {}
+    for k, ref in g_ref.items():
+        got = grads[k].float() / tr.loss_scale
+        assert torch.isfinite(got).all(), k
+        if float(ref.abs().max()) == 0.0:
+            continue
+        kind = k.split(".")[-2] + "." + k.split(".")[-1] if "." in k else k
+        worst[kind] = max(worst.get(kind, 0.0), rel(got.reshape(ref.shape), ref))
+    print("[C4 training step, sd15 geometry, 11 experts] worst relative L2 per gradient kind:", {k: f"{v:.2e}" for k, v in worst.items()})
+    for k, v in worst.items():
+        assert v < (ROUTER_TOL if k.startswith("router") else 3e-2), (k, v)
