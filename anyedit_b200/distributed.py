@@ -59,3 +59,17 @@ def max_over_ranks(value: float, device) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+@torch.no_grad()
+def allreduce_sum_(tensors, async_op=True):
+    """Training path (train.py:536, 703: DDP over the trainable set only): sum every gradient tensor
+    over the ranks in place -- the only data-path collective of the training step.  The mean's 1/world is folded
+    into the optimizer's gradient scale by the caller (no extra elementwise pass).  Returns the world size."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 1
+    works = [dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op) for t in tensors if t is not None]
+    if async_op:
+        for w in works:
+            w.wait()
+    return dist.get_world_size()

@@ -295,7 +295,8 @@ def geglu(pre, out):
 def geglu_bwd(pre, d_out, d_pre):
     _cuda(pre, d_out, d_pre)
     inner = d_out.shape[-1]
-    _lib.check(_lib.load().anysd_geglu_bwd_f16(_ptr(pre), _ptr(d_out), _ptr(d_pre), d_out.numel() // inner, inner, _stream()), "geglu_bwd")
+    with _Traced("geglu_bwd", 0.0, f"inner={inner}"):
+        _lib.check(_lib.load().anysd_geglu_bwd_f16(_ptr(pre), _ptr(d_out), _ptr(d_pre), d_out.numel() // inner, inner, _stream()), "geglu_bwd")
     _count()
 
 
@@ -309,16 +310,18 @@ def groupnorm_bwd(x1, gamma, beta, dy, dx, N, HW, eps, silu, x2=None, G=32):
     _cuda(x1, dy, dx)
     C1 = x1.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
-    _lib.check(_lib.load().anysd_groupnorm_bwd_nhwc_f16(_ptr(x1), C1, _ptr(x2), C2, _ptr(gamma), _ptr(beta), _ptr(dy), _ptr(dx), N, HW,
-                                                        G, float(eps), int(bool(silu)), _stream()), "groupnorm_bwd")
+    with _Traced("groupnorm_bwd", 0.0, f"N={N} HW={HW} C={C1}+{C2}"):
+        _lib.check(_lib.load().anysd_groupnorm_bwd_nhwc_f16(_ptr(x1), C1, _ptr(x2), C2, _ptr(gamma), _ptr(beta), _ptr(dy), _ptr(dx), N, HW,
+                                                            G, float(eps), int(bool(silu)), _stream()), "groupnorm_bwd")
     _count()
 
 
 def layernorm_bwd(x, gamma, dy, dx, eps=1e-5):
     _cuda(x, dy, dx)
     Cc = x.shape[-1]
-    _lib.check(_lib.load().anysd_layernorm_bwd_f16(_ptr(x), _ptr(gamma), _ptr(dy), _ptr(dx), x.numel() // Cc, Cc, float(eps), _stream()),
-               "layernorm_bwd")
+    with _Traced("layernorm_bwd", 0.0, f"C={Cc}"):
+        _lib.check(_lib.load().anysd_layernorm_bwd_f16(_ptr(x), _ptr(gamma), _ptr(dy), _ptr(dx), x.numel() // Cc, Cc, float(eps), _stream()),
+                   "layernorm_bwd")
     _count()
 
 
@@ -343,7 +346,8 @@ def attention_bwd(q, k, v, d_out, dq, dk, dv, B, heads, n_q, n_kv, d, ld_q, ld_k
     nbytes = _lib.load().anysd_attention_bwd_workspace_bytes(B, heads, n_q)
     ws = torch.empty(nbytes // 4, dtype=torch.float32, device=q.device)
     p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
-    _lib.check(_lib.load().anysd_attention_bwd_f16(C.byref(p), _stream()), "attention_bwd")
+    with _Traced("attention_bwd", 0.0, f"B={B} h={heads} nq={n_q} nkv={n_kv} d={d} dkv={int(dk is not None)}"):
+        _lib.check(_lib.load().anysd_attention_bwd_f16(C.byref(p), _stream()), "attention_bwd")
     _count(2 if dk is not None else 1)
 
 
@@ -386,9 +390,10 @@ def sumpool2x(src, dst):
 def gemm_tn(A, B, out, M, Ka, Kb, lda=None, ldb=None, alpha=1.0, accumulate=False, head_d=0, head_stride=0):
     """out[ka, kb] (+)= alpha * sum_m A[m, col(ka)] * B[m, kb]; A, B fp16, out fp32."""
     _cuda(A, B, out)
-    _lib.check(_lib.load().anysd_gemm_tn_f32(_ptr(A), lda if lda is not None else A.stride(0), head_d, head_stride, _ptr(B),
-                                             ldb if ldb is not None else B.stride(0), _ptr(out), out.stride(0), M, Ka, Kb, float(alpha),
-                                             int(bool(accumulate)), _stream()), "gemm_tn")
+    with _Traced("gemm_tn", 0.0, f"M={M} Ka={Ka} Kb={Kb}"):
+        _lib.check(_lib.load().anysd_gemm_tn_f32(_ptr(A), lda if lda is not None else A.stride(0), head_d, head_stride, _ptr(B),
+                                                 ldb if ldb is not None else B.stride(0), _ptr(out), out.stride(0), M, Ka, Kb, float(alpha),
+                                                 int(bool(accumulate)), _stream()), "gemm_tn")
     _count()
 
 

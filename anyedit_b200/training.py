@@ -482,11 +482,16 @@ class AdapterTrainer:
     def step(self, latents, noise, timesteps, image_latent, text, visual_tokens=None, edit_code=None):
         """One training step (train.py:629-709): loss, backward, AdamW on the trainables.  Returns (loss, d_visual_tokens)."""
         loss, _, grads = self.loss_and_grads(latents, noise, timesteps, image_latent, text, visual_tokens, edit_code)
-        self.apply_gradients(grads)
-        return loss, grads.get("visual_tokens")
+        d_vis = grads.pop("visual_tokens", None)
+        # DDP semantics over the trainables only (train.py:536, 703): NCCL all-reduce(sum), the 1/world of the mean is
+        # folded into AdamW's gradient scale
+        from . import distributed
+        world = distributed.allreduce_sum_([grads[k] for k in sorted(grads)])
+        self.apply_gradients(grads, world)
+        return loss, d_vis
 
     @torch.no_grad()
-    def apply_gradients(self, grads):
+    def apply_gradients(self, grads, world=1):
         self.step_count += 1
         for name, p in self.trainables().items():
             g = grads.get(name)
@@ -498,5 +503,5 @@ class AdapterTrainer:
             if stt is None:
                 stt = self._state[name] = (torch.zeros_like(p.data, dtype=torch.float32), torch.zeros_like(p.data, dtype=torch.float32))
             ops.adamw_(p.data, g.contiguous(), stt[0], stt[1], self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
-                       self.weight_decay, grad_scale=1.0 / self.loss_scale)
+                       self.weight_decay, grad_scale=1.0 / (self.loss_scale * world))
         self.moe._pack = None            # packed expert / router / task tensors are stale now

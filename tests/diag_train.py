@@ -53,5 +53,24 @@ def main():
           f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB", flush=True)
 
 
+    if "--trace" in sys.argv:
+        ops.trace = []
+        e0.record()
+        tr.step(lat, noise, t, img, text, vis, code)
+        e1.record()
+        torch.cuda.synchronize()
+        agg = {}
+        for kind, fl, a, b, tag in ops.trace:
+            d = agg.setdefault(kind, [0.0, 0])
+            d[0] += a.elapsed_time(b)
+            d[1] += 1
+        ops.trace = None
+        tot = e0.elapsed_time(e1)
+        print(f"traced step {tot:.1f} ms")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            print(f"  {k:16s} {v[1]:5d} launches {v[0]:8.2f} ms")
+        print(f"  untraced        {tot - sum(v[0] for v in agg.values()):8.2f} ms")
+
+
 if __name__ == "__main__":
     main()

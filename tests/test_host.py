@@ -188,3 +188,24 @@ def test_request_sharding_two_rank_gloo(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_gradient_allreduce_two_rank_gloo(tmp_path):
+    """Training path (SURVEY.md 8e / a24): the only data-path collective is the all-reduce of the trainables' gradients;
+    2 gloo ranks on CPU: every rank ends with the rank-sum, the helper reports the world size for the 1/world fold."""
+    script = tmp_path / "g.py"
+    script.write_text(
+        "import os, sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from anyedit_b200 import distributed as D\n"
+        "dist.init_process_group('gloo')\n"
+        "r = dist.get_rank()\n"
+        "g = [torch.full((5, 3), float(r + 1)), torch.arange(4.0) * (r + 1), None]\n"
+        "w = D.allreduce_sum_(g)\n"
+        "assert w == 2 and torch.equal(g[0], torch.full((5, 3), 3.0)) and torch.equal(g[1], torch.arange(4.0) * 3)\n"
+        "if r == 0: print('OK')\n"
+        "dist.destroy_process_group()\n")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29534", str(script)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
