@@ -50,7 +50,8 @@ class AttnBwdParams(C.Structure):          # mirrors anysd_attn_bwd_params field
                 ("B", C.c_int), ("heads", C.c_int), ("n_q", C.c_int), ("n_kv", C.c_int), ("d", C.c_int),
                 ("head_stride", C.c_int), ("qk_scale", C.c_float),
                 ("gate", C.c_void_p), ("gate_stride", C.c_int), ("d_gate", C.c_void_p),
-                ("accumulate_dq", C.c_int), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("accumulate_dq", C.c_int), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("out", C.c_void_p), ("o_batch_stride", C.c_longlong), ("ld_o", C.c_int)]
 
 
 # name -> (restype, argtypes); mirrors include/anysd_b200.h one to one
@@ -89,7 +90,7 @@ SIGNATURES = {
     "anysd_split_channels_f16": (_I, [_VP, _VP, _I, _VP, _I, _LL, _VP]),
     "anysd_zero_insert2x_f16": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "anysd_sumpool2x_f16": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
-    "anysd_gemm_tn_f32": (_I, [_VP, _I, _I, _I, _VP, _I, _VP, _I, _I, _I, _I, _F, _I, _VP]),
+    "anysd_gemm_tn_f32": (_I, [_VP, _I, _I, _I, _I, _I, _VP, _I, _VP, _I, _I, _I, _I, _F, _I, _VP]),
     "anysd_router_bwd_f32": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _F, _VP, _VP, _VP, _VP]),
     "anysd_scatter_add_rows_f32": (_I, [_VP, _VP, _I, _I, _I, _F, _VP, _VP]),
     "anysd_adamw_f32": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _F, _VP]),

@@ -33,6 +33,7 @@ struct BwdArgs {
     const float* gate; int gate_stride; float* dgate;
     int accumulate_dq;
     float* lse; float* D;                // [B, heads, n_q]
+    const __half* o; long long obs; int ldo;   // optional: this attention's own (ungated) forward output -> D = dO . O
 };
 
 __device__ __forceinline__ float b_ex2(float x) {
@@ -161,8 +162,24 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dq_kernel(const BwdArgs p
         lse[r] = m_run[r] + log2f(l);
     }
 
-    // ---- pass 1: D_raw_i = sum_j p_ij (dO_i . v_j) ----
+    // ---- pass 1: D_raw_i = sum_j p_ij (dO_i . v_j)   (= dO_i . O_i: one smem pass when the caller kept O) ----
     float d_raw[2] = {0.f, 0.f};
+    if (p.o != nullptr) {
+        __syncthreads();
+        b_load_tile<DP>(p.o + (size_t)b * p.obs + (size_t)h * p.d, p.ldo, q0, p.n_q, dch, sK);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int lr = warp * 16 + (lane >> 2) + r * 8;
+            for (int c = (lane & 3) * 2; c < p.d; c += 8) {
+                const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(sdO + lr * LDS + c));
+                const float2 o2 = __half22float2(*reinterpret_cast<const __half2*>(sK + lr * LDS + c));
+                d_raw[r] += a2.x * o2.x + a2.y * o2.y;
+            }
+        }
+    } else
     for (int t = 0; t < nt; ++t) {
         __syncthreads();
         b_load_tile<DP>(kg, p.ldk, t * AB_T, p.n_kv, dch, sK);
@@ -410,6 +427,9 @@ extern "C" int anysd_attention_bwd_f16(const anysd_attn_bwd_params* p, anysd_str
     a.gate = p->gate; a.gate_stride = p->gate_stride; a.dgate = p->d_gate;
     a.accumulate_dq = p->accumulate_dq;
     a.lse = (float*)p->workspace; a.D = a.lse + (size_t)p->B * p->heads * p->n_q;
+    ANYSD_REQUIRE(p->out == nullptr || (p->gate == nullptr && p->ld_o % 8 == 0 && ((uintptr_t)p->out % 16) == 0 && p->o_batch_stride % 8 == 0),
+                  ANYSD_EINVAL, "attention_bwd: `out` must be the un-gated output of this attention, 16-byte aligned, ld_o %% 8 == 0");
+    a.o = (const __half*)p->out; a.obs = p->o_batch_stride; a.ldo = p->ld_o;
     cudaStream_t st = (cudaStream_t)stream;
     const bool need = p->dk != nullptr;
     switch (dp) {

@@ -56,72 +56,137 @@ __global__ void silu_bwd_f32_kernel(const float* __restrict__ x, const float* __
         dx[i] = dy[i] * silu_grad_f(x[i]);
 }
 
-// ---- GroupNorm(+SiLU) backward: one CTA per (image, group) -----------------------------------------------------
+// ---- GroupNorm(+SiLU) backward ---------------------------------------------------------------------------------
 // y = [silu](z), z = xhat * gamma + beta, xhat = (x - mean) * rstd over the group's HW x cpg elements:
 //   dz = dy * silu'(z);  w = dz * gamma;  dx = rstd * (w - mean(w) - xhat * mean(w * xhat))
-__global__ void __launch_bounds__(256) gn_bwd_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
-                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                     const __half* __restrict__ dy, __half* __restrict__ dx, int HW, int G,
-                                                     float eps, int fuse_silu) {
-    const int n = blockIdx.y, g = blockIdx.x;
-    const int C = C1 + C2, cpg = C / G, c0 = g * cpg;
-    const int total = HW * cpg;
-    __shared__ float red[2][8];
-    __shared__ float bc[4];
-    auto X = [&](int row, int c) -> float {
-        return c < C1 ? __half2float(x1[((size_t)n * HW + row) * C1 + c]) : __half2float(x2[((size_t)n * HW + row) * C2 + (c - C1)]);
-    };
-    auto block_sum2 = [&](float a, float b, float& oa, float& ob) {
-        a = warp_sum(a);
-        b = warp_sum(b);
+// One CTA per (image, span of `gpc` whole groups that is also a whole number of 16-byte channel vectors): VC =
+// gpc*cpg/8 vector columns x RL row lanes.  Three passes over the slab (statistics; the two sums; dx), the slab
+// stays in L2.  Per-channel partials are folded over the row lanes in smem, then per group.
+constexpr int GNB_THREADS = 256;
+__global__ void __launch_bounds__(GNB_THREADS) gn_bwd_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const __half* __restrict__ dy, __half* __restrict__ dx, int HW, int cpg,
+                                                             int gpc, float eps, int fuse_silu) {
+    extern __shared__ float gsm[];                 // [2][RL][VC*8] partials | [VC*8] a | [VC*8] b | per group 4 floats
+    const int n = blockIdx.y;
+    const int C = C1 + C2;
+    const int VC = gpc * cpg / 8, CW = VC * 8;     // channel vectors / channels of this CTA
+    const int c_base = blockIdx.x * CW;
+    const int RL = GNB_THREADS / VC;
+    const int vl = threadIdx.x % VC, rl = threadIdx.x / VC;
+    const bool active = rl < RL;
+    float* part = gsm;                             // [2][RL][CW]
+    float* grp = gsm + 2 * RL * CW;                // [gpc][4]: mean, rstd, mean(w), mean(w*xhat)
+    const int c0 = c_base + vl * 8;                // first channel of this thread's vector (a vector never straddles x1|x2: C1 % 8 == 0)
+    const bool first = c0 < C1;
+    const __half* xb = first ? x1 + (size_t)n * HW * C1 + c0 : x2 + (size_t)n * HW * C2 + (c0 - C1);
+    const int xs = first ? C1 : C2;
+    const __half* dyb = dy + (size_t)n * HW * C + c0;
+    __half* dxb = dx + (size_t)n * HW * C + c0;
+    const float inv_cnt = 1.0f / ((float)HW * cpg);
+
+    auto fold = [&](const float* a8, const float* b8, int slot_a, int slot_b) {
+        // per-thread 8-channel partials -> per-group means into grp[g][slot_a / slot_b]
         __syncthreads();
-        if ((threadIdx.x & 31) == 0) {
-            red[0][threadIdx.x >> 5] = a;
-            red[1][threadIdx.x >> 5] = b;
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                part[(0 * RL + rl) * CW + vl * 8 + j] = a8[j];
+                part[(1 * RL + rl) * CW + vl * 8 + j] = b8[j];
+            }
         }
         __syncthreads();
-        float ta = 0.f, tb = 0.f;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-            ta += red[0][w];
-            tb += red[1][w];
+        for (int i = threadIdx.x; i < 2 * CW; i += GNB_THREADS) {
+            const int which = i / CW, c = i - which * CW;
+            float t = 0.f;
+            for (int r = 0; r < RL; ++r) t += part[(which * RL + r) * CW + c];
+            part[(which * RL) * CW + c] = t;
         }
-        oa = ta;
-        ob = tb;
+        __syncthreads();
+        if (threadIdx.x < gpc) {
+            float ta = 0.f, tb = 0.f;
+            for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+                ta += part[c];
+                tb += part[RL * CW + c];
+            }
+            grp[threadIdx.x * 4 + slot_a] = ta * inv_cnt;
+            grp[threadIdx.x * 4 + slot_b] = tb * inv_cnt;
+        }
+        __syncthreads();
     };
-    float s = 0.f, q = 0.f;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const float v = X(i / cpg, c0 + i % cpg);
-        s += v;
-        q += v * v;
+
+    float a8[8], b8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a8[j] = b8[j] = 0.f;
+    if (active)
+        for (int r = rl; r < HW; r += RL) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(xb + (size_t)r * xs)), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a8[j] += f[j];
+                b8[j] += f[j] * f[j];
+            }
+        }
+    fold(a8, b8, 0, 1);
+    if (threadIdx.x < gpc) {                       // slot 1 holds E[x^2] -> rstd
+        const float mean = grp[threadIdx.x * 4], ex2 = grp[threadIdx.x * 4 + 1];
+        float var = ex2 - mean * mean;
+        var = var < 0.f ? 0.f : var;
+        grp[threadIdx.x * 4 + 1] = rsqrtf(var + eps);
     }
-    float S, Q;
-    block_sum2(s, q, S, Q);
-    const float mean = S / total;
-    float var = Q / total - mean * mean;
-    var = var < 0.f ? 0.f : var;
-    const float rstd = rsqrtf(var + eps);
-    float a = 0.f, b = 0.f;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int row = i / cpg, c = c0 + i % cpg;
-        const float xh = (X(row, c) - mean) * rstd;
-        float d = __half2float(dy[((size_t)n * HW + row) * C + c]);
-        if (fuse_silu) d *= silu_grad_f(xh * gamma[c] + beta[c]);
-        const float w = d * gamma[c];
-        a += w;
-        b += w * xh;
+    __syncthreads();
+    float mean8[8], rstd8[8], g8[8], be8[8];
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int gl = (vl * 8 + j) / cpg;
+            mean8[j] = grp[gl * 4];
+            rstd8[j] = grp[gl * 4 + 1];
+            g8[j] = gamma[c0 + j];
+            be8[j] = beta[c0 + j];
+        }
     }
-    float A, Bq;
-    block_sum2(a, b, A, Bq);
-    const float mw = A / total, mwx = Bq / total;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int row = i / cpg, c = c0 + i % cpg;
-        const float xh = (X(row, c) - mean) * rstd;
-        float d = __half2float(dy[((size_t)n * HW + row) * C + c]);
-        if (fuse_silu) d *= silu_grad_f(xh * gamma[c] + beta[c]);
-        const float w = d * gamma[c];
-        dx[((size_t)n * HW + row) * C + c] = __float2half_rn(rstd * (w - mw - xh * mwx));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a8[j] = b8[j] = 0.f;
+    if (active)
+        for (int r = rl; r < HW; r += RL) {
+            float f[8], d[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(xb + (size_t)r * xs)), f);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(dyb + (size_t)r * C)), d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (f[j] - mean8[j]) * rstd8[j];
+                float dd = d[j];
+                if (fuse_silu) dd *= silu_grad_f(xh * g8[j] + be8[j]);
+                const float w = dd * g8[j];
+                a8[j] += w;
+                b8[j] += w * xh;
+            }
+        }
+    fold(a8, b8, 2, 3);
+    if (active) {
+        float mw8[8], mwx8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int gl = (vl * 8 + j) / cpg;
+            mw8[j] = grp[gl * 4 + 2];
+            mwx8[j] = grp[gl * 4 + 3];
+        }
+        for (int r = rl; r < HW; r += RL) {
+            float f[8], d[8], o[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(xb + (size_t)r * xs)), f);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(dyb + (size_t)r * C)), d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (f[j] - mean8[j]) * rstd8[j];
+                float dd = d[j];
+                if (fuse_silu) dd *= silu_grad_f(xh * g8[j] + be8[j]);
+                o[j] = rstd8[j] * (dd * g8[j] - mw8[j] - xh * mwx8[j]);
+            }
+            *reinterpret_cast<uint4*>(dxb + (size_t)r * C) = pack8(o);
+        }
     }
-    (void)bc;
 }
 
 // ---- LayerNorm backward: one warp per token row ----------------------------------------------------------------
@@ -338,8 +403,9 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 // A [M, lda] fp16 with optional head padding (logical column ka lives at (ka / head_d) * head_stride + ka % head_d),
 // B [M, ldb] fp16, out fp32 [Ka, ldo].  32 x 32 output tile per CTA, 16 x 16 threads, 2 x 2 outputs each.
 __global__ void __launch_bounds__(256) gemm_tn_kernel(const __half* __restrict__ A, int lda, int head_d, int head_stride,
-                                                      const __half* __restrict__ B, int ldb, float* __restrict__ out, int ldo,
-                                                      int M, int Ka, int Kb, float alpha, int accumulate) {
+                                                      int group_c, int group_stride, const __half* __restrict__ B, int ldb,
+                                                      float* __restrict__ out, int ldo, int M, int Ka, int Kb, float alpha,
+                                                      int accumulate) {
     __shared__ float sA[32][33], sB[32][33];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
@@ -352,7 +418,12 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const __half* __restrict__
             if (m < M) {
                 const int ka = a0 + cc;
                 if (ka < Ka) {
-                    const int col = head_d > 0 ? (ka / head_d) * head_stride + ka % head_d : ka;
+                    int base = 0, c = ka;
+                    if (group_c > 0) {
+                        base = (ka / group_c) * group_stride;
+                        c = ka % group_c;
+                    }
+                    const int col = base + (head_d > 0 ? (c / head_d) * head_stride + c % head_d : c);
                     va = __half2float(A[(size_t)m * lda + col]);
                 }
                 const int kb = b0 + cc;
@@ -468,8 +539,20 @@ int anysd_groupnorm_bwd_nhwc_f16(const void* x1, int C1, const void* x2, int C2,
     if (x2 == nullptr) C2 = 0;
     const int C = C1 + C2;
     ANYSD_REQUIRE(N > 0 && HW > 0 && G > 0 && C1 > 0 && C2 >= 0 && C % G == 0 && N <= 65535, ANYSD_EINVAL, "groupnorm_bwd: bad shape");
-    gn_bwd_kernel<<<dim3(G, N), 256, 0, (cudaStream_t)stream>>>((const __half*)x1, C1, (const __half*)x2, C2, gamma, beta,
-                                                               (const __half*)dy, (__half*)dx, HW, G, eps, fuse_silu);
+    ANYSD_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0, ANYSD_EINVAL, "groupnorm_bwd: channel counts must be multiples of 8");
+    const int cpg = C / G;
+    int gpc = 1;                                   // groups per CTA: smallest span that is a whole number of 8-channel vectors
+    while ((gpc * cpg) % 8 != 0) ++gpc;
+    ANYSD_REQUIRE(G % gpc == 0 && gpc * cpg / 8 <= GNB_THREADS, ANYSD_EUNSUPPORTED,
+                  "groupnorm_bwd: C=%d, G=%d does not tile into 16-byte channel vectors", C, G);
+    const int VC = gpc * cpg / 8, RL = GNB_THREADS / VC;
+    const size_t smem = ((size_t)2 * RL * VC * 8 + 4 * gpc) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(gn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ANYSD_REQUIRE(e == cudaSuccess, ANYSD_ECUDA, "groupnorm_bwd: smem opt-in failed: %s", cudaGetErrorString(e));
+    }
+    gn_bwd_kernel<<<dim3(G / gpc, N), GNB_THREADS, smem, (cudaStream_t)stream>>>((const __half*)x1, C1, (const __half*)x2, C2, gamma, beta,
+                                                                               (const __half*)dy, (__half*)dx, HW, cpg, gpc, eps, fuse_silu);
     return check_launch("groupnorm_bwd");
 }
 
@@ -546,13 +629,14 @@ int anysd_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_
     return check_launch("adamw");
 }
 
-int anysd_gemm_tn_f32(const void* A, int lda, int head_d, int head_stride, const void* B, int ldb, float* out, int ldo, int M,
-                      int Ka, int Kb, float alpha, int accumulate, anysd_stream_t stream) {
+int anysd_gemm_tn_f32(const void* A, int lda, int head_d, int head_stride, int group_c, int group_stride, const void* B, int ldb,
+                      float* out, int ldo, int M, int Ka, int Kb, float alpha, int accumulate, anysd_stream_t stream) {
     ANYSD_REQUIRE(A && B && out && M > 0 && Ka > 0 && Kb > 0 && lda > 0 && ldb >= Kb && ldo >= Kb, ANYSD_EINVAL, "gemm_tn: bad args");
     ANYSD_REQUIRE(head_d == 0 || (head_d > 0 && head_stride >= head_d), ANYSD_EINVAL, "gemm_tn: bad head mapping");
-    gemm_tn_kernel<<<dim3(cdiv(Kb, 32), cdiv(Ka, 32)), 256, 0, (cudaStream_t)stream>>>((const __half*)A, lda, head_d, head_stride,
-                                                                                     (const __half*)B, ldb, out, ldo, M, Ka, Kb, alpha,
-                                                                                     accumulate);
+    ANYSD_REQUIRE(group_c >= 0 && (group_c == 0 || group_stride > 0), ANYSD_EINVAL, "gemm_tn: bad group mapping");
+    gemm_tn_kernel<<<dim3(cdiv(Kb, 32), cdiv(Ka, 32)), 256, 0, (cudaStream_t)stream>>>((const __half*)A, lda, head_d, head_stride, group_c,
+                                                                                     group_stride, (const __half*)B, ldb, out, ldo, M, Ka,
+                                                                                     Kb, alpha, accumulate);
     return check_launch("gemm_tn");
 }
 

@@ -326,8 +326,9 @@ def layernorm_bwd(x, gamma, dy, dx, eps=1e-5):
 
 
 def attention_bwd(q, k, v, d_out, dq, dk, dv, B, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk=0, ld_dv=0,
-                  qk_scale=None, gate=None, gate_stride=1, d_gate=None, accumulate_dq=False, head_stride=0):
-    """Backward of `attention` (recomputing the probabilities).  dk/dv None: frozen K/V."""
+                  qk_scale=None, gate=None, gate_stride=1, d_gate=None, accumulate_dq=False, head_stride=0, out=None, ld_o=0):
+    """Backward of `attention` (recomputing the probabilities).  dk/dv None: frozen K/V.  out: this attention's own
+    un-gated forward output (saves one sweep over K/V)."""
     _cuda(q, k, v, d_out, dq)
     p = _lib.AttnBwdParams()
     p.q, p.k, p.v, p.d_out, p.dq = q.data_ptr(), k.data_ptr(), v.data_ptr(), d_out.data_ptr(), dq.data_ptr()
@@ -343,6 +344,8 @@ def attention_bwd(q, k, v, d_out, dq, dk, dv, B, heads, n_q, n_kv, d, ld_q, ld_k
     p.gate_stride = gate_stride
     p.d_gate = d_gate.data_ptr() if d_gate is not None else None
     p.accumulate_dq = int(bool(accumulate_dq))
+    p.out = out.data_ptr() if out is not None else None
+    p.o_batch_stride, p.ld_o = n_q * ld_o, ld_o
     nbytes = _lib.load().anysd_attention_bwd_workspace_bytes(B, heads, n_q)
     ws = torch.empty(nbytes // 4, dtype=torch.float32, device=q.device)
     p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
@@ -387,11 +390,13 @@ def sumpool2x(src, dst):
     _count()
 
 
-def gemm_tn(A, B, out, M, Ka, Kb, lda=None, ldb=None, alpha=1.0, accumulate=False, head_d=0, head_stride=0):
+def gemm_tn(A, B, out, M, Ka, Kb, lda=None, ldb=None, alpha=1.0, accumulate=False, head_d=0, head_stride=0, group_c=0,
+            group_stride=0):
     """out[ka, kb] (+)= alpha * sum_m A[m, col(ka)] * B[m, kb]; A, B fp16, out fp32."""
     _cuda(A, B, out)
     with _Traced("gemm_tn", 0.0, f"M={M} Ka={Ka} Kb={Kb}"):
-        _lib.check(_lib.load().anysd_gemm_tn_f32(_ptr(A), lda if lda is not None else A.stride(0), head_d, head_stride, _ptr(B),
+        _lib.check(_lib.load().anysd_gemm_tn_f32(_ptr(A), lda if lda is not None else A.stride(0), head_d, head_stride, group_c, group_stride,
+                                                 _ptr(B),
                                                  ldb if ldb is not None else B.stride(0), _ptr(out), out.stride(0), M, Ka, Kb, float(alpha),
                                                  int(bool(accumulate)), _stream()), "gemm_tn")
     _count()

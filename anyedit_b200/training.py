@@ -409,7 +409,7 @@ class AdapterTrainer:
             ops.gemm(xq, ad["qkv_w"], qkv, bias=ad["qkv_b"])
             ops.attention(qkv, qkv[:, Cp:], qkv[:, 2 * Cp:], a, N, ad["heads"], n_q, n_q, ad["d"], 3 * Cp, 3 * Cp, 3 * Cp, C,
                           head_stride=hs, aux_cols=ad["aux"])
-            c["qkv"] = qkv
+            c["qkv"], c["a"] = qkv, a
         else:
             L = ctx.shape[1]
             q = torch.empty(N * n_q, Cp, dtype=torch.float16, device=dev)
@@ -447,7 +447,7 @@ class AdapterTrainer:
             qkv = c["qkv"]
             dqkv = torch.empty_like(qkv)
             ops.attention_bwd(qkv, qkv[:, Cp:], qkv[:, 2 * Cp:], d_a, dqkv, dqkv[:, Cp:], dqkv[:, 2 * Cp:], N, heads, n_q, n_q, d,
-                              3 * Cp, 3 * Cp, 3 * Cp, C, 3 * Cp, 3 * Cp, 3 * Cp, qk_scale=qk, head_stride=hs)
+                              3 * Cp, 3 * Cp, 3 * Cp, C, 3 * Cp, 3 * Cp, 3 * Cp, qk_scale=qk, head_stride=hs, out=c["a"], ld_o=C)
             d_x = torch.empty(N * n_q, ad["qkv_w"].shape[1], dtype=torch.float16, device=dev)
             ops.gemm(dqkv, _memo(ad, "qkv", lambda: ad["qkv_w"].t().contiguous()), d_x)
             return d_x
@@ -466,9 +466,9 @@ class AdapterTrainer:
                                   gate_stride=nl * E, d_gate=G["d_gates"][:, layer, e:], accumulate_dq=True, head_stride=hs)
             vis = st["vis"].view(N * n_vis, -1)
             gk, gv = G[f"adapter_modules.{layer}.to_k_ip.weight"], G[f"adapter_modules.{layer}.to_v_ip.weight"]
-            for e in range(E):                                               # dW_e = dK_e^T vis (parameter layout, un-padded heads)
-                ops.gemm_tn(dekv[:, e * 2 * Cp:], vis, gk[e * C:(e + 1) * C], N * n_vis, C, vis.shape[1], lda=ld, head_d=d, head_stride=hs)
-                ops.gemm_tn(dekv[:, e * 2 * Cp + Cp:], vis, gv[e * C:(e + 1) * C], N * n_vis, C, vis.shape[1], lda=ld, head_d=d, head_stride=hs)
+            # dW_e = dK_e^T vis for all experts in one launch each (parameter layout: expert-major rows, un-padded heads)
+            ops.gemm_tn(dekv, vis, gk, N * n_vis, E * C, vis.shape[1], lda=ld, head_d=d, head_stride=hs, group_c=C, group_stride=2 * Cp)
+            ops.gemm_tn(dekv[:, Cp:], vis, gv, N * n_vis, E * C, vis.shape[1], lda=ld, head_d=d, head_stride=hs, group_c=C, group_stride=2 * Cp)
             Lp = st["MP"]["layers"][layer]
             d_vis = torch.empty(N * n_vis, vis.shape[1], dtype=torch.float16, device=dev)
             ops.gemm(dekv, _memo(Lp, "kv", lambda: Lp["kv_w"].t().contiguous()), d_vis, residual=G["d_vis"])

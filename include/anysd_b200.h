@@ -213,6 +213,10 @@ typedef struct {
     const float* gate; int gate_stride; float* d_gate;
     int accumulate_dq;      /* 1: dq += (the experts share the text attention's q) */
     void* workspace; size_t workspace_bytes;
+    const void* out;        /* optional: the forward output of exactly this attention ([B, n_q, ld_o], head h at h*d, no
+                               gate, nothing accumulated into it): D = dO . O then costs one pass instead of a second
+                               sweep over K/V.  NULL: recomputed. */
+    long long o_batch_stride; int ld_o;
 } anysd_attn_bwd_params;
 size_t anysd_attention_bwd_workspace_bytes(int B, int heads, int n_q);
 int anysd_attention_bwd_f16(const anysd_attn_bwd_params* p, anysd_stream_t stream);
@@ -229,10 +233,12 @@ int anysd_zero_insert2x_f16(const void* src, void* dst, int N, int H, int W, int
 int anysd_sumpool2x_f16(const void* src, void* dst, int N, int H, int W, int C, anysd_stream_t stream);
 
 /* Weight gradient with few rows: out[ka, kb] (+)= alpha * sum_m A[m, col(ka)] B[m, kb]; A, B fp16, out fp32.
- * head_d > 0: A has padded heads, logical column ka sits at (ka / head_d) * head_stride + ka % head_d.
+ * Column mapping of A for logical row ka of out: group_c > 0: e = ka / group_c, c = ka % group_c, base = e * group_stride
+ * (all experts of a layer in one launch); head_d > 0: padded heads, column = base + (c / head_d) * head_stride + c % head_d.
  * (dW of to_k_ip / to_v_ip: A = dK_e / dV_e, B = visual tokens; ip_adapter/attention_processor.py:160-166) */
-int anysd_gemm_tn_f32(const void* A, int lda, int head_d, int head_stride, const void* B, int ldb, float* out, int ldo,
-                      int M, int Ka, int Kb, float alpha, int accumulate, anysd_stream_t stream);
+int anysd_gemm_tn_f32(const void* A, int lda, int head_d, int head_stride, int group_c, int group_stride, const void* B,
+                      int ldb, float* out, int ldo, int M, int Ka, int Kb, float alpha, int accumulate,
+                      anysd_stream_t stream);
 
 /* Router backward (restated spec, oracle/anysd_oracle.py): gates = softmax(W te + b) per (sample, layer);
  * dW [L,E,D] +=, db [L,E] +=, d_te [N,D] += (atomic).  gates/d_gates fp32 [N,L,E], te fp32 [N,D], W fp16 [L,E,D]. */

@@ -80,6 +80,15 @@ def test_attention_backward(ops, B, heads, nq, nkv, d, self_attn, gated, ln2):
     if gated:
         e = rel(dg, gr.grad)
         assert e < 4e-3, ("d_gate", e)
+    if not gated:
+        # with the forward output supplied (self-attention): same gradients, one sweep less
+        o16 = torch.einsum("bhij,bjhd->bihd", (torch.einsum("bihd,bjhd->bhij", q, k) * c).softmax(-1), v).reshape(B, nq, C).half().cuda()
+        dq3, dk3, dv3 = torch.empty_like(dq), torch.empty_like(dk), torch.empty_like(dv)
+        ops.attention_bwd(q16, k16, v16, dO16, dq3, dk3, dv3, B, heads, nq, nkv, d, Cp, Cp, Cp, C, Cp, Cp, Cp, qk_scale=c, head_stride=hs,
+                          out=o16.contiguous(), ld_o=C)
+        for name, got, ref, n in (("dq", dq3, qr.grad, nq), ("dk", dk3, kr.grad, nkv), ("dv", dv3, vr.grad, nkv)):
+            e = rel(unpad(got, n)[..., :d], ref)
+            assert e < 4e-3, (name + " (with out)", e)
     # frozen K/V (text cross-attention): dq only, accumulated onto an existing gradient
     dq2 = dq.clone()
     ops.attention_bwd(q16, k16, v16, dO16, dq2, None, None, B, heads, nq, nkv, d, Cp, Cp, Cp, C, Cp, qk_scale=c, gate=g_dev,
@@ -202,7 +211,7 @@ def test_small_training_kernels(ops):
     dp = torch.empty(2, 30, 64, dtype=torch.float16, device="cuda")
     loss = torch.zeros(1, device="cuda")
     ops.mse_loss(pred.cuda(), target.cuda(), dp, loss, grad_scale=256.0)
-    assert float(loss) == pytest.approx(float(loss_ref), rel=1e-5)
+    assert float(loss) == pytest.approx(float(loss_ref.detach()), rel=1e-5)
     got = dp.float().cpu().view(2, 6, 5, 64)
     assert float(got[..., 4:].abs().max()) == 0.0
     assert rel(got[..., :4].permute(0, 3, 1, 2) / 256.0, pr.grad) < 1e-3
@@ -237,6 +246,13 @@ def test_small_training_kernels(ops):
     outw = torch.zeros(heads * d, Kb, device="cuda")
     ops.gemm_tn(Ap.reshape(M, heads * hs).half().cuda(), Bm.half().cuda(), outw, M, heads * d, Kb, alpha=0.5, head_d=d, head_stride=hs)
     assert rel(outw, 0.5 * A.reshape(M, heads * d).t() @ Bm) < 1e-5
+    # two "experts" side by side (group mapping): rows [e*C, (e+1)*C) of out read columns e*group_stride + ...
+    A2 = torch.cat([Ap.reshape(M, heads * hs), torch.zeros(M, 8), 2 * Ap.reshape(M, heads * hs), torch.zeros(M, 8)], 1)
+    outg = torch.zeros(2 * heads * d, Kb, device="cuda")
+    ops.gemm_tn(A2.half().cuda(), Bm.half().cuda(), outg, M, 2 * heads * d, Kb, head_d=d, head_stride=hs, group_c=heads * d,
+                group_stride=heads * hs + 8)
+    refw = A.reshape(M, heads * d).t() @ Bm
+    assert rel(outg, torch.cat([refw, 2 * refw], 0)) < 1e-5
     # AdamW
     p0, g0 = randn(62, 1000), randn(63, 1000) * 0.1
     p, m, v = p0.clone().cuda(), torch.zeros(1000, device="cuda"), torch.zeros(1000, device="cuda")
