@@ -54,6 +54,14 @@ class AttnBwdParams(C.Structure):          # mirrors anysd_attn_bwd_params field
                 ("out", C.c_void_p), ("o_batch_stride", C.c_longlong), ("ld_o", C.c_int)]
 
 
+class ExpertAttnParams(C.Structure):       # mirrors anysd_expert_attn_params field for field
+    _fields_ = [("q", C.c_void_p), ("kv", C.c_void_p), ("out", C.c_void_p),
+                ("ld_q", C.c_int), ("ld_kv", C.c_int), ("ld_o", C.c_int),
+                ("B", C.c_int), ("heads", C.c_int), ("n_q", C.c_int), ("n_kv", C.c_int), ("d", C.c_int),
+                ("head_stride", C.c_int), ("E", C.c_int), ("set_stride", C.c_int), ("v_offset", C.c_int),
+                ("qk_scale", C.c_float), ("gates", C.c_void_p), ("gate_b_stride", C.c_int)]
+
+
 # name -> (restype, argtypes); mirrors include/anysd_b200.h one to one
 _VP, _I, _LL, _F, _SZ = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 SIGNATURES = {
@@ -85,6 +93,9 @@ SIGNATURES = {
     "anysd_layernorm_bwd_f16": (_I, [_VP, _VP, _VP, _VP, _LL, _I, _F, _VP]),
     "anysd_attention_bwd_workspace_bytes": (_SZ, [_I, _I, _I]),
     "anysd_attention_bwd_f16": (_I, [C.POINTER(AttnBwdParams), _VP]),
+    "anysd_expert_attention_f16": (_I, [C.POINTER(ExpertAttnParams), _VP]),
+    "anysd_expert_attention_bwd_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "anysd_expert_attention_bwd_f16": (_I, [C.POINTER(ExpertAttnParams), _VP, _I, _VP, _I, _VP, _VP, _VP, _SZ, _VP]),
     "anysd_colsum_f16": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "anysd_add_f16": (_I, [_VP, _VP, _LL, _VP]),
     "anysd_split_channels_f16": (_I, [_VP, _VP, _I, _VP, _I, _LL, _VP]),

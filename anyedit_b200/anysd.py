@@ -17,6 +17,8 @@ GEMM + tiny softmax; all experts' K/V projections of a layer are ONE GEMM ([B*N_
 expert's attention is accumulated into the text-attention output by the attention kernel's gated
 epilogue (out += g[b, e] * attn).
 """
+import math
+
 import torch
 import torch.nn as nn
 
@@ -125,10 +127,14 @@ class MoE(nn.Module):
                 kv = torch.empty(N_ * n_vis, E * 2 * Cp, dtype=torch.float16, device=dev)
                 ops.gemm(v16.view(N_ * n_vis, -1), L["kv_w"], kv, bias=L["kv_b"])
                 ld = E * 2 * Cp
-                for e in range(E):
-                    ops.attention(q, kv[:, e * 2 * Cp:], kv[:, e * 2 * Cp + Cp:], a, N_, heads, n_q, n_vis, d,
-                                  Cp, ld, ld, C, gate=gates[:, layer, e:], gate_stride=nl * E, accumulate=True,
-                                  head_stride=hs, aux_cols=aux)
+                qk = math.log(2.0) if aux else d ** -0.5          # aux packing: q already carries scale*log2(e)
+                if n_vis <= 64:                                   # all experts of the layer in one launch
+                    ops.expert_attention(q, kv, gates[:, layer], a, N_, heads, n_q, n_vis, d, E, Cp, ld, C, 2 * Cp, Cp, qk, head_stride=hs)
+                else:
+                    for e in range(E):
+                        ops.attention(q, kv[:, e * 2 * Cp:], kv[:, e * 2 * Cp + Cp:], a, N_, heads, n_q, n_vis, d,
+                                      Cp, ld, ld, C, gate=gates[:, layer, e:], gate_stride=nl * E, accumulate=True,
+                                      head_stride=hs, aux_cols=aux)
 
             hook["experts"] = experts
         return self.unet(noisy_latents, timesteps, context=encoder_hidden_states, anysd=hook)

@@ -34,6 +34,7 @@ struct BwdArgs {
     int accumulate_dq;
     float* lse; float* D;                // [B, heads, n_q]
     const __half* o; long long obs; int ldo;   // optional: this attention's own (ungated) forward output -> D = dO . O
+    int sets, set_stride, gate_set_stride;     // expert streams: blockIdx.z = b * sets + e; K/V/dK/dV of set e sit e*set_stride columns on
 };
 
 __device__ __forceinline__ float b_ex2(float x) {
@@ -289,14 +290,16 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const BwdArgs 
     float* s_lse = reinterpret_cast<float*>(sdO + TILE);
     float* s_D = s_lse + AB_T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * AB_T;
+    const int e = p.sets > 1 ? blockIdx.z % p.sets : 0;
+    const int b = p.sets > 1 ? blockIdx.z / p.sets : blockIdx.z;
+    const int h = blockIdx.y, k0 = blockIdx.x * AB_T;
     const int dch = p.d / 8;
     const __half* qg = p.q + (size_t)b * p.qbs + (size_t)h * p.hs;
-    const __half* kg = p.k + (size_t)b * p.kbs + (size_t)h * p.hs;
-    const __half* vg = p.v + (size_t)b * p.vbs + (size_t)h * p.hs;
+    const __half* kg = p.k + (size_t)b * p.kbs + (size_t)h * p.hs + (size_t)e * p.set_stride;
+    const __half* vg = p.v + (size_t)b * p.vbs + (size_t)h * p.hs + (size_t)e * p.set_stride;
     const __half* og = p.dout + (size_t)b * p.dobs + (size_t)h * p.d;
-    const float g = p.gate ? p.gate[(size_t)b * p.gate_stride] : 1.0f;
-    const size_t sbase = ((size_t)b * p.heads + h) * p.n_q;
+    const float g = p.gate ? p.gate[(size_t)b * p.gate_stride + (size_t)e * p.gate_set_stride] : 1.0f;
+    const size_t sbase = (((size_t)b * p.heads + h) * p.sets + e) * p.n_q;
     const int nqt = (p.n_q + AB_T - 1) / AB_T;
 
     b_load_tile<DP>(kg, p.ldk, k0, p.n_kv, dch, sK);
@@ -343,8 +346,8 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const BwdArgs 
             b_mma_nn<DP, AB_T, DC>(dv, pf, sdO, c0, lane);          // dv += P^T dO
             b_mma_nn<DP, AB_T, DC>(dk, dsf, sQ, c0, lane);          // dk += dS^T Q
         }
-        __half* dkg = p.dk + (size_t)b * p.dkbs + (size_t)h * p.hs;
-        __half* dvg = p.dv + (size_t)b * p.dvbs + (size_t)h * p.hs;
+        __half* dkg = p.dk + (size_t)b * p.dkbs + (size_t)h * p.hs + (size_t)e * p.set_stride;
+        __half* dvg = p.dv + (size_t)b * p.dvbs + (size_t)h * p.hs + (size_t)e * p.set_stride;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int row = k0 + warp * 16 + (lane >> 2) + r * 8;
@@ -361,6 +364,172 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const BwdArgs 
             }
         }
     }
+}
+
+// ---- expert streams: sum_e g_e Attn(q, K_e, V_e) with every expert's few visual tokens in ONE key tile ------------
+// (oracle/anysd_oracle.py cross_extra; ip_adapter/attention_processor.py:160-176).  One launch per layer instead of E:
+// the CTA keeps its 64 query rows and walks the experts; each expert has its own softmax, complete inside the tile,
+// so P is normalised and gated BEFORE the P.V product and the output / dq accumulators simply add over experts.
+struct ExpArgs {
+    const __half* q; const __half* kv; const __half* dout;
+    __half* out; __half* dq;
+    long long qbs, kvbs, obs, dobs, dqbs;
+    int ldq, ldkv, ldo, lddo, lddq;
+    int n_q, n_kv, d, hs, heads, E, set_stride, v_off;
+    float c_nat, c_log2;
+    const float* gates; float* dgates; int gate_b_stride;
+    float* lse; float* D;                // [B, heads, E, n_q]
+};
+
+template <int DP, bool BWD>
+__global__ void __launch_bounds__(AB_THREADS) expert_attn_kernel(const ExpArgs p) {
+    constexpr int LDS = DP + 8, TILE = AB_T * LDS;
+    extern __shared__ __align__(128) __half ab_smem[];
+    __half* sQ = ab_smem;
+    __half* sK = sQ + TILE;
+    __half* sV = sK + TILE;
+    __half* sdO = sV + TILE;             // BWD only
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AB_T;
+    const int dch = p.d / 8;
+    const __half* qg = p.q + (size_t)b * p.qbs + (size_t)h * p.hs;
+    b_load_tile<DP>(qg, p.ldq, q0, p.n_q, dch, sQ);
+    if (BWD) b_load_tile<DP>(p.dout + (size_t)b * p.dobs + (size_t)h * p.d, p.lddo, q0, p.n_q, dch, sdO);
+    cp_async_commit();
+    float acc[DP / 8][4];                // forward: O;  backward: dq
+#pragma unroll
+    for (int i = 0; i < DP / 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int e = 0; e < p.E; ++e) {
+        const __half* kg = p.kv + (size_t)b * p.kvbs + (size_t)e * p.set_stride + (size_t)h * p.hs;
+        __syncthreads();
+        b_load_tile<DP>(kg, p.ldkv, 0, p.n_kv, dch, sK);
+        b_load_tile<DP>(kg + p.v_off, p.ldkv, 0, p.n_kv, dch, sV);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        const float g = p.gates[(size_t)b * p.gate_b_stride + e];
+        float s[AB_T / 8][4];
+        b_mma_nt<DP, AB_T>(s, sQ, warp * 16, sK, lane);
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < AB_T / 8; ++j)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int col = j * 8 + (lane & 3) * 2 + (t & 1);
+                const float v = col < p.n_kv ? s[j][t] * p.c_log2 : -INFINITY;
+                s[j][t] = v;
+                mx[t >> 1] = fmaxf(mx[t >> 1], v);
+            }
+        float l[2] = {0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        }
+#pragma unroll
+        for (int j = 0; j < AB_T / 8; ++j)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                s[j][t] = b_ex2(s[j][t] - mx[t >> 1]);          // masked columns: exp2(-inf) = 0
+                l[t >> 1] += s[j][t];
+            }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+            l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+        }
+        const float inv[2] = {1.0f / l[0], 1.0f / l[1]};
+        uint32_t af[AB_T / 16][4];
+        if (!BWD) {
+#pragma unroll
+            for (int j = 0; j < AB_T / 8; ++j) {
+                af[j >> 1][(j & 1) * 2 + 0] = pack_h2(s[j][0] * inv[0] * g, s[j][1] * inv[0] * g);
+                af[j >> 1][(j & 1) * 2 + 1] = pack_h2(s[j][2] * inv[1] * g, s[j][3] * inv[1] * g);
+            }
+            b_mma_nn<DP, AB_T, DP>(acc, af, sV, 0, lane);       // O += (g / l) P V
+        } else {
+            float dp[AB_T / 8][4];
+            b_mma_nt<DP, AB_T>(dp, sdO, warp * 16, sV, lane);
+            float d_raw[2] = {0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < AB_T / 8; ++j)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    s[j][t] *= inv[t >> 1];                       // p_ij
+                    d_raw[t >> 1] += s[j][t] * dp[j][t];
+                }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                d_raw[r] += __shfl_xor_sync(0xffffffffu, d_raw[r], 1);
+                d_raw[r] += __shfl_xor_sync(0xffffffffu, d_raw[r], 2);
+            }
+            const size_t base = (((size_t)b * p.heads + h) * p.E + e) * p.n_q;
+            float dg_part = 0.f;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int row = q0 + warp * 16 + (lane >> 2) + r * 8;
+                if (row < p.n_q && (lane & 3) == 0) {
+                    p.lse[base + row] = mx[r] + log2f(l[r]);
+                    p.D[base + row] = g * d_raw[r];
+                    dg_part += d_raw[r];
+                }
+            }
+            dg_part = warp_sum(dg_part);
+            if (lane == 0 && dg_part != 0.f) atomicAdd(p.dgates + (size_t)b * p.gate_b_stride + e, dg_part);
+#pragma unroll
+            for (int j = 0; j < AB_T / 8; ++j) {
+                float ds[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) ds[t] = p.c_nat * g * s[j][t] * (dp[j][t] - d_raw[t >> 1]);
+                af[j >> 1][(j & 1) * 2 + 0] = pack_h2(ds[0], ds[1]);
+                af[j >> 1][(j & 1) * 2 + 1] = pack_h2(ds[2], ds[3]);
+            }
+            b_mma_nn<DP, AB_T, DP>(acc, af, sK, 0, lane);       // dq += dS K
+        }
+    }
+    // accumulate onto the text attention's output / dq
+    __half* og = BWD ? p.dq + (size_t)b * p.dqbs + (size_t)h * p.hs : p.out + (size_t)b * p.obs + (size_t)h * p.d;
+    const int ld = BWD ? p.lddq : p.ldo;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int row = q0 + warp * 16 + (lane >> 2) + r * 8;
+        if (row >= p.n_q) continue;
+#pragma unroll
+        for (int i = 0; i < DP / 8; ++i) {
+            const int col = i * 8 + (lane & 3) * 2;
+            if (col >= p.d) continue;
+            __half2* dst = reinterpret_cast<__half2*>(og + (size_t)row * ld + col);
+            const float2 prev = __half22float2(*dst);
+            *dst = __floats2half2_rn(prev.x + acc[i][r * 2], prev.y + acc[i][r * 2 + 1]);
+        }
+    }
+}
+
+template <int DP>
+static int launch_experts(const ExpArgs& a, const BwdArgs* dkv, int B, cudaStream_t st) {
+    constexpr int LDS = DP + 8;
+    constexpr int DC = DP > 96 ? DP / 2 : DP;
+    const int smem = 4 * AB_T * LDS * (int)sizeof(__half) + 2 * AB_T * (int)sizeof(float);
+    static bool done[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!done[dev]) {
+        cudaFuncSetAttribute(expert_attn_kernel<DP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(expert_attn_kernel<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(attn_bwd_dkv_kernel<DP, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        done[dev] = true;
+    }
+    const dim3 grid(cdiv(a.n_q, AB_T), a.heads, B);
+    if (dkv == nullptr) {
+        expert_attn_kernel<DP, false><<<grid, AB_THREADS, smem, st>>>(a);
+        return check_launch("expert attention");
+    }
+    expert_attn_kernel<DP, true><<<grid, AB_THREADS, smem, st>>>(a);
+    int rc = check_launch("expert attention backward (dq)");
+    if (rc) return rc;
+    attn_bwd_dkv_kernel<DP, DC><<<dim3(cdiv(a.n_kv, AB_T), a.heads, B * a.E), AB_THREADS, smem, st>>>(*dkv);
+    return check_launch("expert attention backward (dk, dv)");
 }
 
 template <int DP>
@@ -430,6 +599,7 @@ extern "C" int anysd_attention_bwd_f16(const anysd_attn_bwd_params* p, anysd_str
     ANYSD_REQUIRE(p->out == nullptr || (p->gate == nullptr && p->ld_o % 8 == 0 && ((uintptr_t)p->out % 16) == 0 && p->o_batch_stride % 8 == 0),
                   ANYSD_EINVAL, "attention_bwd: `out` must be the un-gated output of this attention, 16-byte aligned, ld_o %% 8 == 0");
     a.o = (const __half*)p->out; a.obs = p->o_batch_stride; a.ldo = p->ld_o;
+    a.sets = 1; a.set_stride = 0; a.gate_set_stride = 0;
     cudaStream_t st = (cudaStream_t)stream;
     const bool need = p->dk != nullptr;
     switch (dp) {
@@ -445,4 +615,81 @@ extern "C" int anysd_attention_bwd_f16(const anysd_attn_bwd_params* p, anysd_str
             set_error("attention_bwd: head dim %d not supported", p->d);
             return ANYSD_EUNSUPPORTED;
     }
+}
+
+extern "C" size_t anysd_expert_attention_bwd_workspace_bytes(int B, int heads, int E, int n_q) {
+    if (B <= 0 || heads <= 0 || E <= 0 || n_q <= 0) return 0;
+    return (size_t)2 * B * heads * E * n_q * sizeof(float);
+}
+
+static int expert_common(const anysd_expert_attn_params* p, bool bwd, ExpArgs& a) {
+    ANYSD_REQUIRE(p != nullptr && p->q && p->kv && p->gates, ANYSD_EINVAL, "expert_attention: null pointer");
+    ANYSD_REQUIRE(p->B > 0 && p->heads > 0 && p->n_q > 0 && p->E > 0 && p->n_kv > 0 && p->n_kv <= AB_T, ANYSD_EUNSUPPORTED,
+                  "expert_attention: every expert's tokens must fit one key tile (n_kv <= %d, got %d)", AB_T, p->n_kv);
+    ANYSD_REQUIRE(p->d > 0 && p->d % 8 == 0 && p->d <= 160, ANYSD_EUNSUPPORTED, "expert_attention: head dim %d", p->d);
+    const int hs = p->head_stride > 0 ? p->head_stride : p->d;
+    ANYSD_REQUIRE(hs % 8 == 0 && hs >= p->d, ANYSD_EINVAL, "expert_attention: bad head_stride");
+    ANYSD_REQUIRE(p->ld_q % 8 == 0 && p->ld_kv % 8 == 0 && p->set_stride % 8 == 0 && p->v_offset % 8 == 0 && p->ld_o % 2 == 0, ANYSD_EINVAL,
+                  "expert_attention: leading dims / offsets must be multiples of 8");
+    ANYSD_REQUIRE(((uintptr_t)p->q % 16) == 0 && ((uintptr_t)p->kv % 16) == 0, ANYSD_EINVAL, "expert_attention: 16-byte alignment");
+    ANYSD_REQUIRE(p->heads <= 65535 && (long long)p->B * p->E <= 65535, ANYSD_EINVAL, "expert_attention: grid too large");
+    a.q = (const __half*)p->q; a.kv = (const __half*)p->kv; a.out = (__half*)p->out;
+    a.qbs = (long long)p->n_q * p->ld_q; a.kvbs = (long long)p->n_kv * p->ld_kv; a.obs = (long long)p->n_q * p->ld_o;
+    a.ldq = p->ld_q; a.ldkv = p->ld_kv; a.ldo = p->ld_o;
+    a.n_q = p->n_q; a.n_kv = p->n_kv; a.d = p->d; a.hs = hs; a.heads = p->heads; a.E = p->E;
+    a.set_stride = p->set_stride; a.v_off = p->v_offset;
+    a.c_nat = p->qk_scale; a.c_log2 = p->qk_scale * 1.4426950408889634f;
+    a.gates = p->gates; a.gate_b_stride = p->gate_b_stride;
+    a.dout = nullptr; a.dq = nullptr; a.dgates = nullptr; a.lse = a.D = nullptr; a.dobs = a.dqbs = 0; a.lddo = a.lddq = 0;
+    (void)bwd;
+    return ANYSD_OK;
+}
+
+#define ANYSD_EXP_DISPATCH(CALL)                                                               \
+    switch ((p->d + 15) / 16 * 16) {                                                           \
+        case 16: return CALL(16); case 32: return CALL(32); case 48: return CALL(48);          \
+        case 64: return CALL(64); case 80: return CALL(80); case 96: return CALL(96);          \
+        case 128: return CALL(128); case 160: return CALL(160);                                \
+        default: set_error("expert_attention: head dim %d not supported", p->d); return ANYSD_EUNSUPPORTED; \
+    }
+
+extern "C" int anysd_expert_attention_f16(const anysd_expert_attn_params* p, anysd_stream_t stream) {
+    ExpArgs a;
+    int rc = expert_common(p, false, a);
+    if (rc) return rc;
+    ANYSD_REQUIRE(p->out != nullptr, ANYSD_EINVAL, "expert_attention: null out");
+#define ANYSD_CALL(DPV) launch_experts<DPV>(a, nullptr, p->B, (cudaStream_t)stream)
+    ANYSD_EXP_DISPATCH(ANYSD_CALL)
+#undef ANYSD_CALL
+}
+
+extern "C" int anysd_expert_attention_bwd_f16(const anysd_expert_attn_params* p, const void* d_out, int ld_do, void* dq, int ld_dq,
+                                              void* dkv, float* d_gates, void* workspace, size_t workspace_bytes,
+                                              anysd_stream_t stream) {
+    ExpArgs a;
+    int rc = expert_common(p, true, a);
+    if (rc) return rc;
+    ANYSD_REQUIRE(d_out && dq && dkv && d_gates && workspace, ANYSD_EINVAL, "expert_attention_bwd: null pointer");
+    ANYSD_REQUIRE(ld_do % 8 == 0 && ld_dq % 2 == 0 && ((uintptr_t)d_out % 16) == 0, ANYSD_EINVAL, "expert_attention_bwd: bad strides");
+    ANYSD_REQUIRE(workspace_bytes >= anysd_expert_attention_bwd_workspace_bytes(p->B, p->heads, p->E, p->n_q), ANYSD_EINVAL,
+                  "expert_attention_bwd: workspace too small");
+    const int dp = (p->d + 15) / 16 * 16;
+    ANYSD_REQUIRE(a.hs <= dp, ANYSD_EINVAL, "expert_attention_bwd: head_stride must be <= ceil16(d)");
+    a.dout = (const __half*)d_out; a.lddo = ld_do; a.dobs = (long long)p->n_q * ld_do;
+    a.dq = (__half*)dq; a.lddq = ld_dq; a.dqbs = (long long)p->n_q * ld_dq;
+    a.dgates = d_gates;
+    a.lse = (float*)workspace; a.D = a.lse + (size_t)p->B * p->heads * p->E * p->n_q;
+    BwdArgs k;
+    k.q = a.q; k.k = a.kv; k.v = a.kv + p->v_offset; k.dout = a.dout;
+    k.dq = nullptr; k.dk = (__half*)dkv; k.dv = (__half*)dkv + p->v_offset;
+    k.qbs = a.qbs; k.kbs = a.kvbs; k.vbs = a.kvbs; k.dobs = a.dobs; k.dqbs = 0; k.dkbs = a.kvbs; k.dvbs = a.kvbs;
+    k.ldq = a.ldq; k.ldk = a.ldkv; k.ldv = a.ldkv; k.lddo = ld_do; k.lddq = 0; k.lddk = a.ldkv; k.lddv = a.ldkv;
+    k.n_q = a.n_q; k.n_kv = a.n_kv; k.d = a.d; k.hs = a.hs; k.heads = a.heads;
+    k.c_nat = a.c_nat; k.c_log2 = a.c_log2;
+    k.gate = a.gates; k.gate_stride = a.gate_b_stride; k.dgate = nullptr; k.accumulate_dq = 0;
+    k.lse = a.lse; k.D = a.D; k.o = nullptr; k.obs = 0; k.ldo = 0;
+    k.sets = p->E; k.set_stride = p->set_stride; k.gate_set_stride = 1;
+#define ANYSD_CALL(DPV) launch_experts<DPV>(a, &k, p->B, (cudaStream_t)stream)
+    ANYSD_EXP_DISPATCH(ANYSD_CALL)
+#undef ANYSD_CALL
 }

@@ -1,12 +1,10 @@
 // GroupNorm(+SiLU) on NHWC fp16 and LayerNorm on token rows.  HBM-bound kernels:
 // 16-byte vector loads/stores, fp32 statistics, warp-shuffle / smem reductions.
 //
-// GroupNorm is two launches:
-//   gn_stats_kernel : grid (S, N); each thread owns ONE 8-channel vector column and walks rows,
-//                     so per-channel partial sums live in registers; one smem reduction per block
-//                     writes per-(block, group) {sum, sumsq} partials.
-//   gn_apply_kernel : prologue folds the S partials (in double) into per-channel a = rstd*gamma,
-//                     b = beta - mean*a held in registers, then streams y = silu(a*x + b).
+// GroupNorm: the image is cut into chunks of GN_U * R rows; each thread owns ONE 8-channel vector column and issues
+// its row loads at once, so per-channel partial sums live in registers; one smem fold per chunk writes per-(chunk,
+// group) {sum, sumsq} partials.  Default = one cooperative launch (gn_fused_kernel: partials | grid barrier | fold in
+// double + streaming y = silu(a*x + b)); gn_stats_kernel + gn_apply_kernel run the same chunks as two launches.
 // The input may be the channel concat of two tensors (x2 != nullptr): columns < C1/8 come from x1.
 #include "common.cuh"
 

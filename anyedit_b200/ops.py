@@ -354,6 +354,42 @@ def attention_bwd(q, k, v, d_out, dq, dk, dv, B, heads, n_q, n_kv, d, ld_q, ld_k
     _count(2 if dk is not None else 1)
 
 
+def _expert_params(q, ekv, gates, B, heads, n_q, n_kv, d, E, ld_q, ld_kv, ld_o, set_stride, v_offset, qk_scale, head_stride, out=None):
+    p = _lib.ExpertAttnParams()
+    p.q, p.kv = q.data_ptr(), ekv.data_ptr()
+    p.out = out.data_ptr() if out is not None else None
+    p.ld_q, p.ld_kv, p.ld_o = ld_q, ld_kv, ld_o
+    p.B, p.heads, p.n_q, p.n_kv, p.d, p.head_stride, p.E = B, heads, n_q, n_kv, d, head_stride, E
+    p.set_stride, p.v_offset = set_stride, v_offset
+    p.qk_scale = float(qk_scale)
+    p.gates, p.gate_b_stride = gates.data_ptr(), gates.stride(0)
+    return p
+
+
+def expert_attention(q, ekv, gates, out, B, heads, n_q, n_kv, d, E, ld_q, ld_kv, ld_o, set_stride, v_offset, qk_scale, head_stride=0):
+    """out += sum_e gates[b, e] * softmax(qk_scale * q K_e^T) V_e for the E expert streams of one layer (one launch).
+    gates: fp32 view [B, >= E] whose row stride selects the layer (gates[:, layer])."""
+    _cuda(q, ekv, gates, out)
+    p = _expert_params(q, ekv, gates, B, heads, n_q, n_kv, d, E, ld_q, ld_kv, ld_o, set_stride, v_offset, qk_scale, head_stride, out)
+    with _Traced("expert_attention", 4.0 * B * heads * n_q * n_kv * d * E, f"B={B} h={heads} nq={n_q} nkv={n_kv} d={d} E={E}"):
+        _lib.check(_lib.load().anysd_expert_attention_f16(C.byref(p), _stream()), "expert_attention")
+    _count()
+
+
+def expert_attention_bwd(q, ekv, gates, d_out, dq, dekv, d_gates, B, heads, n_q, n_kv, d, E, ld_q, ld_kv, ld_do, ld_dq, set_stride, v_offset,
+                         qk_scale, head_stride=0):
+    """Backward of `expert_attention`: dq += , dekv written in ekv's layout, d_gates (same view shape as gates) += ."""
+    _cuda(q, ekv, gates, d_out, dq, dekv, d_gates)
+    assert d_gates.stride(0) == gates.stride(0)
+    p = _expert_params(q, ekv, gates, B, heads, n_q, n_kv, d, E, ld_q, ld_kv, ld_do, set_stride, v_offset, qk_scale, head_stride)
+    nbytes = _lib.load().anysd_expert_attention_bwd_workspace_bytes(B, heads, E, n_q)
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=q.device)
+    with _Traced("expert_attention_bwd", 0.0, f"B={B} h={heads} nq={n_q} nkv={n_kv} d={d} E={E}"):
+        _lib.check(_lib.load().anysd_expert_attention_bwd_f16(C.byref(p), _ptr(d_out), ld_do, _ptr(dq), ld_dq, _ptr(dekv), _ptr(d_gates),
+                                                              _ptr(ws), nbytes, _stream()), "expert_attention_bwd")
+    _count(2)
+
+
 def colsum(x, out, N, rows, accumulate=False):
     """x [N, rows, C] fp16 -> out[:N, :C] (fp32, row stride out.stride(0))."""
     _cuda(x, out)

@@ -425,11 +425,10 @@ class AdapterTrainer:
                     Lp = st["MP"]["layers"][st["layer"]]
                     ekv = torch.empty(N * n_vis, E * 2 * Cp, dtype=torch.float16, device=dev)
                     ops.gemm(st["vis"].view(N * n_vis, -1), Lp["kv_w"], ekv, bias=Lp["kv_b"])
-                    ld, nl = E * 2 * Cp, st["gates"].shape[1]
-                    for e in range(E):
-                        ops.attention(q, ekv[:, e * 2 * Cp:], ekv[:, e * 2 * Cp + Cp:], a, N, ad["heads"], n_q, n_vis, ad["d"], Cp, ld, ld, C,
-                                      gate=st["gates"][:, st["layer"], e:], gate_stride=nl * E, accumulate=True, head_stride=hs,
-                                      aux_cols=ad["aux"])
+                    assert n_vis <= 64, "training path: at most 64 visual tokens per request"
+                    qk = math.log(2.0) if ad["aux"] else ad["d"] ** -0.5
+                    ops.expert_attention(q, ekv, st["gates"][:, st["layer"]], a, N, ad["heads"], n_q, n_vis, ad["d"], E, Cp, E * 2 * Cp, C,
+                                         2 * Cp, Cp, qk, head_stride=hs)
                     c["ekv"] = ekv
                 st["layer"] += 1
         ops.gemm(a, ad["o_w"], out, bias=ad["o_b"], residual=residual)
@@ -459,11 +458,9 @@ class AdapterTrainer:
             E, n_vis, layer = st["E"], st["n_vis"], c["layer"]
             ekv = c["ekv"]
             dekv = torch.empty_like(ekv)
-            ld, nl = E * 2 * Cp, st["gates"].shape[1]
-            for e in range(E):
-                ops.attention_bwd(q, ekv[:, e * 2 * Cp:], ekv[:, e * 2 * Cp + Cp:], d_a, dq, dekv[:, e * 2 * Cp:], dekv[:, e * 2 * Cp + Cp:],
-                                  N, heads, n_q, n_vis, d, Cp, ld, ld, C, Cp, ld, ld, qk_scale=qk, gate=st["gates"][:, layer, e:],
-                                  gate_stride=nl * E, d_gate=G["d_gates"][:, layer, e:], accumulate_dq=True, head_stride=hs)
+            ld = E * 2 * Cp
+            ops.expert_attention_bwd(q, ekv, st["gates"][:, layer], d_a, dq, dekv, G["d_gates"][:, layer], N, heads, n_q, n_vis, d, E,
+                                     Cp, ld, C, Cp, 2 * Cp, Cp, qk, head_stride=hs)
             vis = st["vis"].view(N * n_vis, -1)
             gk, gv = G[f"adapter_modules.{layer}.to_k_ip.weight"], G[f"adapter_modules.{layer}.to_v_ip.weight"]
             # dW_e = dK_e^T vis for all experts in one launch each (parameter layout: expert-major rows, un-padded heads)

@@ -221,6 +221,27 @@ typedef struct {
 size_t anysd_attention_bwd_workspace_bytes(int B, int heads, int n_q);
 int anysd_attention_bwd_f16(const anysd_attn_bwd_params* p, anysd_stream_t stream);
 
+/* ---- expert streams of one cross-attention layer in one launch (restated spec, oracle/anysd_oracle.py; template
+ * ip_adapter/attention_processor.py:160-176):  out += sum_e gates[b, e] * softmax(c q K_e^T) V_e.
+ * kv [B, n_kv, ld_kv] holds, for expert e, K at columns [e*set_stride + h*head_stride, ...) and V v_offset columns
+ * further (the layout one GEMM over the stacked to_k_ip / to_v_ip weights produces); n_kv <= 64 visual tokens.
+ * qk_scale as in anysd_attention_bwd_f16.  out [B, n_q, ld_o] fp16 is accumulated onto (the text attention's output). */
+typedef struct {
+    const void* q; const void* kv; void* out;
+    int ld_q, ld_kv, ld_o;
+    int B, heads, n_q, n_kv, d, head_stride, E;
+    int set_stride, v_offset;
+    float qk_scale;
+    const float* gates; int gate_b_stride;      /* gates[b * gate_b_stride + e] */
+} anysd_expert_attn_params;
+int anysd_expert_attention_f16(const anysd_expert_attn_params* p, anysd_stream_t stream);
+/* backward: dq [B, n_q, ld_dq] += (onto the text attention's dq), dkv written in the layout of kv, d_gates indexed like
+ * gates and accumulated atomically; workspace >= anysd_expert_attention_bwd_workspace_bytes(B, heads, E, n_q). */
+size_t anysd_expert_attention_bwd_workspace_bytes(int B, int heads, int E, int n_q);
+int anysd_expert_attention_bwd_f16(const anysd_expert_attn_params* p, const void* d_out, int ld_do, void* dq, int ld_dq,
+                                   void* dkv, float* d_gates, void* workspace, size_t workspace_bytes,
+                                   anysd_stream_t stream);
+
 /* out[n, c] (+)= sum_rows x[n, r, c]: gradient of the per-image time-embedding row add (openaimodel.py:262-263) */
 int anysd_colsum_f16(const void* x, float* out, int N, int rows, int C, int ld_out, int accumulate, anysd_stream_t stream);
 /* y += x (gradient accumulation where a tensor feeds two consumers: residual / skip connections) */

@@ -282,3 +282,55 @@ def test_router_backward_and_scatter(ops):
     dtab = torch.zeros(T, D, device="cuda")
     ops.scatter_add_rows(dte, idx.cuda(), dtab)
     assert rel(dtab, tr.grad) < 1e-4
+
+
+@pytest.mark.parametrize("B,heads,nq,nvis,d,E,ln2", [(2, 3, 100, 16, 40, 4, True), (1, 2, 130, 5, 64, 3, False), (2, 2, 70, 64, 160, 2, False),
+                                                     (3, 4, 64, 7, 16, 11, False)])
+def test_expert_attention_forward_backward(ops, B, heads, nq, nvis, d, E, ln2):
+    """All E expert streams of a layer in one launch: out += sum_e g[b,e] softmax(c q K_e^T) V_e, and its backward
+    (dq accumulated, dK_e / dV_e in the fused [K_e | V_e] layout, gate gradients) vs autograd."""
+    from anyedit_b200.unet import head_stride_for
+    hs = head_stride_for(d)
+    C, Cp = heads * d, heads * hs
+    scale = d ** -0.5
+    q = h16(randn(81, B, nq, heads, d))
+    if ln2:
+        q = h16(q * scale * math.log2(math.e))
+    c = math.log(2.0) if ln2 else scale
+    k, v = h16(randn(82, B, nvis, E, heads, d)), h16(randn(83, B, nvis, E, heads, d))
+    gates = torch.rand(B, 3, E, generator=torch.Generator().manual_seed(84))          # [B, layers, E]: layer 1 is used
+    base = h16(randn(85, B, nq, C) * 0.5)
+    dO = h16(randn(86, B, nq, heads, d) * 0.1)
+    qr, kr, vr, gr = (t.clone().requires_grad_(True) for t in (q, k, v, gates))
+    s = torch.einsum("bihd,bjehd->behij", qr, kr) * c
+    o = torch.einsum("behij,bjehd->behid", s.softmax(-1), vr)
+    o = (o * gr[:, 1].view(B, E, 1, 1, 1)).sum(1).permute(0, 2, 1, 3)                 # [B, nq, heads, d]
+    o.backward(dO)
+
+    def padq(t):
+        out = torch.zeros(B, nq, heads, hs, dtype=torch.float16)
+        out[..., :d] = t
+        return out.reshape(B, nq, Cp).cuda().contiguous()
+
+    ekv = torch.zeros(B, nvis, E, 2, heads, hs, dtype=torch.float16)
+    ekv[:, :, :, 0, :, :d] = k
+    ekv[:, :, :, 1, :, :d] = v
+    ekv = ekv.reshape(B * nvis, E * 2 * Cp).cuda().contiguous()
+    out = base.half().cuda().contiguous()
+    g_dev = gates.cuda()
+    q16 = padq(q)
+    ops.expert_attention(q16, ekv, g_dev[:, 1], out, B, heads, nq, nvis, d, E, Cp, E * 2 * Cp, C, 2 * Cp, Cp, c, head_stride=hs)
+    assert rel(out.float().cpu() - base, o.detach().reshape(B, nq, C)) < 3e-3
+    dq = torch.zeros(B, nq, Cp, dtype=torch.float16, device="cuda")
+    dekv = torch.full_like(ekv, float("nan"))
+    dg = torch.zeros_like(g_dev)
+    ops.expert_attention_bwd(q16, ekv, g_dev[:, 1], dO.reshape(B, nq, C).half().cuda().contiguous(), dq, dekv, dg[:, 1], B, heads, nq, nvis, d,
+                             E, Cp, E * 2 * Cp, C, Cp, 2 * Cp, Cp, c, head_stride=hs)
+    torch.cuda.synchronize()
+    assert rel(dq.float().cpu().view(B, nq, heads, hs)[..., :d], qr.grad) < 4e-3
+    d5 = dekv.float().cpu().view(B, nvis, E, 2, heads, hs)
+    assert torch.isfinite(d5).all()
+    assert rel(d5[:, :, :, 0, :, :d], kr.grad) < 4e-3 and rel(d5[:, :, :, 1, :, :d], vr.grad) < 4e-3
+    if hs > d:
+        assert float(d5[..., d:].abs().max()) == 0.0
+    assert rel(dg[:, 1], gr.grad[:, 1]) < 4e-3 and float(dg[:, 0].abs().max()) == 0.0

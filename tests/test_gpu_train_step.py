@@ -175,3 +175,47 @@ def test_c4_training_step_sd15_geometry():
     print("[C4 training step, sd15 geometry, 11 experts] worst relative L2 per gradient kind:", {k: f"{v:.2e}" for k, v in worst.items()})
     for k, v in worst.items():
         assert v < (ROUTER_TOL if k.startswith("router") else 3e-2), (k, v)
+
+
+def test_training_two_rank_nccl(tmp_path):
+    """config 4 is data parallel over 8 GPUs: 2 ranks (skipped on a 1-GPU box) each back-propagate half of a 4-request
+    batch, all-reduce the trainables' gradients over NCCL and step; both ranks end with identical parameters, equal
+    (up to fp16 batch-composition noise) to one rank stepping on the whole batch's mean gradient."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    script = tmp_path / "t.py"
+    script.write_text(
+        "import os, sys, json, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "from anyedit_b200 import distributed as D\n"
+        "from anyedit_b200.training import AdapterTrainer\n"
+        "from test_gpu_train_step import _setup\n"
+        "rank, local, world = D.init_from_env('nccl')\n"
+        "moe, sd, asd, cfg, b, acp = _setup('tiny_a', 11, E=3, T=6, B=4, hw=16, n_vis=5)\n"
+        "D.broadcast_module_(moe, src=0)\n"
+        "lo, hi = D.shard_range(4, rank, world)\n"
+        "c = {k: (v[lo:hi].cuda() if v is not None else None) for k, v in b.items()}\n"
+        "tr = AdapterTrainer(moe, lr=1e-2, loss_scale=256.0)\n"
+        "tr.step(c['latents'], c['noise'], c['t'], c['image_latent'], c['text'], c['vis'], c['code'])\n"
+        "w = moe.adapter_modules[3].to_k_ip.weight.detach().float().flatten()[:4096].contiguous()\n"
+        "ws = [torch.empty_like(w) for _ in range(world)]\n"
+        "dist.all_gather(ws, w)\n"
+        "assert torch.equal(ws[0], ws[1])\n"
+        "if rank == 0:\n"
+        "    moe2, *_ = _setup('tiny_a', 11, E=3, T=6, B=4, hw=16, n_vis=5)\n"
+        "    full = {k: (v.cuda() if v is not None else None) for k, v in b.items()}\n"
+        "    tr2 = AdapterTrainer(moe2, lr=1e-2, loss_scale=256.0)\n"
+        "    l0, _, g0 = tr2.loss_and_grads(*(full[k][:2] for k in ('latents', 'noise', 't', 'image_latent', 'text', 'vis', 'code')))\n"
+        "    l1, _, g1 = tr2.loss_and_grads(*(full[k][2:] for k in ('latents', 'noise', 't', 'image_latent', 'text', 'vis', 'code')))\n"
+        "    g0.pop('visual_tokens'); g1.pop('visual_tokens')\n"
+        "    tr2.apply_gradients({k: g0[k] + g1[k] for k in g0}, world=2)\n"
+        "    w2 = moe2.adapter_modules[3].to_k_ip.weight.detach().float().flatten()[:4096]\n"
+        "    assert float((w2 - w).abs().max()) < 1e-6, float((w2 - w).abs().max())\n"
+        "    print('OK')\n"
+        "dist.destroy_process_group()\n")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", str(script)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
