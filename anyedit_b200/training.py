@@ -53,6 +53,9 @@ class AdapterTrainer:
     trainables (train.py:486-492): ``moe.adapter_modules[*].{router.weight, router.bias, to_k_ip.weight, to_v_ip.weight}``
     and ``moe.task_embs.weight`` (the image projector lives upstream: ``step`` returns d loss / d visual tokens).
     Gradients are carried multiplied by ``loss_scale`` (fp16 activation gradients) and divided out inside AdamW.
+    ``lr`` is a plain attribute (set it per step for the reference's lr scheduler, train.py:706).  The reference's
+    ``clip_grad_norm_(unet.parameters(), ...)`` (train.py:703-704) acts on the frozen UNet, whose parameters carry no
+    gradients, so it never changes the adapter update; it is not reproduced.
     """
 
     def __init__(self, moe: MoE, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, loss_scale=1024.0,

@@ -209,3 +209,35 @@ def test_gradient_allreduce_two_rank_gloo(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29534", str(script)],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_training_host_logic():
+    """a24 host side: conditioning dropout == the restated train.py:651-669; the dX weight packs are the rotated /
+    transposed weights (checked against torch autograd on CPU, fp32); no CPU fallback for the step itself."""
+    import torch.nn.functional as F
+    from anyedit_b200 import training as T
+    from oracle import train_oracle
+    gen = torch.Generator().manual_seed(3)
+    text, null, img = torch.randn(6, 7, 16, generator=gen), torch.randn(1, 7, 16, generator=gen), torch.randn(6, 4, 8, 8, generator=gen)
+    p = torch.tensor([0.01, 0.06, 0.09, 0.12, 0.2, 0.9])
+    a, b = T.conditioning_dropout(text, null, img, p, 0.05)
+    ra, rb = train_oracle.conditioning_dropout(text, null, img, p, 0.05)
+    assert torch.equal(a, ra) and torch.equal(b, rb)
+    assert torch.equal(a[0], null[0]) and torch.equal(a[2], text[2]) and float(b[1].abs().max()) == 0.0 and torch.equal(b[0], img[0])
+    # conv: dX = conv3x3(dY, pack) with pack[ci, (a, b, co)] = w[co, ci, 2-a, 2-b]
+    w = torch.randn(5, 3, 3, 3, generator=gen)
+    x = torch.randn(2, 3, 6, 7, generator=gen, requires_grad=True)
+    dy = torch.randn(2, 5, 6, 7, generator=gen)
+    F.conv2d(x, w, padding=1).backward(dy)
+    pack = T.pack_conv3_dx(w, "cpu").float().reshape(3, 3, 3, 5).permute(0, 3, 1, 2)       # -> OIHW of the dX conv
+    assert torch.allclose(F.conv2d(dy, pack, padding=1), x.grad, atol=2e-2)                 # pack is fp16-rounded
+    wl = torch.randn(9, 4, generator=gen)
+    assert torch.allclose(T.pack_linear_dx(wl, "cpu").float(), wl.t().half().float())
+    # the step needs CUDA tensors
+    from anyedit_b200.anysd import MoE
+    from anyedit_b200.unet import UNetModel
+    meta = json.load(open(os.path.join(G, "tiny_a_keys.json")))
+    tr = T.AdapterTrainer(MoE(UNetModel(**meta["config"]), None, expert_num=2, num_tasks=3))
+    z = torch.zeros(1, 4, 16, 16)
+    with pytest.raises(RuntimeError):
+        tr.loss_and_grads(z, z, torch.zeros(1, dtype=torch.long), z, torch.zeros(1, 7, 64))
