@@ -223,7 +223,8 @@ def test_training_host_logic():
     a, b = T.conditioning_dropout(text, null, img, p, 0.05)
     ra, rb = train_oracle.conditioning_dropout(text, null, img, p, 0.05)
     assert torch.equal(a, ra) and torch.equal(b, rb)
-    assert torch.equal(a[0], null[0]) and torch.equal(a[2], text[2]) and float(b[1].abs().max()) == 0.0 and torch.equal(b[0], img[0])
+    assert torch.equal(a[0], null[0]) and torch.equal(a[2], null[0]) and torch.equal(a[3], text[3])      # text dropped for p < 2P
+    assert torch.equal(b[0], img[0]) and float(b[1].abs().max()) == 0.0 and float(b[3].abs().max()) == 0.0 and torch.equal(b[4], img[4])
     # conv: dX = conv3x3(dY, pack) with pack[ci, (a, b, co)] = w[co, ci, 2-a, 2-b]
     w = torch.randn(5, 3, 3, 3, generator=gen)
     x = torch.randn(2, 3, 6, 7, generator=gen, requires_grad=True)
