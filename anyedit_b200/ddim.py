@@ -11,6 +11,8 @@ Differences in execution only:
     step (conditioning mux, UNet forward, update) is captured once into a CUDA graph and
     replayed S times.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -316,6 +318,34 @@ def _cat_cond(uc, c):
     return torch.cat([uc, c])
 
 
+def _halves_share_prefix(uc, c):
+    """True when the uncond / cond halves of a CFG batch can only differ in the cross-attention context: dict
+    conditioning whose ``c_concat`` entries are the same tensors (or equal values) and no ``c_adm``.  The UNet then
+    computes everything before the first cross-attention once (unet.UNetModel.forward, shared CFG halves)."""
+    if os.environ.get("ANYSD_SHARE_CFG", "1")[:1] == "0":
+        return False
+    if not (isinstance(c, dict) and isinstance(uc, dict)) or set(c) != set(uc):
+        return False
+    if c.get("c_adm") is not None or uc.get("c_adm") is not None:
+        return False
+    a, b = c.get("c_concat") or [], uc.get("c_concat") or []
+    if len(a) != len(b):
+        return False
+    for x, y in zip(a, b):
+        if x is y or (x.data_ptr() == y.data_ptr() and x.shape == y.shape and x.stride() == y.stride() and x.dtype == y.dtype):
+            continue
+        if x.shape != y.shape or not torch.equal(x, y.to(x.device, x.dtype)):      # one host sync per sample() call
+            return False
+    return True
+
+
+def _find_unet(model):
+    """The anyedit_b200 UNetModel behind a LatentDenoiser / DiffusionWrapper (None for any other denoiser)."""
+    from .unet import UNetModel
+    m = getattr(getattr(model, "model", None), "diffusion_model", None)
+    return m if isinstance(m, UNetModel) else None
+
+
 def _tree_sig(c):
     if isinstance(c, dict):
         return tuple((k, _tree_sig(c[k])) for k in sorted(c))
@@ -371,15 +401,26 @@ class _Stepper:
         self.want_graph = bool(graph) and device.type == "cuda" and getattr(sampler.model, "graph_safe", False)
         self.scale = None
         self.n_eager = 0
+        self.unet = _find_unet(sampler.model)
+        self.shared = bool(use_cfg and self.unet is not None and _halves_share_prefix(uncond, cond))
 
     def rebind(self, cond, uncond):
         _tree_copy_(self.c_in, _cat_cond(uncond, cond) if self.use_cfg else cond)
+        shared = bool(self.use_cfg and self.unet is not None and _halves_share_prefix(uncond, cond))
+        if shared != self.shared:
+            self.shared, self.graph = shared, None       # the captured graph has the other structure: re-capture
 
     def _body(self, scale, noise):
         if self.use_cfg:
             self.x_in[: self.b].copy_(self.x_buf)
             self.x_in[self.b:].copy_(self.x_buf)
-        eps = self.s.model.apply_model(self.x_in, self.t_buf, self.c_in)
+        if self.shared:
+            self.unet._shared_halves = True              # x, c_concat and t of the two halves are identical
+        try:
+            eps = self.s.model.apply_model(self.x_in, self.t_buf, self.c_in)
+        finally:
+            if self.shared:
+                self.unet._shared_halves = False
         eps = eps.float().contiguous()
         ops.cfg_ddim_step(self.x_buf, eps, self.coef_buf, scale, self.use_cfg, self.x_prev, self.pred_x0, noise)
 

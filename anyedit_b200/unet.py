@@ -508,14 +508,31 @@ class UNetModel(nn.Module):
         st = {"N": N, "ws": ws, "emb_all": emb_all, "ctx": ctx16, "anysd": anysd, "layer": 0}
 
         # -- input conv --
-        xin = torch.zeros(N, H, W, self._cin_pad, **f16) if self._cin_pad != Cin else torch.empty(N, H, W, Cin, **f16)
-        ops.nchw_to_nhwc(x.contiguous(), xin, 0)
-        h = torch.empty(N, H, W, mc, **f16)
+        # Shared CFG halves (set by the DDIM stepper when x, c_concat, t and y of the uncond / cond halves are
+        # identical, ddim.py:190-210): only the cross-attention context differs, so everything before the first
+        # cross-attention K/V is computed for one half and duplicated -- bit-identical (every kernel is
+        # batch-independent), ~3 % of a forward at the SD-1.5 geometry (the first self-attention is the big part).
+        share = bool(getattr(self, "_shared_halves", False)) and N % 2 == 0 and y is None and control is None and anysd is None
+        Nx = N // 2 if share else N
+        xin = torch.zeros(Nx, H, W, self._cin_pad, **f16) if self._cin_pad != Cin else torch.empty(Nx, H, W, Cin, **f16)
+        ops.nchw_to_nhwc(x[:Nx].contiguous(), xin, 0)
+        h = torch.empty(Nx, H, W, mc, **f16)
         ops.conv3x3(xin, P["in_w"], h.view(-1, mc), bias=P["in_b"], logical_cin=Cin)
-        hs = [h]
+        hs = [self._dup_rows(h) if share else h]
         for blk in P["input"]:
-            h = self._run(blk, h, None, st)
-            hs.append(h)
+            if share:
+                has_st = any(kind == "st" for kind, _ in blk)
+                h = self._run(blk, h, None, st, share=has_st)
+                if has_st:
+                    share = False
+                    hs.append(h)
+                else:
+                    hs.append(self._dup_rows(h))
+            else:
+                h = self._run(blk, h, None, st)
+                hs.append(h)
+        if share:                                                 # no attention anywhere in the encoder
+            h = self._dup_rows(h)
         h = self._run(P["middle"], h, None, st)
         if control is not None:                                   # cldm.py:33-34
             ops.add_nchw_into_nhwc(control.pop().contiguous(), h)
@@ -536,13 +553,15 @@ class UNetModel(nn.Module):
         return out.to(x.dtype)
 
     # ---- block executors ----------------------------------------------------------------------------
-    def _run(self, blk, h, skip, st):
+    def _run(self, blk, h, skip, st, share=False):
+        """``share``: h is one CFG half (see _transformer); the first SpatialTransformer of the block widens it."""
         for kind, d in blk:
             if kind == "res":
                 h = self._resblock(d, h, skip, st)
                 skip = None
             elif kind == "st":
-                h = self._transformer(d, h, st)
+                h = self._transformer(d, h, st, share=share)
+                share = False
             elif kind == "down":
                 N, H, W, C = h.shape
                 o = torch.empty(N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, d["w"].shape[0], dtype=h.dtype, device=h.device)
@@ -582,12 +601,13 @@ class UNetModel(nn.Module):
         ops.conv3x3(b, d["c2_w"], out.view(-1, cout), bias=d["c2_b"], residual=res)
         return out
 
-    def _attn(self, ad, xq, ctx, N, n_q, st, self_attn, residual, out, expert=False):
-        """CrossAttention.forward (attention.py:163-194) + residual add of the caller (:272-273)."""
+    def _attn(self, ad, xq, ctx, N, n_q, st, self_attn, residual, out, expert=False, q_pre=None):
+        """CrossAttention.forward (attention.py:163-194) + residual add of the caller (:272-273).
+        ``q_pre``: the query projection computed by the caller (shared CFG halves), ``xq`` is then unused."""
         C = ad["heads"] * ad["d"]
         hs = ad["hs"]
         Cp = ad["heads"] * hs                     # projection width with padded heads (== C unless d % 16 != 0)
-        dev = xq.device
+        dev = residual.device
         a = torch.empty(N * n_q, C, dtype=torch.float16, device=dev)
         if self_attn:
             qkv = torch.empty(N * n_q, 3 * Cp, dtype=torch.float16, device=dev)
@@ -596,8 +616,11 @@ class UNetModel(nn.Module):
                           3 * Cp, 3 * Cp, 3 * Cp, C, head_stride=hs, aux_cols=ad["aux"])
         else:
             L = ctx.shape[1]
-            q = torch.empty(N * n_q, Cp, dtype=torch.float16, device=dev)
-            ops.gemm(xq, ad["q_w"], q)
+            if q_pre is not None:
+                q = q_pre
+            else:
+                q = torch.empty(N * n_q, Cp, dtype=torch.float16, device=dev)
+                ops.gemm(xq, ad["q_w"], q)
             kv = torch.empty(N * L, 2 * Cp, dtype=torch.float16, device=dev)
             ops.gemm(ctx.view(N * L, -1), ad["kv_w"], kv, bias=ad["kv_b"])
             ops.attention(q, kv, kv[:, Cp:], a, N, ad["heads"], n_q, L, ad["d"], Cp, 2 * Cp, 2 * Cp, C, head_stride=hs,
@@ -608,8 +631,19 @@ class UNetModel(nn.Module):
                 st["layer"] += 1
         ops.gemm(a, ad["o_w"], out, bias=ad["o_b"], residual=residual)
 
-    def _transformer(self, d, h, st):
-        """SpatialTransformer.forward (attention.py:321-340); NHWC makes both rearranges free."""
+    @staticmethod
+    def _dup_rows(t):
+        """[rows, ...] -> [2*rows, ...]: both CFG halves get the same values (two device-to-device copies)."""
+        out = torch.empty((2 * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        out[: t.shape[0]].copy_(t)
+        out[t.shape[0]:].copy_(t)
+        return out
+
+    def _transformer(self, d, h, st, share=False):
+        """SpatialTransformer.forward (attention.py:321-340); NHWC makes both rearranges free.
+        ``share``: ``h`` holds ONE half of a CFG batch whose two halves are identical up to here; everything before
+        the first cross-attention's K/V (GroupNorm, proj_in, LN1, self-attention, LN2, the query projection) is
+        computed once and duplicated, the rest runs on the full batch.  Returns the full batch."""
         N, H, W, C = h.shape
         n = H * W
         M = N * n
@@ -627,18 +661,27 @@ class UNetModel(nn.Module):
             if b["self"]:
                 self._attn(b["attn1"], ln, None, N, n, st, True, t, t2)
             else:
+                assert not share
                 self._attn(b["attn1"], ln, ctx, N, n, st, False, t, t2)
             ln2 = torch.empty_like(t)
             ops.layernorm(t2, b["ln2_w"], b["ln2_b"], ln2)
-            t3 = torch.empty_like(t)
             if ctx is None:   # "if no context is given, cross-attention defaults to self-attention"
                 raise NotImplementedError("attn2 without context (self-attention fallback) is not used on the AnySD path")
-            self._attn(b["attn2"], ln2, ctx, N, n, st, False, t2, t3, expert=True)
-            ln3 = torch.empty_like(t)
+            q_pre = None
+            if share:
+                ad = b["attn2"]
+                q_half = torch.empty(M, ad["heads"] * ad["hs"], dtype=torch.float16, device=dev)
+                ops.gemm(ln2, ad["q_w"], q_half)
+                q_pre, t2, h = self._dup_rows(q_half), self._dup_rows(t2), self._dup_rows(h)
+                N, M, share = 2 * N, 2 * M, False
+                t = None                                        # (half-batch tensor, not used again)
+            t3 = torch.empty_like(t2)
+            self._attn(b["attn2"], ln2, ctx, N, n, st, False, t2, t3, expert=True, q_pre=q_pre)
+            ln3 = torch.empty_like(t3)
             ops.layernorm(t3, b["ln3_w"], b["ln3_b"], ln3)
             ffh = torch.empty(M, b["ff2_w"].shape[1], dtype=torch.float16, device=dev)
             ops.gemm(ln3, b["ff1_w"], ffh, bias=b["ff1_b"], act=2)
-            t4 = torch.empty_like(t)
+            t4 = torch.empty_like(t3)
             ops.gemm(ffh, b["ff2_w"], t4, bias=b["ff2_b"], residual=t3)
             t = t4
         out = torch.empty(N, H, W, C, dtype=torch.float16, device=dev)

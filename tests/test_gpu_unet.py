@@ -389,3 +389,48 @@ def test_ddim_encode_inversion_vs_reference_formula():
     print(f"[ddim encode, 6 steps, scale 3] rel-L2 vs reference formula = {err:.3e}")
     assert err < 3e-3, err
     assert len(info["intermediates"]) == len(info["intermediate_steps"]) and tuple(info["x_encoded"].shape) == tuple(x0.shape)
+
+
+def test_shared_cfg_halves_bit_identical(monkeypatch):
+    """CFG doubles the batch with identical x / c_concat / t halves (ddim.py:190-210); only the context differs, so the
+    UNet computes everything before the first cross-attention K/V once and duplicates it.  Bit-identical to the plain
+    forward (every kernel is batch-independent), on the forward and through the sampler (graph and eager)."""
+    from anyedit_b200.ddim import DDIMSampler
+    net, _, _ = _build("tiny_a", 11)
+    gen = torch.Generator().manual_seed(77)
+    B = 3
+    x, ctx = torch.randn(B, 8, 16, 16, generator=gen), torch.randn(2 * B, 7, 64, generator=gen)
+    t = torch.tensor([981, 21, 501])
+    x2, t2 = torch.cat([x, x]).cuda(), torch.cat([t, t]).cuda()
+    plain = net(x2, t2, context=ctx.cuda())
+    net._shared_halves = True
+    try:
+        shared = net(x2, t2, context=ctx.cuda())
+    finally:
+        net._shared_halves = False
+    assert torch.equal(plain, shared)
+    assert not torch.equal(plain[:B], plain[B:])                # the halves do differ (different context)
+    # through the sampler: same c_concat tensor for both halves -> the stepper turns sharing on
+    model = _denoiser(net)
+    x_T, c_cat = torch.randn(B, 4, 16, 16, generator=gen).cuda(), torch.randn(B, 4, 16, 16, generator=gen).cuda()
+    c_txt, u_txt = torch.randn(B, 7, 64, generator=gen).cuda(), torch.randn(B, 7, 64, generator=gen).cuda()
+    outs = {}
+    for share in ("1", "0"):
+        monkeypatch.setenv("ANYSD_SHARE_CFG", share)
+        for graph in (True, False):
+            smp = DDIMSampler(model, use_cuda_graph=graph)
+            out, _ = smp.sample(5, B, (4, 16, 16), {"c_concat": [c_cat], "c_crossattn": [c_txt]}, verbose=False, x_T=x_T, eta=0.0,
+                                unconditional_guidance_scale=7.5,
+                                unconditional_conditioning={"c_concat": [c_cat], "c_crossattn": [u_txt]})
+            outs[(share, graph)] = out
+            st = next(iter(smp._graphs.values()))
+            assert st.shared == (share == "1")
+    ref = outs[("0", False)]
+    for k, v in outs.items():
+        assert torch.equal(v, ref), k
+    # different image conditioning in the two halves: sharing must stay off
+    smp = DDIMSampler(model, use_cuda_graph=False)
+    monkeypatch.setenv("ANYSD_SHARE_CFG", "1")
+    smp.sample(5, B, (4, 16, 16), {"c_concat": [c_cat], "c_crossattn": [c_txt]}, verbose=False, x_T=x_T, eta=0.0,
+               unconditional_guidance_scale=7.5, unconditional_conditioning={"c_concat": [torch.zeros_like(c_cat)], "c_crossattn": [u_txt]})
+    assert next(iter(smp._graphs.values())).shared is False
