@@ -454,6 +454,35 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const __half* __restrict__
         }
 }
 
+// ---- gather + transpose: out[ka, m] = A[m, col(ka)] (column mapping as in gemm_tn), zero for m >= M ------------------
+// Turns the small-M weight gradient dW = A^T B into two K-major operands for anysd_gemm_f16 (K = M rows).
+__global__ void __launch_bounds__(256) gather_transpose_kernel(const __half* __restrict__ A, int lda, int head_d, int head_stride,
+                                                               int group_c, int group_stride, __half* __restrict__ out, int ldo,
+                                                               int M, int Ka) {
+    __shared__ __half tile[32][34];
+    const int k0 = blockIdx.y * 32, m0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    for (int r = ty; r < 32; r += 8) {                               // r: row of A (m), tx: logical column
+        const int m = m0 + r, ka = k0 + tx;
+        __half v = __float2half(0.f);
+        if (m < M && ka < Ka) {
+            int base = 0, c = ka;
+            if (group_c > 0) {
+                base = (ka / group_c) * group_stride;
+                c = ka % group_c;
+            }
+            const int col = base + (head_d > 0 ? (c / head_d) * head_stride + c % head_d : c);
+            v = A[(size_t)m * lda + col];
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {                               // r: logical column (row of out), tx: m
+        const int ka = k0 + r, m = m0 + tx;
+        if (ka < Ka && m < ldo) out[(size_t)ka * ldo + m] = tile[tx][r];
+    }
+}
+
 // ---- router backward (restated spec, oracle/anysd_oracle.py): g = softmax(W te + b) per (sample, layer) -----------
 // dlogit = g * (dg - sum_e g dg);  dW[l] += dlogit^T te;  db[l] += sum_n dlogit;  dte[n] += sum_l dlogit W[l]
 // grid = L, block = 256.  gates / dgates [N, L, E] fp32; te [N, D] fp32 (gathered task embeddings); W [L, E, D] fp16.
@@ -638,6 +667,16 @@ int anysd_gemm_tn_f32(const void* A, int lda, int head_d, int head_stride, int g
                                                                                      group_stride, (const __half*)B, ldb, out, ldo, M, Ka,
                                                                                      Kb, alpha, accumulate);
     return check_launch("gemm_tn");
+}
+
+int anysd_gather_transpose_f16(const void* A, int lda, int head_d, int head_stride, int group_c, int group_stride, void* out, int ldo,
+                               int M, int Ka, anysd_stream_t stream) {
+    ANYSD_REQUIRE(A && out && M > 0 && Ka > 0 && lda > 0 && ldo >= M, ANYSD_EINVAL, "gather_transpose: bad args");
+    ANYSD_REQUIRE(head_d == 0 || (head_d > 0 && head_stride >= head_d), ANYSD_EINVAL, "gather_transpose: bad head mapping");
+    ANYSD_REQUIRE(group_c >= 0 && (group_c == 0 || group_stride > 0), ANYSD_EINVAL, "gather_transpose: bad group mapping");
+    gather_transpose_kernel<<<dim3(cdiv(ldo, 32), cdiv(Ka, 32)), 256, 0, (cudaStream_t)stream>>>((const __half*)A, lda, head_d, head_stride,
+                                                                                              group_c, group_stride, (__half*)out, ldo, M, Ka);
+    return check_launch("gather_transpose");
 }
 
 int anysd_router_bwd_f32(const float* gates, const float* d_gates, const float* te, const void* W, int N, int L, int E, int D,

@@ -438,6 +438,14 @@ def gemm_tn(A, B, out, M, Ka, Kb, lda=None, ldb=None, alpha=1.0, accumulate=Fals
     _count()
 
 
+def gather_transpose(A, out, M, Ka, lda=None, head_d=0, head_stride=0, group_c=0, group_stride=0):
+    """out[ka, m] = A[m, col(ka)]; out fp16 [Ka, ldo >= M] (columns >= M zero-filled)."""
+    _cuda(A, out)
+    _lib.check(_lib.load().anysd_gather_transpose_f16(_ptr(A), lda if lda is not None else A.stride(0), head_d, head_stride, group_c,
+                                                      group_stride, _ptr(out), out.stride(0), M, Ka, _stream()), "gather_transpose")
+    _count()
+
+
 def router_bwd(gates, d_gates, te, W, dW, db, d_te, alpha=1.0):
     _cuda(gates, d_gates, te, W, dW, db, d_te)
     N, L, E = gates.shape

@@ -463,9 +463,17 @@ class AdapterTrainer:
                                      Cp, ld, C, Cp, 2 * Cp, Cp, qk, head_stride=hs)
             vis = st["vis"].view(N * n_vis, -1)
             gk, gv = G[f"adapter_modules.{layer}.to_k_ip.weight"], G[f"adapter_modules.{layer}.to_v_ip.weight"]
-            # dW_e = dK_e^T vis for all experts in one launch each (parameter layout: expert-major rows, un-padded heads)
-            ops.gemm_tn(dekv, vis, gk, N * n_vis, E * C, vis.shape[1], lda=ld, head_d=d, head_stride=hs, group_c=C, group_stride=2 * Cp)
-            ops.gemm_tn(dekv[:, Cp:], vis, gv, N * n_vis, E * C, vis.shape[1], lda=ld, head_d=d, head_stride=hs, group_c=C, group_stride=2 * Cp)
+            # dW = dK^T vis for all experts of the layer (parameter layout: expert-major rows, un-padded heads) on the tensor
+            # cores: both operands transposed to K-major (K = the few visual-token rows), fp32 output straight into the grad
+            Mv = N * n_vis
+            Mp = (Mv + 7) // 8 * 8
+            if "vis_t" not in st:
+                st["vis_t"] = torch.empty(vis.shape[1], Mp, dtype=torch.float16, device=dev)
+                ops.gather_transpose(vis, st["vis_t"], Mv, vis.shape[1])
+            for off, gw in ((0, gk), (Cp, gv)):
+                at = torch.empty(E * C, Mp, dtype=torch.float16, device=dev)
+                ops.gather_transpose(dekv[:, off:], at, Mv, E * C, lda=ld, head_d=d, head_stride=hs, group_c=C, group_stride=2 * Cp)
+                ops.gemm(at, st["vis_t"], gw)
             Lp = st["MP"]["layers"][layer]
             d_vis = torch.empty(N * n_vis, vis.shape[1], dtype=torch.float16, device=dev)
             ops.gemm(dekv, _memo(Lp, "kv", lambda: Lp["kv_w"].t().contiguous()), d_vis, residual=G["d_vis"])

@@ -261,6 +261,11 @@ int anysd_gemm_tn_f32(const void* A, int lda, int head_d, int head_stride, int g
                       int ldb, float* out, int ldo, int M, int Ka, int Kb, float alpha, int accumulate,
                       anysd_stream_t stream);
 
+/* out[ka, m] = A[m, col(ka)] (fp16, column mapping as above), columns m in [M, ldo) zero: the K-major operand that lets
+ * anysd_gemm_f16 compute the same weight gradient on the tensor cores (K = ldo >= M, a multiple of 8). */
+int anysd_gather_transpose_f16(const void* A, int lda, int head_d, int head_stride, int group_c, int group_stride, void* out,
+                               int ldo, int M, int Ka, anysd_stream_t stream);
+
 /* Router backward (restated spec, oracle/anysd_oracle.py): gates = softmax(W te + b) per (sample, layer);
  * dW [L,E,D] +=, db [L,E] +=, d_te [N,D] += (atomic).  gates/d_gates fp32 [N,L,E], te fp32 [N,D], W fp16 [L,E,D]. */
 int anysd_router_bwd_f32(const float* gates, const float* d_gates, const float* te, const void* W, int N, int L, int E,

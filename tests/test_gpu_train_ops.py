@@ -253,6 +253,17 @@ def test_small_training_kernels(ops):
                 group_stride=heads * hs + 8)
     refw = A.reshape(M, heads * d).t() @ Bm
     assert rel(outg, torch.cat([refw, 2 * refw], 0)) < 1e-5
+    # the same gradient on the tensor cores: gather + transpose both operands to K-major, then anysd_gemm_f16 (fp32 out)
+    Mp = (M + 7) // 8 * 8
+    At = torch.full((2 * heads * d, Mp + 8), float("nan"), dtype=torch.float16, device="cuda")[:, :Mp]     # ldo > M, strided rows
+    At = torch.empty(2 * heads * d, Mp, dtype=torch.float16, device="cuda")
+    Bt = torch.empty(Kb, Mp, dtype=torch.float16, device="cuda")
+    ops.gather_transpose(A2.half().cuda(), At, M, 2 * heads * d, head_d=d, head_stride=hs, group_c=heads * d, group_stride=heads * hs + 8)
+    ops.gather_transpose(Bm.half().cuda(), Bt, M, Kb)
+    assert torch.equal(Bt[:, :M].cpu(), Bm.half().t()) and float(Bt[:, M:].float().abs().max() if Mp > M else 0.0) == 0.0
+    outt = torch.empty(2 * heads * d, Kb, device="cuda")
+    ops.gemm(At, Bt, outt)
+    assert rel(outt, torch.cat([refw, 2 * refw], 0)) < 1e-3
     # AdamW
     p0, g0 = randn(62, 1000), randn(63, 1000) * 0.1
     p, m, v = p0.clone().cuda(), torch.zeros(1000, device="cuda"), torch.zeros(1000, device="cuda")
