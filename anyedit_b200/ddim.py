@@ -403,9 +403,13 @@ class _Stepper:
         self.n_eager = 0
         self.unet = _find_unet(sampler.model)
         self.shared = bool(use_cfg and self.unet is not None and _halves_share_prefix(uncond, cond))
+        # cross-attention K/V of the (static) conditioning: projected once per sampling run, not once per step
+        self.kv = {"mode": "fill", "bufs": []} if self.unet is not None and os.environ.get("ANYSD_CTX_KV", "1")[:1] != "0" else None
+        self.kv_dirty = True
 
     def rebind(self, cond, uncond):
         _tree_copy_(self.c_in, _cat_cond(uncond, cond) if self.use_cfg else cond)
+        self.kv_dirty = True                             # new conditioning values: the kept K/V are stale
         shared = bool(self.use_cfg and self.unet is not None and _halves_share_prefix(uncond, cond))
         if shared != self.shared:
             self.shared, self.graph = shared, None       # the captured graph has the other structure: re-capture
@@ -416,13 +420,25 @@ class _Stepper:
             self.x_in[self.b:].copy_(self.x_buf)
         if self.shared:
             self.unet._shared_halves = True              # x, c_concat and t of the two halves are identical
+        if self.kv is not None:
+            self.unet._ctx_kv = self.kv
         try:
             eps = self.s.model.apply_model(self.x_in, self.t_buf, self.c_in)
         finally:
             if self.shared:
                 self.unet._shared_halves = False
+            if self.kv is not None:
+                self.unet._ctx_kv = None
         eps = eps.float().contiguous()
         ops.cfg_ddim_step(self.x_buf, eps, self.coef_buf, scale, self.use_cfg, self.x_prev, self.pred_x0, noise)
+
+    def _eager(self, scale, noise):
+        """One eager step; (re)fills the kept context K/V when the conditioning is new."""
+        if self.kv is not None:
+            self.kv["mode"] = "fill" if self.kv_dirty else "use"
+        self._body(scale, noise)
+        if self.kv is not None:
+            self.kv["mode"], self.kv_dirty = "use", False
 
     def step(self, img, index, t_value, scale, noise, coef=None):
         s = self.s
@@ -442,8 +458,8 @@ class _Stepper:
         if self.want_graph:
             # two eager warm-up steps (lazy weight packing, cuda module loading), then capture
             if self.graph is None or self.scale != scale:
-                if self.n_eager < 1:
-                    self._body(scale, nb)
+                if self.n_eager < 1 or (self.kv is not None and self.kv_dirty):
+                    self._eager(scale, nb)
                     self.n_eager += 1
                     return self.x_prev.clone(), self.pred_x0.clone()
                 g = torch.cuda.CUDAGraph()
@@ -454,8 +470,11 @@ class _Stepper:
                 self.graph_launches = ops.launch_count - n0    # kernels recorded into the graph
                 ops.launch_count = n0
                 self.graph, self.scale = g, scale
+            elif self.kv is not None and self.kv_dirty:      # re-bound to new conditioning: this step runs eagerly and
+                self._eager(scale, nb)                       # refills the K/V buffers the captured graph reads
+                return self.x_prev.clone(), self.pred_x0.clone()
             self.graph.replay()
             ops.launch_count += self.graph_launches
         else:
-            self._body(scale, nb)
+            self._eager(scale, nb)
         return self.x_prev.clone(), self.pred_x0.clone()

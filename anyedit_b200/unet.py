@@ -505,7 +505,8 @@ class UNetModel(nn.Module):
                 t = torch.empty(c32.shape, **f16)
                 ops.cast_f16(c32, t)
                 ctx16.append(t)
-        st = {"N": N, "ws": ws, "emb_all": emb_all, "ctx": ctx16, "anysd": anysd, "layer": 0}
+        st = {"N": N, "ws": ws, "emb_all": emb_all, "ctx": ctx16, "anysd": anysd, "layer": 0, "xl": 0,
+              "kvc": getattr(self, "_ctx_kv", None) if anysd is None else None}
 
         # -- input conv --
         # Shared CFG halves (set by the DDIM stepper when x, c_concat, t and y of the uncond / cond halves are
@@ -621,8 +622,18 @@ class UNetModel(nn.Module):
             else:
                 q = torch.empty(N * n_q, Cp, dtype=torch.float16, device=dev)
                 ops.gemm(xq, ad["q_w"], q)
-            kv = torch.empty(N * L, 2 * Cp, dtype=torch.float16, device=dev)
-            ops.gemm(ctx.view(N * L, -1), ad["kv_w"], kv, bias=ad["kv_b"])
+            # context K/V: constant over the steps of one sampling run, so the DDIM stepper keeps them (st["kvc"]:
+            # mode "fill" computes into persistent buffers, mode "use" skips the projection)
+            kvc, xl = st.get("kvc"), st.get("xl", 0)
+            if kvc is not None and kvc["mode"] == "use":
+                kv = kvc["bufs"][xl]
+            else:
+                have = kvc is not None and len(kvc["bufs"]) > xl
+                kv = kvc["bufs"][xl] if have else torch.empty(N * L, 2 * Cp, dtype=torch.float16, device=dev)
+                ops.gemm(ctx.view(N * L, -1), ad["kv_w"], kv, bias=ad["kv_b"])
+                if kvc is not None and not have:
+                    kvc["bufs"].append(kv)
+            st["xl"] = xl + 1
             ops.attention(q, kv, kv[:, Cp:], a, N, ad["heads"], n_q, L, ad["d"], Cp, 2 * Cp, 2 * Cp, C, head_stride=hs,
                           aux_cols=ad["aux"])
             if expert and st["anysd"] is not None and st["anysd"].get("experts") is not None:

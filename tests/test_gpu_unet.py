@@ -434,3 +434,36 @@ def test_shared_cfg_halves_bit_identical(monkeypatch):
     smp.sample(5, B, (4, 16, 16), {"c_concat": [c_cat], "c_crossattn": [c_txt]}, verbose=False, x_T=x_T, eta=0.0,
                unconditional_guidance_scale=7.5, unconditional_conditioning={"c_concat": [torch.zeros_like(c_cat)], "c_crossattn": [u_txt]})
     assert next(iter(smp._graphs.values())).shared is False
+
+
+def test_kept_context_kv_across_steps(monkeypatch):
+    """The cross-attention K/V of the conditioning are projected once per sampling run (the context does not change
+    between steps): same bits as projecting them every step, graph and eager, and a cached stepper re-bound to NEW
+    conditioning refills them (no stale K/V)."""
+    from anyedit_b200.ddim import DDIMSampler
+    net, _, _ = _build("tiny_a", 11)
+    model = _denoiser(net)
+    gen = torch.Generator().manual_seed(91)
+    B = 2
+    x_T, c_cat = torch.randn(B, 4, 16, 16, generator=gen).cuda(), torch.randn(B, 4, 16, 16, generator=gen).cuda()
+    txt = [torch.randn(B, 7, 64, generator=gen).cuda() for _ in range(3)]
+
+    def run(smp, c_txt, u_txt):
+        out, _ = smp.sample(5, B, (4, 16, 16), {"c_concat": [c_cat], "c_crossattn": [c_txt]}, verbose=False, x_T=x_T, eta=0.0,
+                            unconditional_guidance_scale=5.0, unconditional_conditioning={"c_concat": [c_cat], "c_crossattn": [u_txt]})
+        return out
+
+    monkeypatch.setenv("ANYSD_CTX_KV", "0")
+    ref_a = run(DDIMSampler(model, use_cuda_graph=False), txt[0], txt[2])
+    ref_b = run(DDIMSampler(model, use_cuda_graph=False), txt[1], txt[2])
+    assert not torch.equal(ref_a, ref_b)
+    monkeypatch.setenv("ANYSD_CTX_KV", "1")
+    for graph in (True, False):
+        smp = DDIMSampler(model, use_cuda_graph=graph)
+        assert torch.equal(run(smp, txt[0], txt[2]), ref_a), graph
+        st = next(iter(smp._graphs.values()))
+        assert st.kv is not None and len(st.kv["bufs"]) > 0 and not st.kv_dirty
+        n_bufs = len(st.kv["bufs"])
+        assert torch.equal(run(smp, txt[1], txt[2]), ref_b), graph          # same stepper, new conditioning values
+        assert next(iter(smp._graphs.values())) is st and len(st.kv["bufs"]) == n_bufs
+        assert torch.equal(run(smp, txt[0], txt[2]), ref_a), graph
