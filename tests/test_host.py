@@ -242,3 +242,21 @@ def test_training_host_logic():
     z = torch.zeros(1, 4, 16, 16)
     with pytest.raises(RuntimeError):
         tr.loss_and_grads(z, z, torch.zeros(1, dtype=torch.long), z, torch.zeros(1, 7, 64))
+
+
+def test_cfg_halves_sharing_decision(monkeypatch):
+    """Host logic of the shared-CFG-halves optimisation (ddim.py:190-210 batch construction): only when the two halves
+    can differ in nothing but the cross-attention context."""
+    from anyedit_b200.ddim import _halves_share_prefix
+    monkeypatch.delenv("ANYSD_SHARE_CFG", raising=False)
+    cc, txt, utxt = torch.randn(2, 4, 8, 8), torch.randn(2, 7, 16), torch.randn(2, 7, 16)
+    c = {"c_concat": [cc], "c_crossattn": [txt]}
+    assert _halves_share_prefix({"c_concat": [cc], "c_crossattn": [utxt]}, c)                      # same tensor object
+    assert _halves_share_prefix({"c_concat": [cc.clone()], "c_crossattn": [utxt]}, c)              # equal values
+    assert not _halves_share_prefix({"c_concat": [torch.zeros_like(cc)], "c_crossattn": [utxt]}, c)  # IP2P-style zero image
+    assert not _halves_share_prefix({"c_concat": [cc], "c_crossattn": [utxt], "c_adm": torch.zeros(2)},
+                                    {**c, "c_adm": torch.ones(2)})
+    assert not _halves_share_prefix([utxt], [txt])                                                 # list conditioning: no claim
+    assert _halves_share_prefix({"c_crossattn": [utxt]}, {"c_crossattn": [txt]})                   # pure cross-attention model
+    monkeypatch.setenv("ANYSD_SHARE_CFG", "0")
+    assert not _halves_share_prefix({"c_concat": [cc], "c_crossattn": [utxt]}, c)
