@@ -126,6 +126,33 @@ __global__ void cfg_ddim_kernel(const float4* __restrict__ x, const float4* __re
     }
 }
 
+// ---- InstructPix2Pix three-way guidance + DDIM update (tools/global_tool.py:166-177) ----------------------------
+// eps = [text ; image ; uncond] thirds:  e = e_unc + s_txt (e_txt - e_img) + s_img (e_img - e_unc), then the same
+// update as above; same evaluation order and _rn intrinsics as the reference's fp32 tensor expression.
+__global__ void cfg3_ddim_kernel(const float4* __restrict__ x, const float4* __restrict__ eps, const float4* __restrict__ noise,
+                                 const float* __restrict__ coef, float s_txt, float s_img, float4* __restrict__ x_prev,
+                                 float4* __restrict__ pred_x0, long long n4) {
+    const float c_somat = coef[0], c_sqrt_at = coef[1], c_sqrt_aprev = coef[2], c_dir = coef[3], c_sigma = coef[4];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 xv = x[i], et = eps[i], ei = eps[i + n4], eu = eps[i + 2 * n4];
+        const float4 nz = (noise != nullptr) ? noise[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 p0, o;
+#define ANYSD_DDIM3_LANE(f)                                                                                       \
+        {                                                                                                             \
+            float e = __fadd_rn(__fadd_rn(eu.f, __fmul_rn(s_txt, __fsub_rn(et.f, ei.f))), __fmul_rn(s_img, __fsub_rn(ei.f, eu.f))); \
+            float p = __fdiv_rn(__fsub_rn(xv.f, __fmul_rn(c_somat, e)), c_sqrt_at);                                   \
+            float r = __fadd_rn(__fmul_rn(c_sqrt_aprev, p), __fmul_rn(c_dir, e));                                     \
+            if (noise != nullptr) r = __fadd_rn(r, __fmul_rn(c_sigma, nz.f));                                         \
+            p0.f = p;                                                                                                 \
+            o.f = r;                                                                                                  \
+        }
+        ANYSD_DDIM3_LANE(x) ANYSD_DDIM3_LANE(y) ANYSD_DDIM3_LANE(z) ANYSD_DDIM3_LANE(w)
+#undef ANYSD_DDIM3_LANE
+        x_prev[i] = o;
+        if (pred_x0 != nullptr) pred_x0[i] = p0;
+    }
+}
+
 // ---- task router gate (AnySD restatement, oracle/anysd_oracle.py): -------------------------------
 // gate[b, l, :] = softmax_e(W[l, e, :] . table[idx[b], :] + bias[l, e]); one CTA per (layer, sample),
 // one warp per expert logit: 16-byte weight loads, warp-shuffle dot-product reduction, fp32 softmax.
@@ -275,6 +302,19 @@ int anysd_cfg_ddim_step_f32(const float* x, const float* eps, const float* noise
                                                             (const float4*)noise, coef, guidance_scale, cfg,
                                                             (float4*)x_prev, (float4*)pred_x0, n4, n4);
     return check_launch("cfg_ddim_step");
+}
+
+int anysd_cfg3_ddim_step_f32(const float* x, const float* eps, const float* noise, const float* coef, float text_scale,
+                             float image_scale, float* x_prev, float* pred_x0, long long n_per_batch, int B, anysd_stream_t stream) {
+    ANYSD_REQUIRE(x && eps && coef && x_prev && B > 0 && n_per_batch > 0, ANYSD_EINVAL, "cfg3_ddim_step: bad args");
+    long long total = n_per_batch * B;
+    ANYSD_REQUIRE(total % 4 == 0, ANYSD_EINVAL, "cfg3_ddim_step: B*C*H*W must be a multiple of 4");
+    long long n4 = total / 4;
+    int grid = (int)((n4 + 255) / 256);
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
+    cfg3_ddim_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)eps, (const float4*)noise, coef, text_scale,
+                                                            image_scale, (float4*)x_prev, (float4*)pred_x0, n4);
+    return check_launch("cfg3_ddim_step");
 }
 
 int anysd_router_gate_f32(const float* table, const long long* idx, int table_rows, const void* W, const float* bias,

@@ -70,20 +70,21 @@ class DDIMSampler(object):
         self.use_cuda_graph = kwargs.get("use_cuda_graph", True)
         self._graphs = {}
 
-    def _get_stepper(self, cond, uncond, use_cfg, b, shape, device, graph):
+    def _get_stepper(self, cond, uncond, use_cfg, b, shape, device, graph, img_cond=None, img_scale=None):
         """One stepper (static buffers + captured CUDA graph) per request geometry, reused across ``sample``
         calls: a serving loop captures once and only rebinds conditioning values afterwards."""
         gk = getattr(self.model, "graph_key", None)      # changes whenever the model's packed weights change
         key = (b, tuple(shape), bool(use_cfg), bool(graph), str(device), _tree_sig(cond),
-               _tree_sig(uncond) if use_cfg else None, gk() if callable(gk) else gk)
+               _tree_sig(uncond) if use_cfg else None, gk() if callable(gk) else gk,
+               None if img_cond is None else (_tree_sig(img_cond), float(img_scale)))
         st = self._graphs.get(key)
         if st is None:
             if len(self._graphs) >= 4:
                 self._graphs.pop(next(iter(self._graphs)))
-            st = _Stepper(self, cond, uncond, use_cfg, b, shape, device, graph)
+            st = _Stepper(self, cond, uncond, use_cfg, b, shape, device, graph, img_cond=img_cond, img_scale=img_scale)
             self._graphs[key] = st
         else:
-            st.rebind(cond, uncond)
+            st.rebind(cond, uncond, img_cond)
         return st
 
     def register_buffer(self, name, attr):
@@ -151,7 +152,9 @@ class DDIMSampler(object):
                                   log_every_t=log_every_t,
                                   unconditional_guidance_scale=unconditional_guidance_scale,
                                   unconditional_conditioning=unconditional_conditioning,
-                                  dynamic_threshold=dynamic_threshold, ucg_schedule=ucg_schedule)
+                                  dynamic_threshold=dynamic_threshold, ucg_schedule=ucg_schedule,
+                                  image_guidance_scale=kwargs.get("image_guidance_scale"),
+                                  image_conditioning=kwargs.get("image_conditioning"))
 
     # ---- the loop (ddim.py:122-178) ------------------------------------------------------------------
     @torch.no_grad()
@@ -159,7 +162,10 @@ class DDIMSampler(object):
                       quantize_denoised=False, mask=None, x0=None, img_callback=None, log_every_t=100,
                       temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
                       unconditional_guidance_scale=1., unconditional_conditioning=None, dynamic_threshold=None,
-                      ucg_schedule=None):
+                      ucg_schedule=None, image_guidance_scale=None, image_conditioning=None):
+        """``image_guidance_scale`` + ``image_conditioning`` (extension): InstructPix2Pix three-way
+        guidance of tools/global_tool.py:166-177 -- the batch is [cond (text + image) ; image_conditioning (null text +
+        image) ; unconditional_conditioning (null text + zero image)], ``unconditional_guidance_scale`` is the text scale."""
         if ddim_use_original_steps:
             raise NotImplementedError("ddim_use_original_steps (1000-step DDPM-grid sampling) is not on the AnySD path")
         if quantize_denoised or score_corrector is not None or noise_dropout > 0.:
@@ -183,10 +189,15 @@ class DDIMSampler(object):
         if ucg_schedule is not None:
             assert len(ucg_schedule) == len(time_range)
         use_cfg = not (unconditional_conditioning is None or unconditional_guidance_scale == 1.)
+        three = image_conditioning is not None and image_guidance_scale is not None
+        if three:
+            assert unconditional_conditioning is not None, "three-way guidance needs the unconditional conditioning too"
+            use_cfg = True
         sigma_nonzero = bool(np.any(np.asarray(self.ddim_sigmas[:total_steps]) != 0))
 
         stepper = self._get_stepper(cond, unconditional_conditioning, use_cfg, b, tuple(shape), device,
-                                    graph=self.use_cuda_graph and ucg_schedule is None)
+                                    graph=self.use_cuda_graph and ucg_schedule is None,
+                                    img_cond=image_conditioning if three else None, img_scale=image_guidance_scale if three else None)
         for i, step in enumerate(time_range):
             index = total_steps - i - 1
             if mask is not None:
@@ -381,15 +392,17 @@ class _Stepper:
     ``graph=True`` the step is captured into a CUDA graph on first use and replayed afterwards;
     the per-step timestep and coefficients live in device buffers refreshed by tiny async copies."""
 
-    def __init__(self, sampler, cond, uncond, use_cfg, b, shape, device, graph):
+    def __init__(self, sampler, cond, uncond, use_cfg, b, shape, device, graph, img_cond=None, img_scale=None):
         self.s = sampler
         self.use_cfg = use_cfg
+        self.three = img_cond is not None            # [text ; image ; uncond] batch, InstructPix2Pix guidance
+        self.img_scale = img_scale
         self.b = b
         self.device = device
         # static copy of the (CFG-batched) conditioning: a cached stepper / captured graph is re-bound to new
         # requests by copying values into these tensors (rebind), never by re-capturing
-        self.c_in = _tree_clone(_cat_cond(uncond, cond) if use_cfg else cond)
-        nb = 2 * b if use_cfg else b
+        self.c_in = _tree_clone(self._batch_cond(cond, uncond, img_cond))
+        nb = 3 * b if self.three else (2 * b if use_cfg else b)
         self.t_buf = torch.zeros(nb, dtype=torch.long, device=device)
         self.coef_buf = torch.zeros(5, dtype=torch.float32, device=device)
         self.x_buf = torch.zeros(shape, dtype=torch.float32, device=device)
@@ -402,22 +415,27 @@ class _Stepper:
         self.scale = None
         self.n_eager = 0
         self.unet = _find_unet(sampler.model)
-        self.shared = bool(use_cfg and self.unet is not None and _halves_share_prefix(uncond, cond))
+        self.shared = bool(use_cfg and not self.three and self.unet is not None and _halves_share_prefix(uncond, cond))
         # cross-attention K/V of the (static) conditioning: projected once per sampling run, not once per step
         self.kv = {"mode": "fill", "bufs": []} if self.unet is not None and os.environ.get("ANYSD_CTX_KV", "1")[:1] != "0" else None
         self.kv_dirty = True
 
-    def rebind(self, cond, uncond):
-        _tree_copy_(self.c_in, _cat_cond(uncond, cond) if self.use_cfg else cond)
+    def _batch_cond(self, cond, uncond, img_cond):
+        if self.three:
+            return _cat_cond(_cat_cond(cond, img_cond), uncond)     # [text ; image ; uncond] (global_tool.py:160, 173)
+        return _cat_cond(uncond, cond) if self.use_cfg else cond
+
+    def rebind(self, cond, uncond, img_cond=None):
+        _tree_copy_(self.c_in, self._batch_cond(cond, uncond, img_cond))
         self.kv_dirty = True                             # new conditioning values: the kept K/V are stale
-        shared = bool(self.use_cfg and self.unet is not None and _halves_share_prefix(uncond, cond))
+        shared = bool(self.use_cfg and not self.three and self.unet is not None and _halves_share_prefix(uncond, cond))
         if shared != self.shared:
             self.shared, self.graph = shared, None       # the captured graph has the other structure: re-capture
 
     def _body(self, scale, noise):
         if self.use_cfg:
-            self.x_in[: self.b].copy_(self.x_buf)
-            self.x_in[self.b:].copy_(self.x_buf)
+            for k in range(3 if self.three else 2):
+                self.x_in[k * self.b:(k + 1) * self.b].copy_(self.x_buf)
         if self.shared:
             self.unet._shared_halves = True              # x, c_concat and t of the two halves are identical
         if self.kv is not None:
@@ -430,7 +448,10 @@ class _Stepper:
             if self.kv is not None:
                 self.unet._ctx_kv = None
         eps = eps.float().contiguous()
-        ops.cfg_ddim_step(self.x_buf, eps, self.coef_buf, scale, self.use_cfg, self.x_prev, self.pred_x0, noise)
+        if self.three:
+            ops.cfg3_ddim_step(self.x_buf, eps, self.coef_buf, scale, self.img_scale, self.x_prev, self.pred_x0, noise)
+        else:
+            ops.cfg_ddim_step(self.x_buf, eps, self.coef_buf, scale, self.use_cfg, self.x_prev, self.pred_x0, noise)
 
     def _eager(self, scale, noise):
         """One eager step; (re)fills the kept context K/V when the conditioning is new."""
@@ -445,7 +466,7 @@ class _Stepper:
         self.x_buf.copy_(img)
         if isinstance(t_value, torch.Tensor):
             tv = t_value.to(self.device).long()
-            self.t_buf.copy_(torch.cat([tv, tv]) if self.use_cfg else tv)
+            self.t_buf.copy_(torch.cat([tv] * (3 if self.three else 2)) if self.use_cfg else tv)
         else:
             self.t_buf.fill_(int(t_value))
         self.coef_buf.copy_(s.ddim_coef[index] if coef is None else coef, non_blocking=True)
@@ -465,8 +486,23 @@ class _Stepper:
                 g = torch.cuda.CUDAGraph()
                 torch.cuda.synchronize()
                 n0 = ops.launch_count
-                with torch.cuda.graph(g):
-                    self._body(scale, nb)
+                try:
+                    # "relaxed": host-side queries the launchers make (occupancy, function attributes, tensor-map
+                    # encoding) and other threads' CUDA calls must not invalidate the capture
+                    with torch.cuda.graph(g, capture_error_mode="relaxed"):
+                        self._body(scale, nb)
+                except Exception as e:                    # capture refused / invalidated: this stepper stays eager
+                    import warnings
+                    warnings.warn(f"anyedit_b200: CUDA-graph capture of the DDIM step failed ({type(e).__name__}: "
+                                  f"{str(e).splitlines()[0][:160]}); continuing without a graph")
+                    ops.launch_count = n0
+                    self.want_graph, self.graph = False, None
+                    try:
+                        torch.cuda.synchronize()
+                    except Exception:
+                        pass
+                    self._eager(scale, nb)
+                    return self.x_prev.clone(), self.pred_x0.clone()
                 self.graph_launches = ops.launch_count - n0    # kernels recorded into the graph
                 ops.launch_count = n0
                 self.graph, self.scale = g, scale

@@ -265,6 +265,16 @@ def cfg_ddim_step(x, eps, coef, scale, cfg, x_prev, pred_x0=None, noise=None):
     _count()
 
 
+def cfg3_ddim_step(x, eps, coef, text_scale, image_scale, x_prev, pred_x0=None, noise=None):
+    """InstructPix2Pix three-way guidance (eps = [text ; image ; uncond]) + DDIM update in one kernel."""
+    _cuda(x, eps, coef, x_prev)
+    B = x.shape[0]
+    assert eps.shape[0] == 3 * B and x.dtype == torch.float32 and eps.dtype == torch.float32 and x.is_contiguous() and eps.is_contiguous()
+    _lib.check(_lib.load().anysd_cfg3_ddim_step_f32(_ptr(x), _ptr(eps), _ptr(noise), _ptr(coef), float(text_scale), float(image_scale),
+                                                    _ptr(x_prev), _ptr(pred_x0), x.numel() // B, B, _stream()), "cfg3_ddim_step")
+    _count()
+
+
 # ---- training step (SURVEY.md a24): thin wrappers, same conventions as above -------------------------------------
 def q_sample(x0, noise, t, sqrt_acp, sqrt_1m_acp, out):
     _cuda(x0, noise, t, out)

@@ -159,6 +159,12 @@ int anysd_cfg_ddim_step_f32(const float* x, const float* eps, const float* noise
                             float guidance_scale, int cfg, float* x_prev, float* pred_x0, long long n_per_batch,
                             int B, anysd_stream_t stream);
 
+/* InstructPix2Pix three-way guidance (tools/global_tool.py:166-177) + the same DDIM update:
+ * eps holds [text ; image ; uncond] (3B rows);  e = e_unc + text_scale (e_txt - e_img) + image_scale (e_img - e_unc). */
+int anysd_cfg3_ddim_step_f32(const float* x, const float* eps, const float* noise, const float* coef, float text_scale,
+                             float image_scale, float* x_prev, float* pred_x0, long long n_per_batch, int B,
+                             anysd_stream_t stream);
+
 /* ==== training step (train.py:629-710) =====================================================
  * The reference back-propagates mse_loss(MoE(...), noise) through the frozen UNet with torch autograd
  * (train.py:694-703); trainables are the adapter experts, the router and the task-embedding table

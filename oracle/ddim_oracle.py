@@ -119,7 +119,7 @@ def _cat_cond(uc, c):
 
 
 def ddim_sample(model_fn, sched, S, x_T, cond, uncond=None, scale=1.0, eta=0.0, ddpm_steps=1000,
-                mask=None, x0=None, log_every_t=100, generator=None):
+                mask=None, x0=None, log_every_t=100, generator=None, img_cond=None, img_scale=None):
     """ddim.py:23-52 + 122-178 + 181-251, eps-parameterisation.
     ``model_fn(x, t, cond) -> eps`` (the apply_model boundary).  Returns (x0_latent, intermediates)."""
     ts = make_ddim_timesteps("uniform", S, ddpm_steps)
@@ -136,7 +136,13 @@ def ddim_sample(model_fn, sched, S, x_T, cond, uncond=None, scale=1.0, eta=0.0, 
         if mask is not None:
             noise = torch.randn(x0.shape, generator=generator)
             img = q_sample(sched, x0, t, noise) * mask + (1.0 - mask) * img
-        if uncond is None or scale == 1.0:
+        if img_cond is not None:
+            # InstructPix2Pix three-way guidance, AnyEdit_Collection/adaptive_editing_pipelines/tools/global_tool.py:160-177:
+            # batch [text ; image ; uncond], e = e_unc + s_txt (e_txt - e_img) + s_img (e_img - e_unc)
+            out = model_fn(torch.cat([img] * 3), torch.cat([t] * 3), _cat_cond(_cat_cond(cond, img_cond), uncond))
+            e_txt, e_img, e_unc = out.chunk(3)
+            e_t = e_unc + scale * (e_txt - e_img) + img_scale * (e_img - e_unc)
+        elif uncond is None or scale == 1.0:
             e_t = model_fn(img, t, cond)
         else:
             out = model_fn(torch.cat([img] * 2), torch.cat([t] * 2), _cat_cond(uncond, cond))

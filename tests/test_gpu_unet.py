@@ -467,3 +467,44 @@ def test_kept_context_kv_across_steps(monkeypatch):
         assert torch.equal(run(smp, txt[1], txt[2]), ref_b), graph          # same stepper, new conditioning values
         assert next(iter(smp._graphs.values())) is st and len(st.kv["bufs"]) == n_bufs
         assert torch.equal(run(smp, txt[0], txt[2]), ref_a), graph
+
+
+def test_three_way_ip2p_guidance():
+    """SURVEY.md 8f rank 4 on the sampler boundary: InstructPix2Pix three-way guidance (tools/global_tool.py:160-177),
+    batch [text ; image ; uncond], fused into the DDIM update kernel: the kernel bit-exact vs the fp32 tensor expression,
+    a 10-step run vs the oracle loop."""
+    from anyedit_b200 import ops
+    from anyedit_b200.ddim import DDIMSampler
+    from oracle import ddim_oracle, unet_oracle
+    gen = torch.Generator().manual_seed(123)
+    B = 2
+    x, eps = torch.randn(B, 4, 16, 16, generator=gen), torch.randn(3 * B, 4, 16, 16, generator=gen)
+    coef = torch.tensor([0.6, 0.8, 0.9, 0.3, 0.0])
+    xp, p0 = torch.empty(B, 4, 16, 16, device="cuda"), torch.empty(B, 4, 16, 16, device="cuda")
+    ops.cfg3_ddim_step(x.cuda(), eps.cuda(), coef.cuda(), 7.5, 1.5, xp, p0)
+    et, ei, eu = eps.chunk(3)
+    e = eu + 7.5 * (et - ei) + 1.5 * (ei - eu)
+    pred = (x - coef[0] * e) / coef[1]
+    assert torch.equal(p0.cpu(), pred) and torch.equal(xp.cpu(), coef[2] * pred + coef[3] * e)
+    net, sd, cfg = _build("tiny_a", 11)
+    model = _denoiser(net)
+    x_T, lat = torch.randn(B, 4, 16, 16, generator=gen), torch.randn(B, 4, 16, 16, generator=gen)
+    txt, null = torch.randn(B, 7, 64, generator=gen), torch.randn(1, 7, 64, generator=gen).repeat(B, 1, 1)
+    cond = {"c_concat": [lat], "c_crossattn": [txt]}
+    icond = {"c_concat": [lat], "c_crossattn": [null]}
+    ucond = {"c_concat": [torch.zeros_like(lat)], "c_crossattn": [null]}
+    cu = lambda d: {k: [t.cuda() for t in v] for k, v in d.items()}
+    outs = []
+    for graph in (True, False):
+        out, _ = DDIMSampler(model, use_cuda_graph=graph).sample(10, B, (4, 16, 16), cu(cond), verbose=False, x_T=x_T.cuda(), eta=0.0,
+                                                                 unconditional_guidance_scale=7.5, unconditional_conditioning=cu(ucond),
+                                                                 image_guidance_scale=1.5, image_conditioning=cu(icond))
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    sched = ddim_oracle.register_schedule("linear", 1000, 0.00085, 0.012)
+    unet = lambda xx, tt, context=None, y=None: unet_oracle.unet_forward(sd, xx, tt, context, y, num_heads=cfg["num_heads"])
+    model_fn = lambda xx, tt, c: ddim_oracle.apply_model(unet, "hybrid", xx, tt, c)
+    ref, _ = ddim_oracle.ddim_sample(model_fn, sched, 10, x_T, cond, ucond, 7.5, eta=0.0, img_cond=icond, img_scale=1.5)
+    e = rel(outs[0], ref)
+    print(f"[three-way IP2P guidance, 10 steps] final-latent rel-L2 vs oracle = {e:.3e}")
+    assert e < LATENT_TOL_CFG, e
