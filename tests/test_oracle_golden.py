@@ -142,3 +142,20 @@ def test_adamw_restatement_matches_torch():
         opt.step()
         q, m, v = train_oracle.adamw_step(q, gr, m, v, i, 1e-3, 0.9, 0.999, 1e-8, 1e-2)
         assert torch.allclose(q, p.detach(), rtol=1e-6, atol=1e-7), i
+
+
+def test_vae_oracle_golden():
+    """Groundwork for the next scope row: the autoencoder restatement against the reference's own
+    Encoder / Decoder (tests/golden/make_golden_vae.py): encode -> moments and decode, non-square input."""
+    from oracle import vae_oracle
+    g = _load("vae_tiny.npz")
+    meta = _keys("vae_tiny_keys.json")
+    sd = weights.make_state_dict({k: tuple(v) for k, v in meta["keys"].items()}, int(g["seed"]))
+    assert weights.checksum(sd) == pytest.approx(float(g["wsum"]), rel=1e-12)
+    mom = vae_oracle.vae_encode_moments(sd, torch.from_numpy(g["x"]))
+    img = vae_oracle.vae_decode(sd, torch.from_numpy(g["z"]))
+    assert tuple(mom.shape) == g["moments"].shape and tuple(img.shape) == g["img"].shape
+    for got, ref in ((mom, g["moments"]), (img, g["img"])):
+        ref = torch.from_numpy(ref)
+        assert ref.abs().max() > 1e-2
+        assert float((got - ref).norm() / ref.norm()) < 2e-6
