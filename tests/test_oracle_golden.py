@@ -179,3 +179,22 @@ def test_plms_oracle_golden():
         for got, key in ((img, f"x0_S{S}"), (inter["pred_x0"][-1], f"pred_x0_last_S{S}")):
             ref = torch.from_numpy(g[key])
             assert float((got - ref).norm() / ref.norm()) < 1e-5, (S, key)
+
+
+def test_dpm_solver_oracle_golden():
+    """Groundwork for the next scope row: DPM-Solver++(2M) as the reference configures it
+    (tests/golden/make_golden_dpm.py): 10 steps with CFG 5.0 (order-1 final step) and 20 steps without guidance."""
+    from oracle import dpm_oracle
+    g = _load("dpm_tiny.npz")
+    meta = _keys("tiny_c_keys.json")
+    sd = weights.make_state_dict({k: tuple(v) for k, v in meta["keys"].items()}, int(g["seed"]))
+    assert weights.checksum(sd) == pytest.approx(float(g["wsum"]), rel=1e-12)
+    cfg = meta["config"]
+    sched = ddim_oracle.register_schedule("linear", 1000, 0.00085, 0.012)
+    fn = lambda x, t, c: unet_oracle.unet_forward(sd, x, t, c, None, num_heads=cfg.get("num_heads", -1),
+                                                  num_head_channels=cfg.get("num_head_channels", -1))
+    x_T, c, uc = (torch.from_numpy(g[k]) for k in ("x_T", "c", "uc"))
+    for S, scale in ((10, 5.0), (20, 1.0)):
+        img = dpm_oracle.dpm_solver_pp_2m(fn, sched["alphas_cumprod"], S, x_T, c, uc, scale)
+        ref = torch.from_numpy(g[f"x0_S{S}"])
+        assert float((img - ref).norm() / ref.norm()) < 2e-5, S
