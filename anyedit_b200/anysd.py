@@ -23,6 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .diffusion import LatentDenoiser
 from .unet import UNetModel, _Param, aux_bias, aux_cols_for, head_stride_for, pad_heads
 
 
@@ -68,13 +69,13 @@ class MoE(nn.Module):
                         self._site_heads.append((m.heads, m.d_head))
         self.adapter_modules = nn.ModuleList([_Adapter(c, ctx_dim, expert_num, d_emb) for c in sites])
         self.image_proj_model = nn.Identity()
-        self._pack, self._pack_key = None, None
+        self._pack, self._pack_key, self._epoch = None, None, 0
         if ckpt_path is not None:
             self.load_state_dict(torch.load(ckpt_path, map_location="cpu"), strict=False)
 
     def _prepare(self, dev):
         key = (str(dev), sum(p._version for p in self.task_embs.parameters()) +
-               sum(p._version for p in self.adapter_modules.parameters()))
+               sum(p._version for p in self.adapter_modules.parameters()), self._epoch)
         if self._pack is not None and self._pack_key == key:
             return self._pack
         E = self.expert_num
@@ -139,8 +140,52 @@ class MoE(nn.Module):
             hook["experts"] = experts
         return self.unet(noisy_latents, timesteps, context=encoder_hidden_states, anysd=hook)
 
+    def invalidate(self, unet=False):
+        """Drop the packed adapter / router / task tensors (after an in-place weight change that does not bump parameter
+        versions: the raw AdamW kernel, a ``.data`` broadcast); ``unet=True`` also drops the frozen UNet's packs."""
+        self._pack = None
+        self._epoch += 1
+        if unet:
+            self.unet.invalidate()
+
     def save_pretrained(self, path):
         import os
         os.makedirs(path, exist_ok=True)
         sd = {k: v for k, v in self.state_dict().items() if not k.startswith("unet.")}
         torch.save(sd, os.path.join(path, "anysd_adapter.pt"))
+
+
+class AnySDDenoiser(LatentDenoiser):
+    """The ``apply_model`` boundary (ddpm.py:854-869) for the AnySD ``MoE``: what a sampler drives when the task
+    router, the task-embedding add and the visual expert stream are active (BASELINE configs[2] / configs[3]).
+
+    ``cond`` is the ``hybrid`` dict of ``DiffusionWrapper.forward`` (ddpm.py:1344-1347) plus two optional AnySD keys,
+    batched and CFG-concatenated by the samplers exactly like the others:
+      ``c_task``    int64 [B] edit codes                (train.py:695 ``batch["edit_code"]``)
+      ``c_visual``  list of [B, N_vis, context_dim] visual tokens, concatenated along tokens (train.py:688-694)
+    """
+
+    def __init__(self, moe: "MoE", **schedule_kwargs):
+        assert isinstance(moe, MoE)
+        super().__init__(moe.unet, "hybrid", **schedule_kwargs)
+        self.moe = moe
+
+    @property
+    def graph_safe(self):
+        return True
+
+    def graph_key(self):
+        ps = list(self.moe.unet.parameters()) + list(self.moe.task_embs.parameters()) + list(self.moe.adapter_modules.parameters())
+        return (tuple((str(p.device), p._version, p.data_ptr()) for p in ps).__hash__(), self.moe._epoch, self.moe.unet._epoch)
+
+    def invalidate(self):
+        self.moe.invalidate(unet=True)
+
+    def apply_model(self, x_noisy, t, cond, return_ids=False):
+        assert isinstance(cond, dict), "AnySDDenoiser takes the hybrid conditioning dict"
+        xc = torch.cat([x_noisy] + list(cond.get("c_concat") or []), dim=1)
+        cc = torch.cat(cond["c_crossattn"], 1)
+        vis = cond.get("c_visual")
+        if isinstance(vis, (list, tuple)):
+            vis = torch.cat(vis, 1) if len(vis) else None
+        return self.moe(xc, t, cc, vis, cond.get("c_task"))

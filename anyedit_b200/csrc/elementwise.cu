@@ -98,10 +98,13 @@ __global__ void emb_finalize_kernel(const float* __restrict__ emb_lin, const flo
 
 // ---- CFG combine + DDIM update (ddim.py:211-212, 228-250) -------------------------------------
 __global__ void cfg_ddim_kernel(const float4* __restrict__ x, const float4* __restrict__ eps,
-                                const float4* __restrict__ noise, const float* __restrict__ coef, float scale, int cfg,
+                                const float4* __restrict__ noise, const float* __restrict__ coef, float scale, int cfg, int vparam,
                                 float4* __restrict__ x_prev, float4* __restrict__ pred_x0, long long n4_total,
                                 long long n4_half) {
     const float c_somat = coef[0], c_sqrt_at = coef[1], c_sqrt_aprev = coef[2], c_dir = coef[3], c_sigma = coef[4];
+    // v-parameterisation (ddim.py:214-218, 224-226; ddpm.py predict_eps_from_z_and_v / predict_start_from_z_and_v):
+    // coef[5] = sqrt(acp[t]), coef[6] = sqrt(1 - acp[t]) of the DDPM timestep t the model was called with
+    const float c_sacp = vparam ? coef[5] : 0.f, c_s1m = vparam ? coef[6] : 0.f;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4_total;
          i += (long long)gridDim.x * blockDim.x) {
         float4 xv = x[i];
@@ -113,7 +116,14 @@ __global__ void cfg_ddim_kernel(const float4* __restrict__ x, const float4* __re
 #define ANYSD_DDIM_LANE(f)                                                                          \
         {                                                                                               \
             float e = cfg ? __fadd_rn(eu.f, __fmul_rn(scale, __fsub_rn(ec.f, eu.f))) : eu.f;            \
-            float p = __fdiv_rn(__fsub_rn(xv.f, __fmul_rn(c_somat, e)), c_sqrt_at);                     \
+            float p;                                                                                    \
+            if (vparam) {                                                                               \
+                const float v = e;                                                                      \
+                e = __fadd_rn(__fmul_rn(c_sacp, v), __fmul_rn(c_s1m, xv.f));                            \
+                p = __fsub_rn(__fmul_rn(c_sacp, xv.f), __fmul_rn(c_s1m, v));                            \
+            } else {                                                                                    \
+                p = __fdiv_rn(__fsub_rn(xv.f, __fmul_rn(c_somat, e)), c_sqrt_at);                       \
+            }                                                                                           \
             float r = __fadd_rn(__fmul_rn(c_sqrt_aprev, p), __fmul_rn(c_dir, e));                       \
             if (noise != nullptr) r = __fadd_rn(r, __fmul_rn(c_sigma, nz.f));                           \
             p0.f = p;                                                                                   \
@@ -150,6 +160,76 @@ __global__ void cfg3_ddim_kernel(const float4* __restrict__ x, const float4* __r
 #undef ANYSD_DDIM3_LANE
         x_prev[i] = o;
         if (pred_x0 != nullptr) pred_x0[i] = p0;
+    }
+}
+
+// ---- PLMS step (ldm/models/diffusion/plms.py:178-244): CFG combine + linear-multistep eps + DDIM update ----------
+// coef[10] = {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev), c0, c1, c2, c3, den, push}:
+//   e' = (((c0 e - c1 o1) + c2 o2) - c3 o3) / den       the reference's left-to-right evaluation of
+//        (3e - o1)/2, (23e - 16 o1 + 5 o2)/12, (55e - 59 o1 + 37 o2 - 9 o3)/24   (plms.py:229-238)
+//        [c = (1,0,0,0)/1: e' = e (first half of the pseudo improved Euler step, :226-228);  (1,-1,0,0)/2: (e + o1)/2]
+//   pred_x0 = (x - sqrt(1-a_t) e') / sqrt(a_t);  x_prev = sqrt(a_prev) pred_x0 + sqrt(1-a_prev) e'   (:205-225, sigma = 0)
+//   push != 0: the history (o1, o2, o3) <- (e, o1, o2)   (old_eps.append / pop, :170-172)
+// _rn intrinsics (no FMA contraction): bit-identical to the reference's fp32 tensor expressions given the same eps.
+__global__ void cfg_plms_kernel(const float4* __restrict__ x, const float4* __restrict__ eps, const float* __restrict__ coef, float scale,
+                                int cfg, float4* __restrict__ hist, float4* __restrict__ x_prev, float4* __restrict__ pred_x0,
+                                long long n4) {
+    const float c_somat = coef[0], c_sqrt_at = coef[1], c_sqrt_aprev = coef[2], c_dir = coef[3];
+    const float c0 = coef[4], c1 = coef[5], c2 = coef[6], c3 = coef[7], den = coef[8];
+    const bool push = coef[9] != 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 xv = x[i], eu = eps[i], ec = cfg ? eps[i + n4] : eu;
+        const float4 o1 = hist[i], o2 = hist[i + n4], o3 = hist[i + 2 * n4];
+        float4 e4, p0, o;
+#define ANYSD_PLMS_LANE(f)                                                                                                    \
+        {                                                                                                                         \
+            const float e = cfg ? __fadd_rn(eu.f, __fmul_rn(scale, __fsub_rn(ec.f, eu.f))) : eu.f;                                \
+            float ep = __fsub_rn(__fmul_rn(c0, e), __fmul_rn(c1, o1.f));                                                          \
+            ep = __fsub_rn(__fadd_rn(ep, __fmul_rn(c2, o2.f)), __fmul_rn(c3, o3.f));                                              \
+            ep = __fdiv_rn(ep, den);                                                                                              \
+            const float p = __fdiv_rn(__fsub_rn(xv.f, __fmul_rn(c_somat, ep)), c_sqrt_at);                                        \
+            e4.f = e;                                                                                                             \
+            p0.f = p;                                                                                                             \
+            o.f = __fadd_rn(__fmul_rn(c_sqrt_aprev, p), __fmul_rn(c_dir, ep));                                                    \
+        }
+        ANYSD_PLMS_LANE(x) ANYSD_PLMS_LANE(y) ANYSD_PLMS_LANE(z) ANYSD_PLMS_LANE(w)
+#undef ANYSD_PLMS_LANE
+        x_prev[i] = o;
+        if (pred_x0 != nullptr) pred_x0[i] = p0;
+        if (push) {
+            hist[i + 2 * n4] = o2;
+            hist[i + n4] = o1;
+            hist[i] = e4;
+        }
+    }
+}
+
+// ---- DPM-Solver++(2M) step (ldm/models/diffusion/dpm_solver/dpm_solver.py:352-365, 469-513, 723-778) ------------------
+// coef[6] = {sigma_s, alpha_s, sigma_t/sigma_s, c, 0.5 c, 1/r0}  (s = the time of this model call, t = the next grid point):
+//   m     = (x - sigma_s e) / alpha_s                                   data prediction at s
+//   x_t   = ((sigma_t/sigma_s) x - c m) - (0.5 c) ((1/r0) (m - m_prev))      c = alpha_t (exp(-h) - 1)
+//           [first-order steps pass c = alpha_t expm1(-h) and 0.5 c = 0: the update of :469-513]
+//   m_prev <- m
+__global__ void cfg_dpmpp_kernel(const float4* __restrict__ x, const float4* __restrict__ eps, const float* __restrict__ coef, float scale,
+                                 int cfg, float4* __restrict__ m_prev, float4* __restrict__ x_next, float4* __restrict__ x0_out,
+                                 long long n4) {
+    const float sig = coef[0], alp = coef[1], ratio = coef[2], c = coef[3], half_c = coef[4], inv_r0 = coef[5];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 xv = x[i], eu = eps[i], ec = cfg ? eps[i + n4] : eu, mp = m_prev[i];
+        float4 m4, o;
+#define ANYSD_DPMPP_LANE(f)                                                                                                   \
+        {                                                                                                                         \
+            const float e = cfg ? __fadd_rn(eu.f, __fmul_rn(scale, __fsub_rn(ec.f, eu.f))) : eu.f;                                \
+            const float m = __fdiv_rn(__fsub_rn(xv.f, __fmul_rn(sig, e)), alp);                                                   \
+            const float d1 = __fmul_rn(inv_r0, __fsub_rn(m, mp.f));                                                               \
+            m4.f = m;                                                                                                             \
+            o.f = __fsub_rn(__fsub_rn(__fmul_rn(ratio, xv.f), __fmul_rn(c, m)), __fmul_rn(half_c, d1));                           \
+        }
+        ANYSD_DPMPP_LANE(x) ANYSD_DPMPP_LANE(y) ANYSD_DPMPP_LANE(z) ANYSD_DPMPP_LANE(w)
+#undef ANYSD_DPMPP_LANE
+        x_next[i] = o;
+        m_prev[i] = m4;
+        if (x0_out != nullptr) x0_out[i] = m4;
     }
 }
 
@@ -290,7 +370,7 @@ int anysd_emb_finalize(const float* emb_lin, const float* table, const long long
 }
 
 int anysd_cfg_ddim_step_f32(const float* x, const float* eps, const float* noise, const float* coef,
-                            float guidance_scale, int cfg, float* x_prev, float* pred_x0, long long n_per_batch,
+                            float guidance_scale, int cfg, int v_param, float* x_prev, float* pred_x0, long long n_per_batch,
                             int B, anysd_stream_t stream) {
     ANYSD_REQUIRE(x && eps && coef && x_prev && B > 0 && n_per_batch > 0, ANYSD_EINVAL, "cfg_ddim_step: bad args");
     long long total = n_per_batch * B;
@@ -299,7 +379,7 @@ int anysd_cfg_ddim_step_f32(const float* x, const float* eps, const float* noise
     int grid = (int)((n4 + 255) / 256);
     if (grid > sm_count() * 8) grid = sm_count() * 8;
     cfg_ddim_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)eps,
-                                                            (const float4*)noise, coef, guidance_scale, cfg,
+                                                            (const float4*)noise, coef, guidance_scale, cfg, v_param,
                                                             (float4*)x_prev, (float4*)pred_x0, n4, n4);
     return check_launch("cfg_ddim_step");
 }
@@ -315,6 +395,32 @@ int anysd_cfg3_ddim_step_f32(const float* x, const float* eps, const float* nois
     cfg3_ddim_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)eps, (const float4*)noise, coef, text_scale,
                                                             image_scale, (float4*)x_prev, (float4*)pred_x0, n4);
     return check_launch("cfg3_ddim_step");
+}
+
+int anysd_cfg_plms_step_f32(const float* x, const float* eps, const float* coef, float guidance_scale, int cfg, float* hist,
+                            float* x_prev, float* pred_x0, long long n_per_batch, int B, anysd_stream_t stream) {
+    ANYSD_REQUIRE(x && eps && coef && hist && x_prev && B > 0 && n_per_batch > 0, ANYSD_EINVAL, "cfg_plms_step: bad args");
+    long long total = n_per_batch * B;
+    ANYSD_REQUIRE(total % 4 == 0, ANYSD_EINVAL, "cfg_plms_step: B*C*H*W must be a multiple of 4");
+    long long n4 = total / 4;
+    int grid = (int)((n4 + 255) / 256);
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
+    cfg_plms_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)eps, coef, guidance_scale, cfg, (float4*)hist,
+                                                            (float4*)x_prev, (float4*)pred_x0, n4);
+    return check_launch("cfg_plms_step");
+}
+
+int anysd_cfg_dpmpp_step_f32(const float* x, const float* eps, const float* coef, float guidance_scale, int cfg, float* m_prev,
+                             float* x_next, float* x0_out, long long n_per_batch, int B, anysd_stream_t stream) {
+    ANYSD_REQUIRE(x && eps && coef && m_prev && x_next && B > 0 && n_per_batch > 0, ANYSD_EINVAL, "cfg_dpmpp_step: bad args");
+    long long total = n_per_batch * B;
+    ANYSD_REQUIRE(total % 4 == 0, ANYSD_EINVAL, "cfg_dpmpp_step: B*C*H*W must be a multiple of 4");
+    long long n4 = total / 4;
+    int grid = (int)((n4 + 255) / 256);
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
+    cfg_dpmpp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)eps, coef, guidance_scale, cfg, (float4*)m_prev,
+                                                             (float4*)x_next, (float4*)x0_out, n4);
+    return check_launch("cfg_dpmpp_step");
 }
 
 int anysd_router_gate_f32(const float* table, const long long* idx, int table_rows, const void* W, const float* bias,

@@ -112,7 +112,12 @@ class LatentDenoiser(nn.Module):
     def graph_key(self):
         """Identity of the packed weights a captured CUDA graph would point at (parameter versions + device)."""
         m = self.model.diffusion_model
-        return tuple((str(p.device), p._version, p.data_ptr()) for p in m.parameters()).__hash__()
+        return (tuple((str(p.device), p._version, p.data_ptr()) for p in m.parameters()).__hash__(), getattr(m, "_epoch", 0))
+
+    def invalidate(self):
+        m = self.model.diffusion_model
+        if hasattr(m, "invalidate"):
+            m.invalidate()
 
     def register_schedule(self, given_betas=None, beta_schedule="linear", timesteps=1000, linear_start=1e-4,
                           linear_end=2e-2, cosine_s=8e-3):

@@ -44,8 +44,19 @@ def broadcast_module_(module, src=0):
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src)
-    if hasattr(module, "invalidate"):
-        module.invalidate()
+    invalidate_caches_(module)
+
+
+def invalidate_caches_(module):
+    """``.data`` writes do not bump parameter versions: every module in the tree that caches packed weights (UNetModel,
+    MoE) or keys CUDA graphs on them (LatentDenoiser / AnySDDenoiser) is told explicitly, so nothing packed or captured
+    before the write can survive it."""
+    seen = set()
+    for m in module.modules():
+        inv = getattr(m, "invalidate", None)
+        if callable(inv) and id(m) not in seen:
+            seen.add(id(m))
+            inv()
 
 
 def barrier():

@@ -253,14 +253,15 @@ def attention(q, k, v, out, B, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o, q_bs
     _count()
 
 
-def cfg_ddim_step(x, eps, coef, scale, cfg, x_prev, pred_x0=None, noise=None):
-    """ddim.py:211-212, 228-250 in one kernel; all fp32 NCHW; coef is a 5-float device tensor."""
+def cfg_ddim_step(x, eps, coef, scale, cfg, x_prev, pred_x0=None, noise=None, v_param=False):
+    """ddim.py:211-212, 228-250 in one kernel; all fp32 NCHW; coef is a device tensor of >= 5 floats (7 with v_param:
+    the model output is v and coef[5:7] = sqrt(acp[t]), sqrt(1 - acp[t]))."""
     _cuda(x, eps, coef, x_prev)
     B = x.shape[0]
     n_per = x.numel() // B
     assert x.dtype == torch.float32 and eps.dtype == torch.float32 and x.is_contiguous() and eps.is_contiguous()
     _lib.check(_lib.load().anysd_cfg_ddim_step_f32(_ptr(x), _ptr(eps), _ptr(noise), _ptr(coef), float(scale),
-                                                   int(bool(cfg)), _ptr(x_prev), _ptr(pred_x0), n_per, B, _stream()),
+                                                   int(bool(cfg)), int(bool(v_param)), _ptr(x_prev), _ptr(pred_x0), n_per, B, _stream()),
                "cfg_ddim_step")
     _count()
 
@@ -272,6 +273,29 @@ def cfg3_ddim_step(x, eps, coef, text_scale, image_scale, x_prev, pred_x0=None, 
     assert eps.shape[0] == 3 * B and x.dtype == torch.float32 and eps.dtype == torch.float32 and x.is_contiguous() and eps.is_contiguous()
     _lib.check(_lib.load().anysd_cfg3_ddim_step_f32(_ptr(x), _ptr(eps), _ptr(noise), _ptr(coef), float(text_scale), float(image_scale),
                                                     _ptr(x_prev), _ptr(pred_x0), x.numel() // B, B, _stream()), "cfg3_ddim_step")
+    _count()
+
+
+def cfg_plms_step(x, eps, coef, scale, cfg, hist, x_prev, pred_x0=None):
+    """plms.py:178-244 in one kernel: CFG combine, multistep eps, DDIM update, history push; coef: 10 floats on the device,
+    hist: fp32 [3, B, C, H, W] (zero-initialised)."""
+    _cuda(x, eps, coef, hist, x_prev)
+    B = x.shape[0]
+    assert x.dtype == torch.float32 and eps.dtype == torch.float32 and hist.dtype == torch.float32
+    assert x.is_contiguous() and eps.is_contiguous() and hist.is_contiguous() and hist.numel() == 3 * x.numel()
+    _lib.check(_lib.load().anysd_cfg_plms_step_f32(_ptr(x), _ptr(eps), _ptr(coef), float(scale), int(bool(cfg)), _ptr(hist), _ptr(x_prev),
+                                                   _ptr(pred_x0), x.numel() // B, B, _stream()), "cfg_plms_step")
+    _count()
+
+
+def cfg_dpmpp_step(x, eps, coef, scale, cfg, m_prev, x_next, x0_out=None):
+    """One DPM-Solver++(2M) step (dpm_solver.py:352-365, 469-513, 723-778); coef: 6 floats on the device, m_prev: fp32 like x."""
+    _cuda(x, eps, coef, m_prev, x_next)
+    B = x.shape[0]
+    assert x.dtype == torch.float32 and eps.dtype == torch.float32 and m_prev.dtype == torch.float32
+    assert x.is_contiguous() and eps.is_contiguous() and m_prev.is_contiguous() and m_prev.numel() == x.numel()
+    _lib.check(_lib.load().anysd_cfg_dpmpp_step_f32(_ptr(x), _ptr(eps), _ptr(coef), float(scale), int(bool(cfg)), _ptr(m_prev), _ptr(x_next),
+                                                    _ptr(x0_out), x.numel() // B, B, _stream()), "cfg_dpmpp_step")
     _count()
 
 

@@ -312,6 +312,7 @@ class UNetModel(nn.Module):
 
         self._pack = None
         self._pack_key = None
+        self._epoch = 0                  # bumped by invalidate(): part of the pack key and of LatentDenoiser.graph_key
 
     # the reference's no-op stubs (openaimodel.py:738-752)
     def convert_to_fp16(self):
@@ -327,10 +328,13 @@ class UNetModel(nn.Module):
         for p in self.parameters():
             ver += p._version
             dev = p.device
-        return (str(dev), ver)
+        return (str(dev), ver, self._epoch)
 
     def invalidate(self):
+        """Call after an in-place weight change that does not bump parameter versions (a ``.data`` write, a raw-pointer
+        kernel): drops the packed weights and makes every sampler re-capture its CUDA graphs."""
         self._pack = None
+        self._epoch += 1
 
     def prepare(self):
         """Repack parameters into kernel layouts on their device (done lazily, redone when any
@@ -666,13 +670,17 @@ class UNetModel(nn.Module):
         ops.gemm(g.view(M, C), d["pin_w"], t, bias=d["pin_b"])
         for i, b in enumerate(d["blocks"]):
             ctx = st["ctx"][i] if i < len(st["ctx"]) else st["ctx"][-1]
+            if share and not b["self"]:
+                # disable_self_attn: attn1 already attends to the context, which differs between the CFG halves --
+                # nothing more can be shared, widen to the full batch here
+                t, h = self._dup_rows(t), self._dup_rows(h)
+                N, M, share = 2 * N, 2 * M, False
             ln = torch.empty_like(t)
             ops.layernorm(t, b["ln1_w"], b["ln1_b"], ln)
             t2 = torch.empty_like(t)
             if b["self"]:
                 self._attn(b["attn1"], ln, None, N, n, st, True, t, t2)
             else:
-                assert not share
                 self._attn(b["attn1"], ln, ctx, N, n, st, False, t, t2)
             ln2 = torch.empty_like(t)
             ops.layernorm(t2, b["ln2_w"], b["ln2_b"], ln2)

@@ -154,9 +154,11 @@ int anysd_attention_f16(const anysd_attn_params* p, anysd_stream_t stream);
  *   x_prev = sqrt(a_prev) pred_x0 + sqrt(1 - a_prev - sigma^2) e + sigma * noise
  * all fp32, NCHW.  eps holds [uncond ; cond] (2B rows) when cfg != 0, else B rows.
  * coef[5] = {sqrt(1-a_t), 1/sqrt(a_t) as sqrt(a_t) divisor, sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma}
- * lives on the device so that one CUDA graph serves all steps.  noise/pred_x0 may be NULL. */
+ * lives on the device so that one CUDA graph serves all steps.  noise/pred_x0 may be NULL.
+ * v_param != 0: the model output is v (ddim.py:214-218, 224-226); coef[5] = sqrt(acp[t]), coef[6] = sqrt(1-acp[t]):
+ *   e = coef[5] v + coef[6] x;  pred_x0 = coef[5] x - coef[6] v  (ddpm.py predict_eps/start_from_z_and_v). */
 int anysd_cfg_ddim_step_f32(const float* x, const float* eps, const float* noise, const float* coef,
-                            float guidance_scale, int cfg, float* x_prev, float* pred_x0, long long n_per_batch,
+                            float guidance_scale, int cfg, int v_param, float* x_prev, float* pred_x0, long long n_per_batch,
                             int B, anysd_stream_t stream);
 
 /* InstructPix2Pix three-way guidance (tools/global_tool.py:166-177) + the same DDIM update:
@@ -164,6 +166,20 @@ int anysd_cfg_ddim_step_f32(const float* x, const float* eps, const float* noise
 int anysd_cfg3_ddim_step_f32(const float* x, const float* eps, const float* noise, const float* coef, float text_scale,
                              float image_scale, float* x_prev, float* pred_x0, long long n_per_batch, int B,
                              anysd_stream_t stream);
+
+/* PLMSSampler.p_sample_plms (ldm/models/diffusion/plms.py:178-244): CFG combine, Adams-Bashforth combination of the eps
+ * history, DDIM update (sigma = 0) and the history push in one kernel.  hist = three [B, n_per_batch] fp32 planes (o1, o2, o3),
+ * zero-initialised by the caller.  coef[10] = {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev), c0, c1, c2, c3, den, push}:
+ * e' = (((c0 e - c1 o1) + c2 o2) - c3 o3) / den, evaluated left to right like the reference's tensor expressions. */
+int anysd_cfg_plms_step_f32(const float* x, const float* eps, const float* coef, float guidance_scale, int cfg, float* hist,
+                            float* x_prev, float* pred_x0, long long n_per_batch, int B, anysd_stream_t stream);
+
+/* DPM-Solver++(2M) as DPMSolverSampler configures it (ldm/models/diffusion/dpm_solver/sampler.py:61-87; dpm_solver.py:352-365
+ * data prediction, :469-513 first-order update, :723-778 second-order multistep update): coef[6] = {sigma_s, alpha_s,
+ * sigma_t/sigma_s, c, 0.5 c (0 for a first-order step), 1/r0};  m = (x - sigma_s e)/alpha_s;
+ * x_next = ((sigma_t/sigma_s) x - c m) - (0.5 c)((1/r0)(m - m_prev));  m_prev <- m (zero-initialised by the caller). */
+int anysd_cfg_dpmpp_step_f32(const float* x, const float* eps, const float* coef, float guidance_scale, int cfg, float* m_prev,
+                             float* x_next, float* x0_out, long long n_per_batch, int B, anysd_stream_t stream);
 
 /* ==== training step (train.py:629-710) =====================================================
  * The reference back-propagates mse_loss(MoE(...), noise) through the frozen UNet with torch autograd

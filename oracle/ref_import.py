@@ -1,9 +1,14 @@
-"""Import the real reference modules from /root/reference (BUILD CONTAINER ONLY).
+"""Import the real reference modules: from /root/reference in the build container, from the staged copy
+``oracle/_ref/`` on the GPU box.
 
-TEST INFRASTRUCTURE.  /root/reference does not exist on the GPU box, so nothing at run time
-may depend on this module; it is used by ``tests/golden/make_golden.py`` to generate the
-committed golden vectors and by ``tests/test_oracle_vs_reference.py`` (skipped when the
-reference tree is absent) to pin the restatement.
+TEST INFRASTRUCTURE.  Used by ``tests/golden/make_golden*.py`` to generate the committed golden vectors, by
+``tests/test_oracle_golden.py`` to pin the restatement, and by ``bench.py --impl reference`` / the ``cpu_baseline``
+leg to time the reference's OWN ``UNetModel`` + ``DDIMSampler`` on the box's host cores.
+
+``stage()`` (called by ``__graft_entry__.build()`` when /root/reference is present) copies the five source files of
+the path -- and nothing else -- into ``oracle/_ref/ldm/...``.  ``oracle/_ref/`` is git-ignored (reference sources
+never enter the history) but not gpurun-ignored, so it travels to the GPU box like the built ``.so`` does; when it
+is absent the CPU legs fall back to the restatement (``cpu_baseline.kind = "port"``).
 
 Work-arounds:
   * ``omegaconf`` is not installed and UNetModel.__init__ imports
@@ -14,11 +19,35 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("ANYEDIT_REFERENCE", "/root/reference")
+SRC_ROOT = os.environ.get("ANYEDIT_REFERENCE", "/root/reference")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+# the files of the hot path; ldm/ is a namespace package (no top-level __init__.py)
+STAGED_FILES = ("ldm/util.py", "ldm/modules/attention.py", "ldm/modules/diffusionmodules/__init__.py",
+                "ldm/modules/diffusionmodules/util.py", "ldm/modules/diffusionmodules/openaimodel.py",
+                "ldm/models/diffusion/__init__.py", "ldm/models/diffusion/ddim.py")
+
+
+def _has(root) -> bool:
+    return all(os.path.isfile(os.path.join(root, f)) for f in STAGED_FILES)
+
+
+REF_ROOT = SRC_ROOT if os.path.isdir(os.path.join(SRC_ROOT, "ldm")) else STAGED_ROOT
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REF_ROOT, "ldm"))
+    return _has(REF_ROOT)
+
+
+def stage() -> str:
+    """Copy the path's reference sources into oracle/_ref/ (build container only; no-op elsewhere)."""
+    import shutil
+    if not os.path.isdir(os.path.join(SRC_ROOT, "ldm")):
+        return STAGED_ROOT if _has(STAGED_ROOT) else ""
+    for f in STAGED_FILES:
+        dst = os.path.join(STAGED_ROOT, f)
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        shutil.copyfile(os.path.join(SRC_ROOT, f), dst)
+    return STAGED_ROOT
 
 
 def _stub_omegaconf():

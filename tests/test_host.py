@@ -115,7 +115,7 @@ def test_schedule_bit_exact_through_product_api():
             assert np.array_equal(np.asarray(s.ddim_alphas, dtype=np.float32), g[f"alphas_{tag}"])
             assert np.array_equal(np.asarray(s.ddim_alphas_prev, dtype=np.float64), g[f"alphas_prev_{tag}"])
             assert np.array_equal(np.asarray(s.ddim_sigmas, dtype=np.float64), g[f"sigmas_{tag}"])
-            assert tuple(s.ddim_coef_host.shape) == (S, 5)
+            assert tuple(s.ddim_coef_host.shape) == (S, 7)        # 5 DDIM scalars + sqrt(acp[t]), sqrt(1 - acp[t]) for v-param
     assert np.array_equal(ddim.make_ddim_timesteps("quad", 20, 1000, verbose=False), g["ts_quad_20"])
     with pytest.raises(NotImplementedError):
         ddim.make_ddim_timesteps("nope", 20, 1000, verbose=False)
@@ -260,3 +260,63 @@ def test_cfg_halves_sharing_decision(monkeypatch):
     assert _halves_share_prefix({"c_crossattn": [utxt]}, {"c_crossattn": [txt]})                   # pure cross-attention model
     monkeypatch.setenv("ANYSD_SHARE_CFG", "0")
     assert not _halves_share_prefix({"c_concat": [cc], "c_crossattn": [utxt]}, c)
+
+
+def _toy_eps(x, t):
+    return 0.3 * torch.sin(1.7 * x) + 0.05 * torch.cos(x * 0.5 + t.float().reshape(-1, 1, 1, 1) * 0.01)
+
+
+def test_plms_plan_and_rows_match_oracle_on_cpu():
+    """Host logic of anyedit_b200.plms (no GPU): the call plan + coefficient rows, pushed through a torch emulation of
+    ``cfg_plms_kernel``'s arithmetic, reproduce oracle/plms_oracle.py (pinned to the reference PLMSSampler) bit for bit."""
+    import numpy as np
+    from anyedit_b200.ddim import make_ddim_sampling_parameters, make_ddim_timesteps, step_coefficients
+    from anyedit_b200.plms import plms_plan
+    from oracle import ddim_oracle, plms_oracle
+    sched = ddim_oracle.register_schedule("linear", 1000, 0.00085, 0.012)
+    x_T = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(3))
+    for S in (5, 10):
+        ts = make_ddim_timesteps("uniform", S, 1000, verbose=False)
+        sig, a, ap = make_ddim_sampling_parameters(sched["alphas_cumprod"], ts, 0.0, verbose=False)
+        ddim = [step_coefficients(a, ap, sig, np.sqrt(1.0 - a), i)[:4] for i in range(S)]
+        hist = [torch.zeros_like(x_T) for _ in range(3)]
+        img, x_tmp = x_T, None
+        f = lambda v: torch.tensor(v, dtype=torch.float32)
+        for call in plms_plan(np.flip(ts)):
+            xm = x_tmp if call["use_tmp"] else img
+            e = _toy_eps(xm, torch.full((2,), call["t"]))
+            c0, c1, c2, c3, den = (f(v) for v in call["comb"])
+            ep = (((c0 * e - c1 * hist[0]) + c2 * hist[1]) - c3 * hist[2]) / den
+            somat, sq_at, sq_ap, dr = (f(v) for v in ddim[call["index"]])
+            pred = (img - somat * ep) / sq_at
+            out = sq_ap * pred + dr * ep
+            if call["push"]:
+                hist = [e, hist[0], hist[1]]
+            if call["final"]:
+                img, x_tmp = out, None
+            else:
+                x_tmp = out
+        ref, _ = plms_oracle.plms_sample(lambda x, t, c: _toy_eps(x, t), sched, S, x_T, None)
+        assert torch.equal(img, ref), S
+
+
+def test_dpmpp_tables_match_oracle_on_cpu():
+    """Host logic of anyedit_b200.dpm_solver (no GPU): the schedule tables + a torch emulation of ``cfg_dpmpp_kernel``
+    reproduce oracle/dpm_oracle.py (pinned to the reference DPMSolverSampler), S < 15 (order-1 final step) and S >= 15."""
+    from anyedit_b200.dpm_solver import NoiseScheduleVP, dpmpp_2m_tables
+    from oracle import ddim_oracle, dpm_oracle
+    sched = ddim_oracle.register_schedule("linear", 1000, 0.00085, 0.012)
+    x_T = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(4))
+    ns = NoiseScheduleVP("discrete", alphas_cumprod=sched["alphas_cumprod"])
+    for S in (10, 20):
+        t_model, coef = dpmpp_2m_tables(ns, S)
+        x, mp = x_T, torch.zeros_like(x_T)
+        for k in range(S):
+            e = _toy_eps(x, torch.full((2,), t_model[k]))
+            sig, alp, ratio, c, half_c, inv_r0 = coef[k]
+            m = (x - sig * e) / alp
+            x = (ratio * x - c * m) - half_c * (inv_r0 * (m - mp))
+            mp = m
+        ref = dpm_oracle.dpm_solver_pp_2m(lambda x_, t, c_: _toy_eps(x_, t), sched["alphas_cumprod"], S, x_T, None)
+        err = float((x - ref).norm() / ref.norm())
+        assert err < 2e-6, (S, err)
