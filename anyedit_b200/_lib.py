@@ -23,6 +23,7 @@ class GemmParams(C.Structure):
         ("Nimg", C.c_int), ("H", C.c_int), ("Wd", C.c_int), ("Cin", C.c_int),
         ("stride", C.c_int), ("upsample", C.c_int),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("conv_pad", C.c_int),
     ]
 
 
@@ -85,10 +86,12 @@ SIGNATURES = {
     "anysd_cfg3_ddim_step_f32": (_I, [_VP, _VP, _VP, _VP, _F, _F, _VP, _VP, _LL, _I, _VP]),
     "anysd_cfg_plms_step_f32": (_I, [_VP, _VP, _VP, _F, _I, _VP, _VP, _VP, _LL, _I, _VP]),
     "anysd_cfg_dpmpp_step_f32": (_I, [_VP, _VP, _VP, _F, _I, _VP, _VP, _VP, _LL, _I, _VP]),
+    "anysd_softmax_rows_f32": (_I, [_VP, _LL, _VP, _LL, _I, _I, _F, _VP]),
+    "anysd_gaussian_posterior_f32": (_I, [_VP, _VP, _VP, _VP, _F, _I, _LL, _VP]),
     # ---- training step ----
     "anysd_q_sample_f32": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _LL, _VP]),
     "anysd_mse_workspace_bytes": (_SZ, []),
-    "anysd_mse_loss_f32": (_I, [_VP, _VP, _I, _I, _I, _I, _F, _VP, _VP, _VP, _SZ, _VP]),
+    "anysd_mse_loss_f32": (_I, [_VP, _VP, _I, _I, _I, _I, _F, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "anysd_geglu_f16": (_I, [_VP, _VP, _LL, _I, _VP]),
     "anysd_geglu_bwd_f16": (_I, [_VP, _VP, _VP, _LL, _I, _VP]),
     "anysd_silu_bwd_f32": (_I, [_VP, _VP, _VP, _LL, _VP]),
@@ -109,6 +112,9 @@ SIGNATURES = {
     "anysd_router_bwd_f32": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _F, _VP, _VP, _VP, _VP]),
     "anysd_scatter_add_rows_f32": (_I, [_VP, _VP, _I, _I, _I, _F, _VP, _VP]),
     "anysd_adamw_f32": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _F, _VP]),
+    "anysd_grad_check_f32": (_I, [_VP, _LL, _VP, _VP]),
+    "anysd_adamw_scaled_f32": (_I, [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _F, _VP, _VP]),
+    "anysd_loss_scale_update_f32": (_I, [_VP, _F, _F, _I, _VP]),
 }
 
 _lib = None

@@ -151,7 +151,8 @@ class MoE(nn.Module):
     def save_pretrained(self, path):
         import os
         os.makedirs(path, exist_ok=True)
-        sd = {k: v for k, v in self.state_dict().items() if not k.startswith("unet.")}
+        # clones: under AdapterTrainer the parameters are views of one flat buffer (torch.save would write all of it per view)
+        sd = {k: v.detach().clone() for k, v in self.state_dict().items() if not k.startswith("unet.")}
         torch.save(sd, os.path.join(path, "anysd_adapter.pt"))
 
 

@@ -336,9 +336,10 @@ __global__ void sumpool2x_kernel(const uint4* __restrict__ src, uint4* __restric
 // pred, target fp32 NCHW [N, C, HW]; loss += mean((pred - target)^2); dpred NHWC fp16 [N, HW, Cpad] =
 // grad_scale * 2 (pred - target) / numel, zero in the padding channels.  Two-stage deterministic sum: partial[blk].
 __global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, int N, int C, int HW,
-                                                  int Cpad, float grad_scale, __half* __restrict__ dpred, float* __restrict__ partial) {
+                                                  int Cpad, float grad_scale, const float* __restrict__ scale_dev, __half* __restrict__ dpred,
+                                                  float* __restrict__ partial) {
     const long long numel = (long long)N * C * HW;
-    const float k = grad_scale * 2.0f / (float)numel;
+    const float k = grad_scale * (scale_dev ? *scale_dev : 1.0f) * 2.0f / (float)numel;
     float acc = 0.f;
     const long long pix = (long long)N * HW;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pix; i += (long long)gridDim.x * blockDim.x) {
@@ -397,6 +398,61 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
         w -= (lr / bc1) * mi / denom;
         p[i] = w;
     }
+}
+
+// ---- mixed-precision step control on the device (the GradScaler semantics accelerate gives train.py:694-709) ------------
+// scaler[4] = {loss scale, growth tracker, optimizer steps taken, found_inf}.  No host synchronisation anywhere:
+//   grad_check   found_inf = 1 if any gradient element (after the all-reduce) is inf / nan
+//   adamw_scaled torch.optim.AdamW over one flat fp32 buffer; skipped when found_inf; step number = steps taken + 1;
+//                gradients are divided by (loss scale x world) on the fly
+//   scale_update found_inf ? (scale *= backoff, tracker = 0) : (steps += 1, ++tracker == interval -> scale *= growth); found_inf = 0
+__global__ void grad_check_kernel(const float4* __restrict__ g, long long n4, const float* __restrict__ tail, int ntail,
+                                  float* __restrict__ scaler) {
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = g[i];
+        const uint32_t a = __float_as_uint(v.x), b = __float_as_uint(v.y), c = __float_as_uint(v.z), d = __float_as_uint(v.w);
+        bad |= ((a & 0x7f800000u) == 0x7f800000u) | ((b & 0x7f800000u) == 0x7f800000u) | ((c & 0x7f800000u) == 0x7f800000u) |
+               ((d & 0x7f800000u) == 0x7f800000u);
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) bad |= (__float_as_uint(tail[threadIdx.x]) & 0x7f800000u) == 0x7f800000u;
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) scaler[3] = 1.0f;      // benign race: every writer stores 1
+}
+
+__global__ void adamw_scaled_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                    long long n, float lr, float b1, float b2, float eps, float wd, float inv_world,
+                                    const float* __restrict__ scaler) {
+    if (scaler[3] != 0.0f) return;                       // overflow somewhere in this step's gradients: skip it (GradScaler.step)
+    const float step = scaler[2] + 1.0f;
+    const float bc1 = 1.0f - powf(b1, step), bc2_sqrt = sqrtf(1.0f - powf(b2, step));
+    const float grad_scale = inv_world / scaler[0];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gr = g[i] * grad_scale;
+        float w = p[i] * (1.0f - lr * wd);
+        const float mi = b1 * m[i] + (1.0f - b1) * gr;
+        const float vi = b2 * v[i] + (1.0f - b2) * gr * gr;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        w -= (lr / bc1) * mi / denom;
+        p[i] = w;
+    }
+}
+
+__global__ void loss_scale_update_kernel(float* __restrict__ scaler, float growth, float backoff, int interval) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (scaler[3] != 0.0f) {
+        scaler[0] *= backoff;
+        scaler[1] = 0.0f;
+    } else {
+        scaler[2] += 1.0f;
+        scaler[1] += 1.0f;
+        if (interval > 0 && scaler[1] >= (float)interval) {
+            scaler[0] *= growth;
+            scaler[1] = 0.0f;
+        }
+    }
+    scaler[3] = 0.0f;
 }
 
 // ---- small-M weight gradient: out[ka, kb] (+)= alpha * sum_m A[m, col(ka)] * B[m, kb] -----------------------------
@@ -627,13 +683,15 @@ int anysd_sumpool2x_f16(const void* src, void* dst, int N, int H, int W, int C, 
 
 size_t anysd_mse_workspace_bytes(void) { return (size_t)1024 * sizeof(float); }
 
-int anysd_mse_loss_f32(const float* pred, const float* target, int N, int C, int HW, int Cpad, float grad_scale, void* d_pred,
-                       float* loss, void* workspace, size_t workspace_bytes, anysd_stream_t stream) {
+int anysd_mse_loss_f32(const float* pred, const float* target, int N, int C, int HW, int Cpad, float grad_scale,
+                       const float* grad_scale_dev, void* d_pred, float* loss, void* workspace, size_t workspace_bytes,
+                       anysd_stream_t stream) {
     ANYSD_REQUIRE(pred && target && d_pred && loss && workspace, ANYSD_EINVAL, "mse_loss: null pointer");
     ANYSD_REQUIRE(N > 0 && C > 0 && HW > 0 && Cpad >= C && workspace_bytes >= anysd_mse_workspace_bytes(), ANYSD_EINVAL, "mse_loss: bad args");
     int grid = grid_for((long long)N * HW, 256, 4);
     if (grid > 1024) grid = 1024;
-    mse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, target, N, C, HW, Cpad, grad_scale, (__half*)d_pred, (float*)workspace);
+    mse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, target, N, C, HW, Cpad, grad_scale, grad_scale_dev, (__half*)d_pred,
+                                                       (float*)workspace);
     int rc = check_launch("mse_loss");
     if (rc) return rc;
     sum_partials_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const float*)workspace, grid, loss);
@@ -656,6 +714,28 @@ int anysd_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_
     adamw_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                               weight_decay, bc1, bc2s, grad_scale);
     return check_launch("adamw");
+}
+
+int anysd_grad_check_f32(const float* grad, long long n, float* scaler, anysd_stream_t stream) {
+    ANYSD_REQUIRE(grad && scaler && n > 0, ANYSD_EINVAL, "grad_check: bad args");
+    ANYSD_REQUIRE(((uintptr_t)grad % 16) == 0, ANYSD_EINVAL, "grad_check: the gradient buffer must be 16-byte aligned");
+    const long long n4 = n / 4;
+    grad_check_kernel<<<grid_for(n4 > 0 ? n4 : 1), 256, 0, (cudaStream_t)stream>>>((const float4*)grad, n4, grad + 4 * n4, (int)(n - 4 * n4), scaler);
+    return check_launch("grad_check");
+}
+
+int anysd_adamw_scaled_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                           float beta2, float eps, float weight_decay, float inv_world, const float* scaler, anysd_stream_t stream) {
+    ANYSD_REQUIRE(param && grad && exp_avg && exp_avg_sq && scaler && n > 0 && inv_world > 0.f, ANYSD_EINVAL, "adamw_scaled: bad args");
+    adamw_scaled_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                     weight_decay, inv_world, scaler);
+    return check_launch("adamw_scaled");
+}
+
+int anysd_loss_scale_update_f32(float* scaler, float growth, float backoff, int interval, anysd_stream_t stream) {
+    ANYSD_REQUIRE(scaler && growth >= 1.f && backoff > 0.f && backoff <= 1.f, ANYSD_EINVAL, "loss_scale_update: bad args");
+    loss_scale_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scaler, growth, backoff, interval);
+    return check_launch("loss_scale_update");
 }
 
 int anysd_gemm_tn_f32(const void* A, int lda, int head_d, int head_stride, int group_c, int group_stride, const void* B, int ldb,

@@ -38,8 +38,11 @@ extern "C" int anysd_gemm_f16(const anysd_gemm_params* p, anysd_stream_t stream)
         ANYSD_REQUIRE(p->stride == 1 || p->stride == 2, ANYSD_EINVAL, "conv3x3: stride must be 1 or 2");
         ANYSD_REQUIRE(p->upsample == 0 || p->upsample == 1, ANYSD_EINVAL, "conv3x3: upsample must be 0 or 1");
         ANYSD_REQUIRE(p->K == 9 * p->Cin, ANYSD_EINVAL, "conv3x3: K=%d != 9*Cin=%d", p->K, 9 * p->Cin);
+        ANYSD_REQUIRE(p->conv_pad == 0 || (p->conv_pad == 1 && p->stride == 2 && !p->upsample), ANYSD_EINVAL,
+                      "conv3x3: conv_pad must be 0, or 1 with stride 2 (right/bottom padding of the first-stage Downsample)");
         const int Hl = p->H << p->upsample, Wl = p->Wd << p->upsample;
-        const int Ho = (Hl - 1) / p->stride + 1, Wo = (Wl - 1) / p->stride + 1;
+        const int Ho = p->conv_pad ? (Hl - 2) / 2 + 1 : (Hl - 1) / p->stride + 1;
+        const int Wo = p->conv_pad ? (Wl - 2) / 2 + 1 : (Wl - 1) / p->stride + 1;
         ANYSD_REQUIRE((long long)p->Nimg * Ho * Wo == p->M, ANYSD_EINVAL, "conv3x3: M=%d != N*Ho*Wo=%lld", p->M,
                       (long long)p->Nimg * Ho * Wo);
     } else {
@@ -55,6 +58,8 @@ extern "C" int anysd_gemm_f16(const anysd_gemm_params* p, anysd_stream_t stream)
     const bool allow_p = !force || !strcmp(force, "tc5p");
     const bool allow_1 = !force || !strcmp(force, "tc5");
     if (allow_p && tc5p_supported(p)) return launch_gemm_tc5p(p, (cudaStream_t)stream);
+    ANYSD_REQUIRE(!(p->conv && p->conv_pad), ANYSD_EUNSUPPORTED,
+                  "conv3x3 with right/bottom padding needs the persistent tcgen05 path (fp16 output, Cin %% 64 == 0)");
     if ((allow_1 || (force && !strcmp(force, "tc5p"))) && tc5_supported(p)) return launch_gemm_tc5(p, (cudaStream_t)stream);
     return launch_gemm_mma(p, (cudaStream_t)stream);
 }

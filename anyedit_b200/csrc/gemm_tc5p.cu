@@ -44,6 +44,7 @@ struct PArgs {
     int Nimg, Ho, Wo;
     int BW, BH, NB, tiles_w, tiles_h;
     int kb_per_tap, stride;
+    int pad_lo;              // zero rows / columns before the image: 1 (pad 1 on every side) or 0 (right / bottom padding only)
 };
 
 // ---- PTX wrappers (same forms as gemm_tc5.cu) -------------------------------------------------------
@@ -290,16 +291,16 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (CTAS == 2) {
                         pm_expect_tx_remote(full_bar(s), p.stage_tx, 0);         // credited to the leader's barrier
                         if (CONV)
-                            p_tma2_load_4d(sa, &tmA, full_bar(s), c0, c.tw * p.BW * p.stride + kx - 1,
-                                           c.th * p.BH * p.stride + ky - 1, c.tn * p.NB);
+                            p_tma2_load_4d(sa, &tmA, full_bar(s), c0, c.tw * p.BW * p.stride + kx - p.pad_lo,
+                                           c.th * p.BH * p.stride + ky - p.pad_lo, c.tn * p.NB);
                         else
                             p_tma2_load_2d(sa, &tmA, full_bar(s), kb * P_BK, c.m0);
                         p_tma2_load_2d(sb, &tmB, full_bar(s), kb * P_BK, c.n0 + rank * (c.nw >> 1));   // its half of B
                     } else {
                         pm_expect_tx(full_bar(s), p.stage_tx);
                         if (CONV)
-                            p_tma_load_4d(sa, &tmA, full_bar(s), c0, c.tw * p.BW * p.stride + kx - 1,
-                                          c.th * p.BH * p.stride + ky - 1, c.tn * p.NB);
+                            p_tma_load_4d(sa, &tmA, full_bar(s), c0, c.tw * p.BW * p.stride + kx - p.pad_lo,
+                                          c.th * p.BH * p.stride + ky - p.pad_lo, c.tn * p.NB);
                         else
                             p_tma_load_2d(sa, &tmA, full_bar(s), kb * P_BK, c.m0);
                         p_tma_load_2d(sb, &tmB, full_bar(s), kb * P_BK, c.n0);
@@ -647,6 +648,7 @@ int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
     a.BW = a.BH = a.NB = a.tiles_w = a.tiles_h = 1;
     a.kb_per_tap = 1;
     a.stride = q->conv ? q->stride : 1;
+    a.pad_lo = (q->conv && q->conv_pad) ? 0 : 1;
     a.Ho = a.Wo = 0;
     const int n_out = q->act == 2 ? q->N / 2 : q->N;
     CUtensorMap tmA, tmB, tmO, tmR;
@@ -661,8 +663,8 @@ int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
             Hin *= 2;
             Win *= 2;
         }
-        a.Ho = (Hin - 1) / a.stride + 1;
-        a.Wo = (Win - 1) / a.stride + 1;
+        a.Ho = q->conv_pad ? (Hin - 2) / 2 + 1 : (Hin - 1) / a.stride + 1;
+        a.Wo = q->conv_pad ? (Win - 2) / 2 + 1 : (Win - 1) / a.stride + 1;
         a.BW = p_pick_extent(a.Wo, 128);
         a.BH = p_pick_extent(a.Ho, 128 / a.BW);
         a.NB = 128 / (a.BW * a.BH);

@@ -573,10 +573,12 @@ class _Stepper:
                 self.graph_launches = ops.launch_count - n0    # kernels recorded into the graph
                 ops.launch_count = n0
                 self.graph, self.scale = g, scale
+                self.graph_eps = self.last_eps                 # lives in the graph's pool: every replay rewrites it
             elif self.kv is not None and self.kv_dirty:      # re-bound to new conditioning: this step runs eagerly and
                 self._eager(scale, nb)                       # refills the K/V buffers the captured graph reads
                 return self.x_prev.clone(), self.pred_x0.clone()
             self.graph.replay()
+            self.last_eps = self.graph_eps                     # (an eager step in between points last_eps elsewhere)
             ops.launch_count += self.graph_launches
         else:
             self._eager(scale, nb)

@@ -89,10 +89,13 @@ class LatentDenoiser(nn.Module):
     """
 
     def __init__(self, unet_config, conditioning_key="hybrid", timesteps=1000, beta_schedule="linear",
-                 linear_start=0.00085, linear_end=0.012, cosine_s=8e-3, parameterization="eps", given_betas=None):
+                 linear_start=0.00085, linear_end=0.012, cosine_s=8e-3, parameterization="eps", given_betas=None,
+                 first_stage_model=None, scale_factor=1.0):
         super().__init__()
         assert parameterization in ("eps", "x0", "v")
         self.parameterization = parameterization
+        # optional first stage (anyedit_b200.autoencoder.AutoencoderKL) and the latent scale (0.18215 for SD, anydoor.yaml:17)
+        self.first_stage_model, self.scale_factor = first_stage_model, float(scale_factor)
         self.model = DiffusionWrapper(unet_config, conditioning_key)
         self.conditioning_key = conditioning_key
         self.register_schedule(given_betas, beta_schedule, timesteps, linear_start, linear_end, cosine_s)
@@ -156,6 +159,20 @@ class LatentDenoiser(nn.Module):
         shape = (t.shape[0],) + (1,) * (x_t.dim() - 1)
         return (self.sqrt_alphas_cumprod.gather(-1, t).reshape(shape) * x_t -
                 self.sqrt_one_minus_alphas_cumprod.gather(-1, t).reshape(shape) * v)
+
+    # ---- first stage (ddpm.py encode_first_stage / get_first_stage_encoding / decode_first_stage) ----
+    def encode_first_stage(self, x):
+        return self.first_stage_model.encode(x)
+
+    def get_first_stage_encoding(self, encoder_posterior, noise=None):
+        """scale_factor * posterior.sample() (a tensor is taken as the encoding itself), scaled inside the sampling kernel."""
+        if isinstance(encoder_posterior, torch.Tensor):
+            return self.scale_factor * encoder_posterior
+        return encoder_posterior.sample(noise, scale=self.scale_factor)
+
+    def decode_first_stage(self, z):
+        """first_stage_model.decode(z / scale_factor); the factor rides in the 1x1 post_quant_conv weights."""
+        return self.first_stage_model.decode(z, z_scale=1.0 / self.scale_factor)
 
     def apply_model(self, x_noisy, t, cond, return_ids=False):
         if not isinstance(cond, dict):

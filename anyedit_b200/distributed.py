@@ -84,3 +84,17 @@ def allreduce_sum_(tensors, async_op=True):
         for w in works:
             w.wait()
     return dist.get_world_size()
+
+
+def world_size() -> int:
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+@torch.no_grad()
+def allreduce_sum_async(t):
+    """Launch ``all_reduce(sum)`` of one gradient bucket and return the work handle (None on a single rank).  With the
+    NCCL backend the collective runs on NCCL's stream behind everything issued so far on the current stream and overlaps
+    whatever is issued next; ``handle.wait()`` makes the current stream wait for it."""
+    if world_size() == 1:
+        return None
+    return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)

@@ -197,12 +197,17 @@ def gemm(A, W, out, bias=None, rowadd=None, rows_per_batch=0, residual=None, act
 
 
 def conv3x3(x, W, out, bias=None, rowadd=None, residual=None, stride=1, upsample=0, ld_rowadd=None,
-            logical_cin=None, logical_cout=None):
-    """x NHWC fp16 [N,H,W,Cin]; W fp16 [Cout, 9*Cin] ((ky,kx,ci) K order); out [N*Ho*Wo, Cout]."""
+            logical_cin=None, logical_cout=None, act=0, pad_rb=False):
+    """x NHWC fp16 [N,H,W,Cin]; W fp16 [Cout, 9*Cin] ((ky,kx,ci) K order); out [N*Ho*Wo, Cout].
+    pad_rb (stride 2 only): zero padding on the right / bottom instead of all around (first-stage Downsample, model.py:83-85)."""
     _cuda(x, W, out)
     Nimg, H, Wd, Cin = x.shape
     Hl, Wl = H << upsample, Wd << upsample
-    Ho, Wo = (Hl - 1) // stride + 1, (Wl - 1) // stride + 1
+    if pad_rb:
+        assert stride == 2 and not upsample
+        Ho, Wo = (Hl - 2) // 2 + 1, (Wl - 2) // 2 + 1
+    else:
+        Ho, Wo = (Hl - 1) // stride + 1, (Wl - 1) // stride + 1
     p = GemmParams()
     p.A, p.W, p.out = x.data_ptr(), W.data_ptr(), out.data_ptr()
     p.bias = bias.data_ptr() if bias is not None else None
@@ -214,9 +219,10 @@ def conv3x3(x, W, out, bias=None, rowadd=None, residual=None, stride=1, upsample
     p.ldr = residual.stride(-2) if residual is not None else 0
     p.ld_rowadd = ld_rowadd if ld_rowadd is not None else (rowadd.stride(0) if rowadd is not None else 0)
     p.rows_per_batch = Ho * Wo
-    p.act = 0
+    p.act = act
     p.out_dtype = _DT[out.dtype]
     p.conv = 1
+    p.conv_pad = int(bool(pad_rb))
     p.Nimg, p.H, p.Wd, p.Cin = Nimg, H, Wd, Cin
     p.stride, p.upsample = stride, upsample
     if upsample:   # scratch for the materialised nearest-x2 input of the tcgen05 path
@@ -299,6 +305,26 @@ def cfg_dpmpp_step(x, eps, coef, scale, cfg, m_prev, x_next, x0_out=None):
     _count()
 
 
+def softmax_rows(S, P, scale):
+    """P[r, :] = softmax(S[r, :] * scale); S fp32 [rows, n], P fp16 [rows, n] (row strides taken from the tensors)."""
+    _cuda(S, P)
+    assert S.dtype == torch.float32 and P.dtype == torch.float16 and S.stride(-1) == 1 and P.stride(-1) == 1
+    rows, n = S.shape
+    _lib.check(_lib.load().anysd_softmax_rows_f32(_ptr(S), S.stride(0), _ptr(P), P.stride(0), rows, n, float(scale), _stream()), "softmax_rows")
+    _count()
+
+
+def gaussian_posterior(moments, noise=None, sample=None, logvar=None, scale=1.0):
+    """DiagonalGaussianDistribution pieces from fp32 NCHW moments [B, 2Z, H, W]; sample = scale * (mean + std * noise)."""
+    _cuda(moments)
+    assert moments.dtype == torch.float32 and moments.is_contiguous()
+    B = moments.shape[0]
+    zhw = moments.numel() // (2 * B)
+    _lib.check(_lib.load().anysd_gaussian_posterior_f32(_ptr(moments), _ptr(noise), _ptr(sample), _ptr(logvar), float(scale), B, zhw, _stream()),
+               "gaussian_posterior")
+    _count()
+
+
 # ---- training step (SURVEY.md a24): thin wrappers, same conventions as above -------------------------------------
 def q_sample(x0, noise, t, sqrt_acp, sqrt_1m_acp, out):
     _cuda(x0, noise, t, out)
@@ -308,14 +334,15 @@ def q_sample(x0, noise, t, sqrt_acp, sqrt_1m_acp, out):
     _count()
 
 
-def mse_loss(pred, target, d_pred, loss, grad_scale=1.0):
-    """pred/target fp32 NCHW; d_pred fp16 [N, HW, Cpad]; loss: 1-element fp32 tensor."""
+def mse_loss(pred, target, d_pred, loss, grad_scale=1.0, grad_scale_dev=None):
+    """pred/target fp32 NCHW; d_pred fp16 [N, HW, Cpad]; loss: 1-element fp32 tensor; grad_scale_dev: optional device
+    scalar multiplied into the gradient (the dynamic loss scale)."""
     _cuda(pred, target, d_pred, loss)
     N, Cc = pred.shape[0], pred.shape[1]
     HW = pred.numel() // (N * Cc)
     ws = torch.empty(_lib.load().anysd_mse_workspace_bytes() // 4, dtype=torch.float32, device=pred.device)
-    _lib.check(_lib.load().anysd_mse_loss_f32(_ptr(pred), _ptr(target), N, Cc, HW, d_pred.shape[-1], float(grad_scale), _ptr(d_pred),
-                                              _ptr(loss), _ptr(ws), ws.numel() * 4, _stream()), "mse_loss")
+    _lib.check(_lib.load().anysd_mse_loss_f32(_ptr(pred), _ptr(target), N, Cc, HW, d_pred.shape[-1], float(grad_scale), _ptr(grad_scale_dev),
+                                              _ptr(d_pred), _ptr(loss), _ptr(ws), ws.numel() * 4, _stream()), "mse_loss")
     _count(2)
 
 
@@ -495,8 +522,44 @@ def scatter_add_rows(src, idx, table_grad, alpha=1.0):
     _count()
 
 
+def _check_flat_f32(*ts):
+    """The optimizer kernels take raw pointers and element counts: anything but dense fp32 on one device would be read and
+    written out of bounds without an error."""
+    dev = ts[0].device
+    for t in ts:
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev or t.numel() != ts[0].numel():
+            raise ValueError("anysd_b200 optimizer kernels need contiguous float32 tensors of equal size on one device "
+                             f"(got {t.dtype}, contiguous={t.is_contiguous()}, {t.device}, {t.numel()} vs {ts[0].numel()} elements)")
+
+
+def grad_check_(grad, scaler):
+    """scaler[3] = 1 when any element of the flat fp32 gradient buffer is inf / nan."""
+    _cuda(grad, scaler)
+    _check_flat_f32(grad)
+    _lib.check(_lib.load().anysd_grad_check_f32(_ptr(grad), grad.numel(), _ptr(scaler), _stream()), "grad_check")
+    _count()
+
+
+def adamw_scaled_(param, grad, exp_avg, exp_avg_sq, scaler, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, inv_world=1.0):
+    """AdamW over flat fp32 buffers under the device-side loss scaler (skipped when scaler[3] != 0)."""
+    _cuda(param, grad, exp_avg, exp_avg_sq, scaler)
+    _check_flat_f32(param, grad, exp_avg, exp_avg_sq)
+    _lib.check(_lib.load().anysd_adamw_scaled_f32(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr),
+                                                  float(beta1), float(beta2), float(eps), float(weight_decay), float(inv_world), _ptr(scaler),
+                                                  _stream()), "adamw_scaled")
+    _count()
+
+
+def loss_scale_update_(scaler, growth=2.0, backoff=0.5, interval=2000):
+    _cuda(scaler)
+    _lib.check(_lib.load().anysd_loss_scale_update_f32(_ptr(scaler), float(growth), float(backoff), int(interval), _stream()),
+               "loss_scale_update")
+    _count()
+
+
 def adamw_(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
     _cuda(param, grad, exp_avg, exp_avg_sq)
+    _check_flat_f32(param, grad, exp_avg, exp_avg_sq)
     _lib.check(_lib.load().anysd_adamw_f32(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr),
                                            float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale),
                                            _stream()), "adamw")

@@ -170,8 +170,11 @@ def cpu_arm(latent, ddim_steps, scale, n_steps_sample=3):
                 return out
 
             shim.apply_model = timed_apply
-            ref_sampler(shim).sample(S, 1, (4, latent, latent), cond, verbose=False, x_T=x_T, eta=0.0,
-                                     unconditional_guidance_scale=scale, unconditional_conditioning=uncond)
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):      # the reference prints its banner on stdout; ours carries ONE JSON line
+                ref_sampler(shim).sample(S, 1, (4, latent, latent), cond, verbose=False, x_T=x_T, eta=0.0,
+                                         unconditional_guidance_scale=scale, unconditional_conditioning=uncond)
             what = "the reference's own ldm UNetModel + DDIMSampler (oracle/_ref staged sources"
         else:
             kind = "port"

@@ -117,6 +117,8 @@ typedef struct {
     int upsample;           /* conv: 1 = nearest x2 before the conv */
     void* workspace;        /* optional scratch (conv with upsample: >= Nimg*2H*2W*Cin fp16), may be NULL */
     size_t workspace_bytes;
+    int conv_pad;           /* conv: 0 = zero pad 1 on every side; 1 = pad right / bottom only (the first-stage Downsample,
+                               ldm/modules/diffusionmodules/model.py:83-85: F.pad(x, (0,1,0,1)) + conv3x3 stride 2 pad 0) */
 } anysd_gemm_params;
 int anysd_gemm_f16(const anysd_gemm_params* p, anysd_stream_t stream);
 
@@ -181,6 +183,19 @@ int anysd_cfg_plms_step_f32(const float* x, const float* eps, const float* coef,
 int anysd_cfg_dpmpp_step_f32(const float* x, const float* eps, const float* coef, float guidance_scale, int cfg, float* m_prev,
                              float* x_next, float* x0_out, long long n_per_batch, int B, anysd_stream_t stream);
 
+/* ==== first stage: AutoencoderKL encode / decode run on the kernels above; two helpers ==============
+ * AttnBlock (ldm/modules/diffusionmodules/model.py:176-203) has ONE head of width C (512 in the SD autoencoder): wider than
+ * the attention tile, so it runs as S = q k^T (anysd_gemm_f16, fp32 out) -> P = softmax(S * scale) (this kernel, fp16) ->
+ * O = P v (anysd_gemm_f16).  S: fp32 [rows, ld_s], P: fp16 [rows, ld_p], n valid columns. */
+int anysd_softmax_rows_f32(const float* S, long long ld_s, void* P, long long ld_p, int rows, int n, float scale,
+                           anysd_stream_t stream);
+/* DiagonalGaussianDistribution (ldm/modules/distributions/distributions.py:24-62) from the moments [B, 2Z, HW] (fp32 NCHW):
+ * logvar = clamp(moments[:, Z:], -30, 20); sample = scale * (mean + exp(0.5 logvar) * noise), noise NULL: scale * mean (the
+ * mode); scale = get_first_stage_encoding's scale_factor (ddpm.py), 1 for the plain distribution.
+ * sample / logvar: fp32 [B, Z, HW], either may be NULL. */
+int anysd_gaussian_posterior_f32(const float* moments, const float* noise, float* sample, float* logvar, float scale,
+                                 int B, long long z_hw, anysd_stream_t stream);
+
 /* ==== training step (train.py:629-710) =====================================================
  * The reference back-propagates mse_loss(MoE(...), noise) through the frozen UNet with torch autograd
  * (train.py:694-703); trainables are the adapter experts, the router and the task-embedding table
@@ -195,10 +210,12 @@ int anysd_q_sample_f32(const float* x0, const float* noise, const long long* t, 
 
 /* F.mse_loss(pred.float(), target.float(), "mean") (train.py:696) and its gradient.  pred/target fp32 NCHW
  * [N, C, HW]; *loss = mean; d_pred fp16 NHWC [N, HW, Cpad] = grad_scale * 2 (pred - target) / numel with zero
- * padding channels (the layout the output conv's backward contraction consumes).  Deterministic two-stage sum. */
+ * padding channels (the layout the output conv's backward contraction consumes).  Deterministic two-stage sum.
+ * grad_scale_dev (may be NULL): one more factor read from device memory -- the dynamic loss scale (see below). */
 size_t anysd_mse_workspace_bytes(void);
 int anysd_mse_loss_f32(const float* pred, const float* target, int N, int C, int HW, int Cpad, float grad_scale,
-                       void* d_pred, float* loss, void* workspace, size_t workspace_bytes, anysd_stream_t stream);
+                       const float* grad_scale_dev, void* d_pred, float* loss, void* workspace, size_t workspace_bytes,
+                       anysd_stream_t stream);
 
 /* GEGLU (attention.py:49-56) un-fused for training: pre [M, 2*inner] fp16 with (a_j, gate_j) interleaved (the
  * packing of anysd_gemm_f16 act = 2), out[m, j] = a_j * gelu(gate_j); backward writes d_pre in the same layout. */
@@ -301,6 +318,19 @@ int anysd_scatter_add_rows_f32(const float* src, const long long* idx, int rows,
 int anysd_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                     anysd_stream_t stream);
+
+/* Mixed-precision step control without host synchronisation (what accelerate's GradScaler does around train.py:694-709).
+ * scaler = 4 floats on the device: {loss scale, growth tracker, optimizer steps taken, found_inf}.
+ *   grad_check        found_inf = 1 when any element of grad[0..n) is inf / nan (run after the gradient all-reduce)
+ *   adamw_scaled      AdamW over one flat fp32 buffer; a no-op when found_inf; step number = steps taken + 1; the gradient
+ *                     is multiplied by inv_world / loss scale on the fly (the 1/world of the DDP mean, train.py:536)
+ *   loss_scale_update found_inf ? (scale *= backoff, tracker = 0) : (steps += 1; ++tracker == interval -> scale *= growth);
+ *                     then found_inf = 0 */
+int anysd_grad_check_f32(const float* grad, long long n, float* scaler, anysd_stream_t stream);
+int anysd_adamw_scaled_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                           float beta1, float beta2, float eps, float weight_decay, float inv_world, const float* scaler,
+                           anysd_stream_t stream);
+int anysd_loss_scale_update_f32(float* scaler, float growth, float backoff, int interval, anysd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -33,8 +33,20 @@ from .unet_oracle import _count, timestep_embedding
 LOG2E = 1.4426950408889634
 
 
+# Precision-lever experiments (tests/experiments/precision_levers.py): which rounding points to drop.
+#   "weights"   False = exact fp32 weights (what a hi + lo split-weight contraction, 2 passes, would give)
+#   "residual"  False = the residual stream (outputs of every residual-add epilogue, conv / proj_in outputs feeding it) in fp32
+#   "acts"      False = no activation rounding at all
+POLICY = {"weights": True, "residual": True, "acts": True}
+
+
 def r16(t):
-    return t.to(torch.float16).to(torch.float32)
+    return t.to(torch.float16).to(torch.float32) if POLICY["acts"] else t
+
+
+def rres(t):
+    """Rounding of a residual-stream tensor."""
+    return r16(t) if POLICY["residual"] else t
 
 
 _W16 = {}
@@ -47,8 +59,12 @@ def _w(sd, k):
     if t is None or t.shape != sd[k].shape:
         if len(_W16) > 4096:
             _W16.clear()
-        t = _W16[ck] = r16(sd[k])
+        t = _W16[ck] = sd[k].to(torch.float16).to(torch.float32) if POLICY["weights"] else sd[k]
     return t
+
+
+def _wr(w):
+    return w.to(torch.float16).to(torch.float32) if POLICY["weights"] else w
 
 
 def _lin(x, w16, b=None):
@@ -84,13 +100,13 @@ def _attention(sd, p, x, ctx, heads, residual):
     d = c // heads
     aux = d % 16 == 8
     wq = sd[p + "to_q.weight"]
-    wq = r16(wq * (d ** -0.5 * LOG2E)) if aux else r16(wq)
+    wq = _wr(wq * (d ** -0.5 * LOG2E)) if aux else _wr(wq)
     src = x if ctx is None else ctx
     q = r16(_lin(x, wq))
     k = r16(_lin(src, _w(sd, p + "to_k.weight")))
     v = r16(_lin(src, _w(sd, p + "to_v.weight")))
     a = _attn_core(q, k, v, heads, d, aux)
-    return r16(_lin(a, _w(sd, p + "to_out.0.weight"), sd[p + "to_out.0.bias"]) + residual)
+    return rres(_lin(a, _w(sd, p + "to_out.0.weight"), sd[p + "to_out.0.bias"]) + residual)
 
 
 def _block(sd, p, t, ctx, heads):
@@ -103,7 +119,7 @@ def _block(sd, p, t, ctx, heads):
     g = _lin(ln3, _w(sd, p + "ff.net.0.proj.weight"), sd[p + "ff.net.0.proj.bias"])
     a, gate = g.chunk(2, dim=-1)
     ffh = r16(a * F.gelu(gate))
-    return r16(_lin(ffh, _w(sd, p + "ff.net.2.weight"), sd[p + "ff.net.2.bias"]) + t3)
+    return rres(_lin(ffh, _w(sd, p + "ff.net.2.weight"), sd[p + "ff.net.2.bias"]) + t3)
 
 
 def _spatial_transformer(sd, p, h, ctx, heads_of):
@@ -111,7 +127,7 @@ def _spatial_transformer(sd, p, h, ctx, heads_of):
     g = _gn(h, sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-6, False)
     tok = g.permute(0, 2, 3, 1).reshape(b, hh * ww, c)
     w_in = sd[p + "proj_in.weight"]
-    t = r16(_lin(tok, r16(w_in.reshape(w_in.shape[0], -1)), sd[p + "proj_in.bias"]))
+    t = rres(_lin(tok, _wr(w_in.reshape(w_in.shape[0], -1)), sd[p + "proj_in.bias"]))
     heads = heads_of(t.shape[-1])
     depth = 0
     while (p + f"transformer_blocks.{depth}.norm1.weight") in sd:
@@ -120,7 +136,7 @@ def _spatial_transformer(sd, p, h, ctx, heads_of):
         depth += 1
     w_out = sd[p + "proj_out.weight"]
     res = h.permute(0, 2, 3, 1).reshape(b, hh * ww, c)
-    o = r16(_lin(t, r16(w_out.reshape(w_out.shape[0], -1)), sd[p + "proj_out.bias"]) + res)
+    o = rres(_lin(t, _wr(w_out.reshape(w_out.shape[0], -1)), sd[p + "proj_out.bias"]) + res)
     return o.reshape(b, hh, ww, c).permute(0, 3, 1, 2)
 
 
@@ -130,10 +146,10 @@ def _resblock(sd, p, x, emb_rows):
     b = _gn(h1, sd[p + "out_layers.0.weight"], sd[p + "out_layers.0.bias"], 1e-5, True)
     if (p + "skip_connection.weight") in sd:
         w = sd[p + "skip_connection.weight"]
-        res = r16(F.conv2d(x, r16(w), sd[p + "skip_connection.bias"], padding=w.shape[-1] // 2))
+        res = rres(F.conv2d(x, _wr(w), sd[p + "skip_connection.bias"], padding=w.shape[-1] // 2))
     else:
         res = x
-    return r16(F.conv2d(b, _w(sd, p + "out_layers.3.weight"), sd[p + "out_layers.3.bias"], padding=1) + res)
+    return rres(F.conv2d(b, _w(sd, p + "out_layers.3.weight"), sd[p + "out_layers.3.bias"], padding=1) + res)
 
 
 def _run_block(sd, p, h, semb, ctx, heads_of):
@@ -147,10 +163,10 @@ def _run_block(sd, p, h, semb, ctx, heads_of):
         elif (q + "transformer_blocks.0.norm1.weight") in sd:
             h = _spatial_transformer(sd, q, h, ctx, heads_of)
         elif (q + "op.weight") in sd:
-            h = r16(F.conv2d(h, _w(sd, q + "op.weight"), sd[q + "op.bias"], stride=2, padding=1))
+            h = rres(F.conv2d(h, _w(sd, q + "op.weight"), sd[q + "op.bias"], stride=2, padding=1))
         elif (q + "conv.weight") in sd:
             h = F.interpolate(h, scale_factor=2, mode="nearest")
-            h = r16(F.conv2d(h, _w(sd, q + "conv.weight"), sd[q + "conv.bias"], padding=1))
+            h = rres(F.conv2d(h, _w(sd, q + "conv.weight"), sd[q + "conv.bias"], padding=1))
         else:
             break
         j += 1
@@ -177,7 +193,7 @@ def unet_forward(sd, x, timesteps, context=None, y=None, *, num_heads=-1, num_he
     h = r16(x.float())
     for i in range(n_in):
         if i == 0:
-            h = r16(F.conv2d(h, _w(sd, "input_blocks.0.0.weight"), sd["input_blocks.0.0.bias"], padding=1))
+            h = rres(F.conv2d(h, _w(sd, "input_blocks.0.0.weight"), sd["input_blocks.0.0.bias"], padding=1))
         else:
             h = _run_block(sd, f"input_blocks.{i}.", h, semb, ctx, heads_of)
         hs.append(h)

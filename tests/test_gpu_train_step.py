@@ -177,6 +177,42 @@ def test_c4_training_step_sd15_geometry():
         assert v < (ROUTER_TOL if k.startswith("router") else 3e-2), (k, v)
 
 
+def test_overflow_step_is_skipped_and_scale_adapts():
+    """fp16 activation gradients under a loss scale: a step whose gradients overflow must not touch the
+    parameters or the AdamW moments and must halve the scale (GradScaler semantics, kept on the device -- no host sync in
+    ``step``); clean steps advance the step count and grow the scale after ``growth_interval`` of them."""
+    from anyedit_b200.training import AdapterTrainer
+    moe, sd, asd, cfg, b, acp = _setup("tiny_a", 11, E=3, T=6, B=2, hw=16, n_vis=5)
+    c = _cuda(b)
+    args = (c["latents"], c["noise"], c["t"], c["image_latent"], c["text"], c["vis"], c["code"])
+    tr = AdapterTrainer(moe, lr=1e-2, loss_scale=2.0 ** 40)                 # 2^40 * dL/dpred overflows fp16 at once
+    before = {k: v.detach().clone() for k, v in tr.trainables().items()}
+    loss, _ = tr.step(*args)
+    assert torch.isfinite(loss).all()
+    assert tr.step_count == 0 and tr.loss_scale == 2.0 ** 39
+    assert all(torch.equal(before[k], v.detach()) for k, v in tr.trainables().items())
+    assert float(tr._flat["M"].abs().max()) == 0.0 and float(tr._flat["V"].abs().max()) == 0.0
+    # the packed adapter tensors a sampler would use are still the old ones, bit for bit
+    tr2 = AdapterTrainer(moe, lr=1e-2, loss_scale=256.0, growth_interval=2)
+    for _ in range(2):
+        tr2.step(*args)
+    assert tr2.step_count == 2 and tr2.loss_scale == 512.0
+    moved = [k for k, v in tr2.trainables().items() if not torch.equal(before[k], v.detach())]
+    assert len(moved) == len(before), sorted(set(before) - set(moved))
+    assert all(torch.isfinite(v).all() for v in tr2.trainables().values())
+    # a static scale never moves
+    tr3 = AdapterTrainer(moe, lr=1e-2, loss_scale=128.0, dynamic_loss_scale=False)
+    tr3.step(*args)
+    assert tr3.loss_scale == 128.0 and tr3.step_count == 1
+    # fp16 / strided tensors must be refused by the raw-pointer optimizer kernels, not silently corrupted (ADVICE r1)
+    from anyedit_b200 import ops
+    p = torch.zeros(8, 8, device="cuda")
+    with pytest.raises(ValueError):
+        ops.adamw_(p.half(), p, p.clone(), p.clone(), 1, 1e-3)
+    with pytest.raises(ValueError):
+        ops.adamw_(p.t(), p, p.clone(), p.clone(), 1, 1e-3)
+
+
 def test_training_two_rank_nccl(tmp_path):
     """config 4 is data parallel over 8 GPUs: 2 ranks (skipped on a 1-GPU box) each back-propagate half of a 4-request
     batch, all-reduce the trainables' gradients over NCCL and step; both ranks end with identical parameters, equal

@@ -203,6 +203,12 @@ def test_gradient_allreduce_two_rank_gloo(tmp_path):
         "g = [torch.full((5, 3), float(r + 1)), torch.arange(4.0) * (r + 1), None]\n"
         "w = D.allreduce_sum_(g)\n"
         "assert w == 2 and torch.equal(g[0], torch.full((5, 3), 3.0)) and torch.equal(g[1], torch.arange(4.0) * 3)\n"
+        "# bucketed form used by AdapterTrainer.step: regions of ONE flat buffer reduced as they complete, waited at the end\n"
+        "flat = torch.arange(10.0) * (r + 1)\n"
+        "works = [D.allreduce_sum_async(flat[6:10]), D.allreduce_sum_async(flat[0:6])]\n"
+        "assert D.world_size() == 2 and all(x is not None for x in works)\n"
+        "for x in works: x.wait()\n"
+        "assert torch.equal(flat, torch.arange(10.0) * 3)\n"
         "if r == 0: print('OK')\n"
         "dist.destroy_process_group()\n")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
