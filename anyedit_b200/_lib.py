@@ -24,6 +24,7 @@ class GemmParams(C.Structure):
         ("stride", C.c_int), ("upsample", C.c_int),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("conv_pad", C.c_int),
+        ("stats", C.c_void_p), ("stats_images", C.c_int),
     ]
 
 
@@ -81,6 +82,8 @@ SIGNATURES = {
     "anysd_groupnorm_nhwc_f16": (_I, [_VP, _I, _VP, _I, _VP, _VP, _VP, _I, _I, _I, _F, _I, _VP, _SZ, _VP]),
     "anysd_layernorm_f16": (_I, [_VP, _VP, _VP, _VP, _LL, _I, _F, _VP]),
     "anysd_gemm_f16": (_I, [C.POINTER(GemmParams), _VP]),
+    "anysd_gemm_stats_slabs": (_I, [C.POINTER(GemmParams)]),
+    "anysd_groupnorm_apply_nhwc_f16": (_I, [_VP, _I, _VP, _I, _VP, _I, _VP, _VP, _VP, _I, _I, _I, _F, _I, _VP, _SZ, _VP]),
     "anysd_attention_f16": (_I, [C.POINTER(AttnParams), _VP]),
     "anysd_cfg_ddim_step_f32": (_I, [_VP, _VP, _VP, _VP, _F, _I, _I, _VP, _VP, _LL, _I, _VP]),
     "anysd_cfg3_ddim_step_f32": (_I, [_VP, _VP, _VP, _VP, _F, _F, _VP, _VP, _LL, _I, _VP]),
@@ -88,6 +91,8 @@ SIGNATURES = {
     "anysd_cfg_dpmpp_step_f32": (_I, [_VP, _VP, _VP, _F, _I, _VP, _VP, _VP, _LL, _I, _VP]),
     "anysd_softmax_rows_f32": (_I, [_VP, _LL, _VP, _LL, _I, _I, _F, _VP]),
     "anysd_gaussian_posterior_f32": (_I, [_VP, _VP, _VP, _VP, _F, _I, _LL, _VP]),
+    "anysd_embed_tokens_f16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "anysd_attention_small_f16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _VP]),
     # ---- training step ----
     "anysd_q_sample_f32": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _LL, _VP]),
     "anysd_mse_workspace_bytes": (_SZ, []),

@@ -10,6 +10,7 @@ int launch_gemm_tc5(const anysd_gemm_params* q, cudaStream_t st);
 bool tc5_supported(const anysd_gemm_params* q);
 int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st);
 bool tc5p_supported(const anysd_gemm_params* q);
+int tc5p_stats_slabs(const anysd_gemm_params* q);
 }
 
 using namespace anysd;
@@ -22,7 +23,7 @@ extern "C" int anysd_gemm_f16(const anysd_gemm_params* p, anysd_stream_t stream)
                   "gemm: K=%d and ldw=%d must be multiples of 8 with ldw >= K", p->K, p->ldw);
     ANYSD_REQUIRE(((uintptr_t)p->A % 16) == 0 && ((uintptr_t)p->W % 16) == 0, ANYSD_EINVAL,
                   "gemm: A and W must be 16-byte aligned");
-    ANYSD_REQUIRE(p->act >= 0 && p->act <= 2, ANYSD_EINVAL, "gemm: bad act %d", p->act);
+    ANYSD_REQUIRE(p->act >= 0 && p->act <= 4, ANYSD_EINVAL, "gemm: bad act %d", p->act);
     ANYSD_REQUIRE(p->out_dtype == ANYSD_F16 || p->out_dtype == ANYSD_F32, ANYSD_EINVAL, "gemm: bad out dtype");
     const int n_out = (p->act == 2) ? p->N / 2 : p->N;
     ANYSD_REQUIRE(p->act != 2 || p->N % 2 == 0, ANYSD_EINVAL, "gemm: GEGLU needs an even N");
@@ -58,8 +59,17 @@ extern "C" int anysd_gemm_f16(const anysd_gemm_params* p, anysd_stream_t stream)
     const bool allow_p = !force || !strcmp(force, "tc5p");
     const bool allow_1 = !force || !strcmp(force, "tc5");
     if (allow_p && tc5p_supported(p)) return launch_gemm_tc5p(p, (cudaStream_t)stream);
+    ANYSD_REQUIRE(p->stats == nullptr, ANYSD_EUNSUPPORTED, "gemm: output statistics need the persistent tcgen05 path");
     ANYSD_REQUIRE(!(p->conv && p->conv_pad), ANYSD_EUNSUPPORTED,
                   "conv3x3 with right/bottom padding needs the persistent tcgen05 path (fp16 output, Cin %% 64 == 0)");
     if ((allow_1 || (force && !strcmp(force, "tc5p"))) && tc5_supported(p)) return launch_gemm_tc5(p, (cudaStream_t)stream);
     return launch_gemm_mma(p, (cudaStream_t)stream);
+}
+
+extern "C" int anysd_gemm_stats_slabs(const anysd_gemm_params* p) {
+    if (p == nullptr || !p->A || !p->W || !p->out) return 0;
+    static const char* force = getenv("ANYSD_GEMM");
+    if (force && strcmp(force, "tc5p")) return 0;
+    if (p->conv && (p->Cin <= 0 || p->K != 9 * p->Cin)) return 0;
+    return tc5p_supported(p) ? tc5p_stats_slabs(p) : 0;
 }

@@ -187,9 +187,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_mma_kernel(const GemmArg
                         ((float*)p.out)[(size_t)m * p.ldo + no] = o;
                     continue;
                 }
-                if (p.act == 1) {
-                    v0 = silu_f(v0);
-                    v1 = silu_f(v1);
+                if (p.act != 0) {
+                    v0 = act_f(v0, p.act);
+                    v1 = act_f(v1, p.act);
                 }
                 if (p.residual) {
                     const __half* rp = p.residual + (size_t)m * p.ldr + n;

@@ -262,9 +262,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc5_kernel(const __grid_co
                     }
                     continue;
                 }
-                if (p.act == 1) {
+                if (p.act != 0) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) vv[j] = silu_f(vv[j]);
+                    for (int j = 0; j < 8; ++j) vv[j] = act_f(vv[j], p.act);
                 }
                 if (p.residual) {
                     const uint4 u = *reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.ldr + n);

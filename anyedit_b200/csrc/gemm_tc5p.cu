@@ -45,6 +45,9 @@ struct PArgs {
     int BW, BH, NB, tiles_w, tiles_h;
     int kb_per_tap, stride;
     int pad_lo;              // zero rows / columns before the image: 1 (pad 1 on every side) or 0 (right / bottom padding only)
+    // per-(32-row slab, channel) {sum, sum of squares} of the OUTPUT for the consumer's GroupNorm (anysd_gemm_params::stats)
+    float* stats;
+    int stats_hw, stats_spi, stats_nimg;     // rows per image, slabs per image (= hw / 32), image slots in the buffer
 };
 
 // ---- PTX wrappers (same forms as gemm_tc5.cu) -------------------------------------------------------
@@ -186,6 +189,22 @@ __device__ __forceinline__ float fast_erf(float x) {
     return copysignf(e, x);
 }
 __device__ __forceinline__ float p_gelu(float v) { return 0.5f * v * (1.0f + fast_erf(v * 0.70710678118654752440f)); }
+
+// Column sums of a 32 x 32 block held one ROW per lane (r[c] = this row's value in column c): after five exchange
+// rounds (16 + 8 + 4 + 2 + 1 shuffles) lane l holds the sum of column l over the 32 rows.  Fixed tree: deterministic.
+__device__ __forceinline__ float p_colsum32(float (&r)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = up ? r[i] : r[i + s];
+            const float keep = up ? r[i + s] : r[i];
+            r[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return r[0];
+}
 
 struct TileCoord {
     int n0, nw;          // first column, width (multiple of 16, <= 256)
@@ -481,6 +500,12 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (p.act == 1) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+                        } else if (p.act == 3) {              // nn.GELU() (CLIP-H MLP, Resampler FeedForward)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = p_gelu(v[i]);
+                        } else if (p.act == 4) {              // QuickGELU (CLIP-L MLP)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = quick_gelu_f(v[i]);
                         }
                     }
                     // combine with the prefetched residual in place; 128-byte swizzled staging row
@@ -496,6 +521,28 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             for (int i = 0; i < 8; ++i) vv[i] += rr[i];
                         }
                         *slot = pack8(vv);
+                    }
+                    if (p.stats != nullptr) {
+                        // GroupNorm statistics of what was just produced (fp32, before the fp16 rounding): per channel over
+                        // this warp's 32 rows.  Each (slab, channel) cell is written exactly once per launch, by one warp.
+                        const int r0 = CONV ? 0 : c.m0 + lg * 32;
+                        int img, sii;
+                        if (CONV) {
+                            const int ppi = p.BW * p.BH;                           // patch pixels per image (multiple of 32)
+                            img = c.tn * p.NB + sdn;
+                            sii = (c.th * p.tiles_w + c.tw) * (ppi >> 5) + (((lg * 32) % ppi) >> 5);
+                        } else {
+                            img = r0 / p.stats_hw;
+                            sii = (r0 - img * p.stats_hw) >> 5;
+                        }
+                        float q2[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) q2[i] = v[i] * v[i];
+                        const float s1 = p_colsum32(v, lane);
+                        const float s2 = p_colsum32(q2, lane);
+                        const int col = c.n0 + j * P_SUB + oc + lane;
+                        if (img < p.stats_nimg && col < p.N)
+                            reinterpret_cast<float2*>(p.stats)[((size_t)img * p.stats_spi + sii) * p.N + col] = make_float2(s1, s2);
                     }
                 }
                 p_fence_async_smem();                          // generic-proxy writes -> visible to the TMA store
@@ -575,6 +622,21 @@ static int p_pick_extent(int len, int cap) {
 
 int launch_upsample2x(const __half* src, __half* dst, int N, int H, int W, int C, cudaStream_t st);
 
+// GroupNorm statistics from the epilogue: possible when every 32-row slab of the output lies inside one image and the
+// conv patches tile the image exactly.  Returns the slabs per image (rows_per_batch / 32), 0 when not possible.
+static void p_conv_patch(const anysd_gemm_params* q, int* Ho, int* Wo, int* BW, int* BH, int* NB);
+int tc5p_stats_slabs(const anysd_gemm_params* q) {
+    if (q->act == 2 || q->out_dtype != ANYSD_F16) return 0;
+    const int hw = q->rows_per_batch;
+    if (hw <= 0 || hw % 32 != 0 || q->M % hw != 0) return 0;
+    if (q->conv) {
+        int Ho, Wo, BW, BH, NB;
+        p_conv_patch(q, &Ho, &Wo, &BW, &BH, &NB);
+        if (Ho * Wo != hw || (BW * BH) % 32 != 0 || Wo % BW != 0 || Ho % BH != 0) return 0;
+    }
+    return hw / 32;
+}
+
 bool tc5p_supported(const anysd_gemm_params* q) {
     if (q->out_dtype != ANYSD_F16) return false;
     if (q->N % 8 != 0 || q->K % 8 != 0) return false;
@@ -633,8 +695,30 @@ static int p_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     return check_launch(CONV ? "conv3x3 (tcgen05 persistent)" : "gemm (tcgen05 persistent)");
 }
 
+static void p_conv_patch(const anysd_gemm_params* q, int* Ho, int* Wo, int* BW, int* BH, int* NB) {
+    const int Hin = q->H << q->upsample, Win = q->Wd << q->upsample;
+    *Ho = q->conv_pad ? (Hin - 2) / 2 + 1 : (Hin - 1) / q->stride + 1;
+    *Wo = q->conv_pad ? (Win - 2) / 2 + 1 : (Win - 1) / q->stride + 1;
+    *BW = p_pick_extent(*Wo, 128);
+    *BH = p_pick_extent(*Ho, 128 / *BW);
+    *NB = 128 / (*BW * *BH);
+}
+
 int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
     PArgs a;
+    a.stats = nullptr;
+    a.stats_hw = a.stats_spi = a.stats_nimg = 0;
+    if (q->stats != nullptr) {
+        a.stats_spi = tc5p_stats_slabs(q);
+        if (a.stats_spi == 0 || q->stats_images <= 0) {
+            set_error("gemm: output statistics requested for a shape that cannot produce them (M=%d rows_per_batch=%d conv=%d act=%d); "
+                      "query anysd_gemm_stats_slabs first", q->M, q->rows_per_batch, q->conv, q->act);
+            return ANYSD_EUNSUPPORTED;
+        }
+        a.stats = q->stats;
+        a.stats_hw = q->rows_per_batch;
+        a.stats_nimg = q->stats_images;
+    }
     a.bias = q->bias;
     a.rowadd = q->rowadd;
     a.M = q->M;

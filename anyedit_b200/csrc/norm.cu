@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const uint4* __restric
 // y = [silu](x * a + b) over the rows of logical chunk (n, s); s_mean / s_rstd: this image's statistics in smem
 // COEF_SMEM: per-channel a = rstd*gamma, b = beta - mean*a were staged in shared memory (coef[0..C) = a, coef[C..2C) = b)
 // by the caller and are read per use (frees 16 registers for loads in flight); otherwise they are built here.
-template <bool COEF_SMEM>
+template <bool COEF_SMEM, bool PIPE = false, int U = GN_U>
 __device__ __forceinline__ void gn_apply_block(const uint4* __restrict__ x1, const uint4* __restrict__ x2, int CV, int CV1, int R,
                                                int HW, int rows_per_block, int cpg, int n, int s, const float* s_mean,
                                                const float* s_rstd, const float* __restrict__ gamma,
@@ -177,15 +177,20 @@ __device__ __forceinline__ void gn_apply_block(const uint4* __restrict__ x1, con
     const uint4* base = first ? (x1 + (size_t)n * HW * CV1 + cv) : (x2 + (size_t)n * HW * CV2 + (cv - CV1));
     const int stride = first ? CV1 : CV2;
     uint4* out = y + (size_t)n * HW * CV + cv;
-    for (int row = row0 + r; row < row1; row += GN_U * R) {      // GN_U independent 16-byte loads in flight per thread
-        uint4 v[GN_U];
+    // Software pipeline over batches of GN_U rows per thread: the loads of batch k+1 are in flight while batch k goes
+    // through the FMA / MUFU / pack / store stretch, so a CTA never sits with an empty memory pipe (a chunk of one batch --
+    // the statistics chunking -- degenerates to load, compute, store).
+    const int step = U * R;
+    auto load = [&](uint4 (&v)[U], int row) {
 #pragma unroll
-        for (int u = 0; u < GN_U; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int rr = row + u * R;
             v[u] = rr < row1 ? __ldg(base + (size_t)rr * stride) : make_uint4(0u, 0u, 0u, 0u);
         }
+    };
+    auto process = [&](uint4 (&v)[U], int row) {
 #pragma unroll
-        for (int u = 0; u < GN_U; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int rr = row + u * R;
             float f[8];
             unpack8(v[u], f);
@@ -203,6 +208,23 @@ __device__ __forceinline__ void gn_apply_block(const uint4* __restrict__ x1, con
             }
             if (rr < row1) out[(size_t)rr * CV] = pack8(f);
         }
+    };
+    if (PIPE) {
+        uint4 va[U], vb[U];
+        int row = row0 + r;
+        load(va, row);
+        for (; row < row1; row += 2 * step) {
+            load(vb, row + step);
+            process(va, row);
+            load(va, row + 2 * step);
+            process(vb, row + step);
+        }
+    } else {
+        uint4 va[U];
+        for (int row = row0 + r; row < row1; row += step) {
+            load(va, row);
+            process(va, row);
+        }
     }
 }
 
@@ -218,6 +240,71 @@ __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const uint4* __restric
     }
     __syncthreads();
     gn_apply_block<false>(x1, x2, CV, CV1, R, HW, rows_per_block, cpg, n, blockIdx.x, s_mean, s_rstd, gamma, beta, fuse_silu, y, nullptr);
+}
+
+// ---- statistics that arrive from the producing contraction's epilogue (anysd_gemm_params::stats) ----------------------
+// stats1 [*, S, C1, 2] (+ stats2 [*, S, C2, 2] for a channel concat): {sum, sum of squares} per (image, 32-row slab, channel).
+// One CTA per (group, image): the S * cpg cells of the group are dealt to the threads in a fixed order, accumulated in double
+// and combined by a fixed smem tree -- deterministic and independent of the batch, like gn_fold.
+// Apply pass of the epilogue-statistics path: chunks of several row batches (the pass is elementwise, so its chunking is
+// free of the statistics' order constraints), per-channel a = rstd * gamma, b = beta - mean * a staged in shared memory.
+__global__ void __launch_bounds__(512, 2) gn_apply_coef_kernel(const uint4* __restrict__ x, int CV, int R, int HW, int rows_per_block, int G,
+                                                               int cpg, const float* __restrict__ meanrstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, int fuse_silu, uint4* __restrict__ y) {
+    extern __shared__ float coef[];                      // a[0..C) | b[0..C)
+    const int n = blockIdx.y, C = CV * 8;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const float a = meanrstd[((size_t)n * G + g) * 2 + 1] * gamma[c];
+        coef[c] = a;
+        coef[C + c] = beta[c] - meanrstd[((size_t)n * G + g) * 2] * a;
+    }
+    __syncthreads();
+    gn_apply_block<true, true, 4>(x, nullptr, CV, CV, R, HW, rows_per_block, cpg, n, blockIdx.x, nullptr, nullptr, gamma, beta, fuse_silu, y, coef);
+}
+
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float2* __restrict__ stats1, int C1, const float2* __restrict__ stats2, int C2,
+                                                          int S, int HW, int cpg, float eps, float* __restrict__ meanrstd) {
+    const int g = blockIdx.x, n = blockIdx.y, G = gridDim.x;
+    double a = 0.0, b = 0.0;
+    // thread t takes slabs t, t + 128, ...; the group's cpg channels of one slab are adjacent (cpg * 8 bytes): the loads of a
+    // slab are issued together (independent), the additions follow in channel order -- a fixed order per thread
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        for (int c0 = 0; c0 < cpg; c0 += 8) {
+            float2 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = g * cpg + c0 + j;
+                v[j] = make_float2(0.f, 0.f);
+                if (c0 + j < cpg)
+                    v[j] = c < C1 ? __ldg(stats1 + ((size_t)n * S + s) * C1 + c) : __ldg(stats2 + ((size_t)n * S + s) * C2 + (c - C1));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a += (double)v[j].x;
+                b += (double)v[j].y;
+            }
+        }
+    }
+    __shared__ double ra[128], rb[128];
+    ra[threadIdx.x] = a;
+    rb[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            ra[threadIdx.x] += ra[threadIdx.x + o];
+            rb[threadIdx.x] += rb[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double cnt = (double)HW * cpg;
+        const double mean = ra[0] / cnt;
+        double var = rb[0] / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        meanrstd[((size_t)n * G + g) * 2] = (float)mean;
+        meanrstd[((size_t)n * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
 }
 
 // One launch instead of two (cooperative: every CTA resident).  The N*S logical chunks -- the SAME chunks, thread
@@ -423,6 +510,34 @@ int anysd_groupnorm_nhwc_f16(const void* x1, int C1, const void* x2, int C2, con
     if (rc) return rc;
     gn_apply_kernel<<<dim3(S, N), g.T, 0, st>>>((const uint4*)x1, (const uint4*)x2, g.CV, g.CV1, g.R, HW, rpb, G, cpg,
                                                 meanrstd, gamma, beta, fuse_silu, (uint4*)y);
+    return check_launch("groupnorm apply");
+}
+
+int anysd_groupnorm_apply_nhwc_f16(const void* x, int C, const float* stats1, int C1, const float* stats2, int S, const float* gamma,
+                                   const float* beta, void* y, int N, int HW, int G, float eps, int fuse_silu, void* workspace,
+                                   size_t workspace_bytes, anysd_stream_t stream) {
+    ANYSD_REQUIRE(x && stats1 && gamma && beta && y && workspace, ANYSD_EINVAL, "groupnorm_apply: null pointer");
+    ANYSD_REQUIRE(N > 0 && HW > 0 && G > 0 && G <= 64 && C > 0 && C % G == 0 && C % 8 == 0 && C / 8 <= 1024, ANYSD_EINVAL,
+                  "groupnorm_apply: bad shape N=%d HW=%d C=%d G=%d", N, HW, C, G);
+    ANYSD_REQUIRE(C1 > 0 && C1 <= C && (C1 == C) == (stats2 == nullptr), ANYSD_EINVAL,
+                  "groupnorm_apply: stats2 must be given exactly when the first source covers fewer than C channels");
+    ANYSD_REQUIRE(S > 0 && S * 32 == HW, ANYSD_EINVAL, "groupnorm_apply: S=%d slabs of 32 rows must cover HW=%d", S, HW);
+    ANYSD_REQUIRE(workspace_bytes >= anysd_groupnorm_workspace_bytes(N, G, C), ANYSD_EINVAL, "groupnorm_apply: workspace too small");
+    const GnGeom g = gn_geom(C, 0);
+    const int cpg = C / G;
+    const int batch = 4 * g.R;                            // the apply kernel keeps 2 x 4 loads in flight per thread
+    // chunk = up to 8 row batches (software-pipelined inside the CTA) while the grid still fills the machine twice over
+    int nb = 8;
+    while (nb > 1 && (long long)N * cdiv(HW, (long long)batch * nb) < 2LL * sm_count()) nb >>= 1;
+    const int rpb = batch * nb;
+    const int Sx = cdiv(HW, rpb);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* meanrstd = (float*)workspace + (size_t)N * GN_MAX_SPLITS * G * 2;
+    gn_finalize_kernel<<<dim3(G, N), 128, 0, st>>>((const float2*)stats1, C1, (const float2*)stats2, C - C1, S, HW, cpg, eps, meanrstd);
+    int rc = check_launch("groupnorm finalize");
+    if (rc) return rc;
+    gn_apply_coef_kernel<<<dim3(Sx, N), g.T, (size_t)2 * C * sizeof(float), st>>>((const uint4*)x, g.CV, g.R, HW, rpb, G, cpg, meanrstd, gamma,
+                                                                                  beta, fuse_silu, (uint4*)y);
     return check_launch("groupnorm apply");
 }
 

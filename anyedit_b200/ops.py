@@ -149,8 +149,21 @@ def groupnorm_workspace(N, G=32, C=0, device="cuda"):
     return torch.zeros(nbytes // 4, dtype=torch.float32, device=device)   # completion counters start at zero
 
 
-def groupnorm(x1, gamma, beta, y, N, HW, eps, silu, ws, x2=None, G=32):
+def groupnorm(x1, gamma, beta, y, N, HW, eps, silu, ws, x2=None, G=32, stats=None):
+    """GroupNorm(+SiLU).  ``stats`` (GnStats of x1, from the contraction(s) that produced it): only the streaming apply pass
+    runs; otherwise the statistics are computed here."""
     _cuda(x1, y, ws)
+    if stats is not None and x2 is None and stats.S * 32 == HW:
+        Cc = x1.shape[-1]
+        parts = stats.parts
+        assert sum(c for _, c in parts) == Cc and len(parts) <= 2 and all(b.shape[0] >= N for b, _ in parts)
+        s2 = parts[1][0] if len(parts) == 2 else None
+        with _Traced("groupnorm", 0.0, f"N={N} HW={HW} C={Cc} epilogue-stats"):
+            _lib.check(_lib.load().anysd_groupnorm_apply_nhwc_f16(_ptr(x1), Cc, _ptr(parts[0][0]), parts[0][1], _ptr(s2), stats.S, _ptr(gamma),
+                                                              _ptr(beta), _ptr(y), N, HW, G, float(eps), int(bool(silu)), _ptr(ws),
+                                                              ws.numel() * 4, _stream()), "groupnorm_apply")
+        _count(2)
+        return
     C1 = x1.shape[-1]
     C2 = x2.shape[-1] if x2 is not None else 0
     with _Traced("groupnorm", 0.0, f"N={N} HW={HW} C={C1}+{C2}"):
@@ -170,9 +183,41 @@ def layernorm(x, gamma, beta, y, eps=1e-5):
     _count()
 
 
+_GN_EPILOGUE = os.environ.get("ANYSD_GN_EPILOGUE", "1")[:1] != "0"      # GroupNorm statistics from the producer's epilogue
+
+
+class GnStats:
+    """Epilogue statistics of one activation tensor: ``parts`` = [(fp32 [images, S, C_i, 2], C_i), ...] in channel order
+    (two parts for a channel concat), ``S`` = slabs per image."""
+    __slots__ = ("parts", "S")
+
+    def __init__(self, parts, S):
+        self.parts, self.S = parts, S
+
+
+def _want_stats(p, images, dev, reuse=None):
+    """Allocate the statistics buffer when the launch can fill it (anysd_gemm_stats_slabs); returns GnStats or None.
+    ``reuse``: a GnStats of the same geometry whose buffer is refilled (persistent outputs read by a captured graph)."""
+    if not _GN_EPILOGUE:
+        return None
+    S = _lib.load().anysd_gemm_stats_slabs(C.byref(p))
+    if S <= 0:
+        return None
+    slots = (images + 7) // 8 * 8            # >= the conv's images-per-tile rounding (at most 4 images share a 128-row tile)
+    if isinstance(reuse, GnStats) and reuse.S == S and tuple(reuse.parts[0][0].shape) == (slots, S, p.N, 2):
+        buf = reuse.parts[0][0]
+    else:
+        reuse = None
+        buf = torch.empty(slots, S, p.N, 2, dtype=torch.float32, device=dev)
+    p.stats, p.stats_images = buf.data_ptr(), slots
+    return reuse if reuse is not None else GnStats([(buf, p.N)], S)
+
+
 def gemm(A, W, out, bias=None, rowadd=None, rows_per_batch=0, residual=None, act=0, M=None, K=None, lda=None,
-         N=None, ldw=None, ld_rowadd=None):
-    """out[M, N'] = epilogue(A[M, K] @ W[N, K]^T); see anysd_gemm_params."""
+         N=None, ldw=None, ld_rowadd=None, stats_images=0):
+    """out[M, N'] = epilogue(A[M, K] @ W[N, K]^T); see anysd_gemm_params.
+    ``stats_images`` > 0 (with ``rows_per_batch`` = rows of one image): also produce the GroupNorm statistics of ``out`` in the
+    epilogue; returns a GnStats (None when the shape cannot)."""
     _cuda(A, W, out)
     p = GemmParams()
     p.A, p.W, p.out = A.data_ptr(), W.data_ptr(), out.data_ptr()
@@ -191,13 +236,15 @@ def gemm(A, W, out, bias=None, rowadd=None, rows_per_batch=0, residual=None, act
     p.act = act
     p.out_dtype = _DT[out.dtype]
     p.conv = 0
+    st = _want_stats(p, stats_images, out.device) if stats_images > 0 else None
     with _Traced("gemm", 2.0 * p.M * p.N * p.K, f"M={p.M} N={p.N} K={p.K} act={p.act} res={int(residual is not None)}"):
         _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "gemm")
     _count()
+    return st
 
 
 def conv3x3(x, W, out, bias=None, rowadd=None, residual=None, stride=1, upsample=0, ld_rowadd=None,
-            logical_cin=None, logical_cout=None, act=0, pad_rb=False):
+            logical_cin=None, logical_cout=None, act=0, pad_rb=False, stats=False):
     """x NHWC fp16 [N,H,W,Cin]; W fp16 [Cout, 9*Cin] ((ky,kx,ci) K order); out [N*Ho*Wo, Cout].
     pad_rb (stride 2 only): zero padding on the right / bottom instead of all around (first-stage Downsample, model.py:83-85)."""
     _cuda(x, W, out)
@@ -230,10 +277,11 @@ def conv3x3(x, W, out, bias=None, rowadd=None, residual=None, stride=1, upsample
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel() * 2
     # algorithmic FLOPs (trace only): zero-padded channels do not count
     fl = 2.0 * p.M * (logical_cout or p.N) * 9 * (logical_cin or Cin)
+    st = _want_stats(p, Nimg, out.device, reuse=stats) if stats else None
     with _Traced("conv3x3", fl, f"N={p.Nimg} {p.H}x{p.Wd} {p.Cin}->{p.N} s={p.stride} up={p.upsample} res={int(residual is not None)}"):
         _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "conv3x3")
     _count()
-    return Ho, Wo
+    return st if stats else (Ho, Wo)
 
 
 def attention(q, k, v, out, B, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o, q_bs=None, k_bs=None, v_bs=None,
@@ -322,6 +370,26 @@ def gaussian_posterior(moments, noise=None, sample=None, logvar=None, scale=1.0)
     zhw = moments.numel() // (2 * B)
     _lib.check(_lib.load().anysd_gaussian_posterior_f32(_ptr(moments), _ptr(noise), _ptr(sample), _ptr(logvar), float(scale), B, zhw, _stream()),
                "gaussian_posterior")
+    _count()
+
+
+def embed_tokens(ids, tok_table, pos_table, out):
+    """out[b*n + i] = tok_table[ids[b, i]] + pos_table[i]; ids int64 [B, n], fp16 tables, out fp16 [B*n, D]."""
+    _cuda(ids, tok_table, pos_table, out)
+    B, n = ids.shape
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and tok_table.dtype == torch.float16 and pos_table.dtype == torch.float16
+    assert tok_table.is_contiguous() and pos_table.is_contiguous() and pos_table.shape[0] >= n and out.is_contiguous()
+    _lib.check(_lib.load().anysd_embed_tokens_f16(_ptr(ids), _ptr(tok_table), _ptr(pos_table), _ptr(out), B, n, tok_table.shape[1],
+                                                  tok_table.shape[0], _stream()), "embed_tokens")
+    _count()
+
+
+def attention_small(q, k, v, out, B, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o, scale=None, causal=False):
+    """softmax(q k^T scale [+ causal mask]) v for short sequences (n_kv <= 256): the CLIP text tower."""
+    _cuda(q, k, v, out)
+    _lib.check(_lib.load().anysd_attention_small_f16(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o,
+                                                     float(scale if scale is not None else d ** -0.5), int(bool(causal)), _stream()),
+               "attention_small")
     _count()
 
 

@@ -211,8 +211,10 @@ class UNetModel(nn.Module):
                  num_heads_upsample=-1, use_scale_shift_norm=False, resblock_updown=False,
                  use_new_attention_order=False, use_spatial_transformer=False, transformer_depth=1,
                  context_dim=None, n_embed=None, legacy=True, disable_self_attentions=None,
-                 num_attention_blocks=None, disable_middle_self_attn=False, use_linear_in_transformer=False):
+                 num_attention_blocks=None, disable_middle_self_attn=False, use_linear_in_transformer=False,
+                 _encoder_only=False):
         super().__init__()
+        self._encoder_only = _encoder_only       # ControlNet (cldm.py:47-304): input blocks + middle block only
         if use_spatial_transformer:
             assert context_dim is not None, "use_spatial_transformer needs context_dim (cross-attention conditioning)"
         if context_dim is not None:
@@ -296,7 +298,7 @@ class UNetModel(nn.Module):
                 ds *= 2
         self.middle_block = _seq(_ResBlock(ch, D, ch), transformer(ch, num_heads, 0, middle=True), _ResBlock(ch, D, ch))
         self.output_blocks = nn.ModuleList([])
-        for level, mult in list(enumerate(channel_mult))[::-1]:
+        for level, mult in ([] if _encoder_only else list(enumerate(channel_mult))[::-1]):
             for i in range(self.num_res_blocks[level] + 1):
                 ich = chans.pop()
                 layers = [_ResBlock(ch + ich, D, model_channels * mult)]
@@ -308,7 +310,10 @@ class UNetModel(nn.Module):
                     layers.append(_Upsample(ch, ch))
                     ds //= 2
                 self.output_blocks.append(_seq(*layers))
-        self.out = _seq(_Param((ch,), kind="norm"), _Slot(), _Param((out_channels, model_channels, 3, 3), kind="conv", zero=True))
+        if _encoder_only:
+            del self.output_blocks
+        else:
+            self.out = _seq(_Param((ch,), kind="norm"), _Slot(), _Param((out_channels, model_channels, 3, 3), kind="conv", zero=True))
 
         self._pack = None
         self._pack_key = None
@@ -433,10 +438,14 @@ class UNetModel(nn.Module):
 
         P["input"] = [pack_block(b) for b in list(self.input_blocks)[1:]]
         P["middle"] = pack_block(self.middle_block)
-        P["output"] = [pack_block(b) for b in self.output_blocks]
+        P["output"] = [] if self._encoder_only else [pack_block(b) for b in self.output_blocks]
         P["emb_w"] = _h(torch.cat(emb_w, 0), dev)                 # all ResBlock emb_layers stacked: one GEMM
         P["emb_b"] = _f(torch.cat(emb_b, 0), dev)
         P["emb_total"] = off
+        if self._encoder_only:
+            self._pack_extra(P, dev)
+            self._pack, self._pack_key = P, key
+            return P
         P["out_gn_w"], P["out_gn_b"] = _f(self.out[0].weight, dev), _f(self.out[0].bias, dev)
         # output conv: rows padded to a multiple of 8 (zero filters) -> tcgen05 kernel with fp32 output
         self._cout_pad = (self.out_channels + 7) // 8 * 8
@@ -461,8 +470,10 @@ class UNetModel(nn.Module):
         """
         assert (y is not None) == (self.num_classes is not None), \
             "must specify y if and only if the model is class-conditional"
+        ctrl_nhwc = bool(getattr(control, "nhwc", False))        # anyedit_b200.cldm.ControlNet hands NHWC fp16 residuals over
         if control is not None:
-            control = [c if c.dtype in (torch.float32, torch.float16) else c.float() for c in control]
+            control = list(control) if ctrl_nhwc else [c if c.dtype in (torch.float32, torch.float16) else c.float() for c in control]
+        add_control = (lambda c, t: ops.add_(t, c)) if ctrl_nhwc else (lambda c, t: ops.add_nchw_into_nhwc(c.contiguous(), t))
         P = self.prepare()
         dev = x.device
         if dev.type != "cuda":
@@ -475,40 +486,9 @@ class UNetModel(nn.Module):
         f32 = dict(dtype=torch.float32, device=dev)
         ws = ops.groupnorm_workspace(N, 32, 0, dev)
 
-        # -- time / class / task embedding (openaimodel.py:767-772) --
-        D, mc = self.time_embed_dim, self.model_channels
-        temb = torch.empty(N, mc, **f16)
-        ops.timestep_embedding(timesteps.to(dev), temb)
-        e1 = torch.empty(N, D, **f16)
-        ops.gemm(temb, P["te0_w"], e1, bias=P["te0_b"], act=1)
-        emb_lin = torch.empty(N, D, **f32)
-        ops.gemm(e1, P["te2_w"], emb_lin, bias=P["te2_b"])
-        semb = torch.empty(N, D, **f16)
-        table, idx = None, None
-        if self.num_classes is not None:
-            table, idx = P["label"], y.to(device=dev, dtype=torch.int64).contiguous()
-        elif anysd is not None and anysd.get("task_table") is not None:
-            table, idx = anysd["task_table"], anysd["edit_code"]
-        ops.emb_finalize(emb_lin, semb, table, idx)
-        emb_all = torch.empty(N, P["emb_total"], **f32)
-        ops.gemm(semb, P["emb_w"], emb_all, bias=P["emb_b"])
-
-        # -- context (list = one tensor per transformer depth, attention.py:323-324) --
-        ctx_list = context if isinstance(context, (list, tuple)) else [context]
-        ctx16 = []
-        for c in ctx_list:
-            if c is None:
-                ctx16.append(None)
-                continue
-            assert c.shape[0] == N, "context batch must match x"
-            c = c.to(dev)
-            if c.dtype == torch.float16 and c.is_contiguous():
-                ctx16.append(c)
-            else:
-                c32 = c.float().contiguous()
-                t = torch.empty(c32.shape, **f16)
-                ops.cast_f16(c32, t)
-                ctx16.append(t)
+        mc = self.model_channels
+        emb_all = self._embeddings(P, N, timesteps, y, anysd, dev)
+        ctx16 = self._context16(context, N, dev)
         st = {"N": N, "ws": ws, "emb_all": emb_all, "ctx": ctx16, "anysd": anysd, "layer": 0, "xl": 0,
               "kvc": getattr(self, "_ctx_kv", None) if anysd is None else None}
 
@@ -522,7 +502,8 @@ class UNetModel(nn.Module):
         xin = torch.zeros(Nx, H, W, self._cin_pad, **f16) if self._cin_pad != Cin else torch.empty(Nx, H, W, Cin, **f16)
         ops.nchw_to_nhwc(x[:Nx].contiguous(), xin, 0)
         h = torch.empty(Nx, H, W, mc, **f16)
-        ops.conv3x3(xin, P["in_w"], h.view(-1, mc), bias=P["in_b"], logical_cin=Cin)
+        # every contraction whose output feeds a GroupNorm also emits that norm's statistics from its epilogue (h._gn)
+        h._gn = ops.conv3x3(xin, P["in_w"], h.view(-1, mc), bias=P["in_b"], logical_cin=Cin, stats=True)
         hs = [self._dup_rows(h) if share else h]
         for blk in P["input"]:
             if share:
@@ -540,22 +521,65 @@ class UNetModel(nn.Module):
             h = self._dup_rows(h)
         h = self._run(P["middle"], h, None, st)
         if control is not None:                                   # cldm.py:33-34
-            ops.add_nchw_into_nhwc(control.pop().contiguous(), h)
+            add_control(control.pop(), h)
+            h._gn = None                                          # changed in place: its epilogue statistics are stale
         for blk in P["output"]:
             skip = hs.pop()
             if control is not None and not only_mid_control:      # cldm.py:36-41
-                ops.add_nchw_into_nhwc(control.pop().contiguous(), skip)
+                add_control(control.pop(), skip)
+                skip._gn = None
             h = self._run(blk, h, skip, st)
         # -- head: GN -> SiLU -> conv3x3 (fp32 out), back to NCHW in x.dtype --
         Nn, Hh, Ww, C = h.shape
         a = torch.empty_like(h)
-        ops.groupnorm(h, P["out_gn_w"], P["out_gn_b"], a, N, Hh * Ww, 1e-5, True, ws)
+        ops.groupnorm(h, P["out_gn_w"], P["out_gn_b"], a, N, Hh * Ww, 1e-5, True, ws, stats=getattr(h, "_gn", None))
         o = torch.empty(N, Hh, Ww, self._cout_pad, **f32)
         ops.conv3x3(a, P["out_w"], o.view(-1, self._cout_pad), bias=P["out_b"], logical_cout=self.out_channels)
         out_dtype = x.dtype if x.dtype in (torch.float32, torch.float16) else torch.float32
         out = torch.empty(N, self.out_channels, Hh, Ww, dtype=out_dtype, device=dev)
         ops.nhwc_to_nchw(o, out)
         return out.to(x.dtype)
+
+    def _embeddings(self, P, N, timesteps, y, anysd, dev):
+        """time / class / task embedding (openaimodel.py:767-772) -> the stacked ResBlock ``emb_layers`` rows [N, sum Cout] fp32."""
+        f16, f32 = dict(dtype=torch.float16, device=dev), dict(dtype=torch.float32, device=dev)
+        D, mc = self.time_embed_dim, self.model_channels
+        temb = torch.empty(N, mc, **f16)
+        ops.timestep_embedding(timesteps.to(dev), temb)
+        e1 = torch.empty(N, D, **f16)
+        ops.gemm(temb, P["te0_w"], e1, bias=P["te0_b"], act=1)
+        emb_lin = torch.empty(N, D, **f32)
+        ops.gemm(e1, P["te2_w"], emb_lin, bias=P["te2_b"])
+        semb = torch.empty(N, D, **f16)
+        table, idx = None, None
+        if self.num_classes is not None:
+            table, idx = P["label"], y.to(device=dev, dtype=torch.int64).contiguous()
+        elif anysd is not None and anysd.get("task_table") is not None:
+            table, idx = anysd["task_table"], anysd["edit_code"]
+        ops.emb_finalize(emb_lin, semb, table, idx)
+        emb_all = torch.empty(N, P["emb_total"], **f32)
+        ops.gemm(semb, P["emb_w"], emb_all, bias=P["emb_b"])
+        return emb_all
+
+    @staticmethod
+    def _context16(context, N, dev):
+        """context (list = one tensor per transformer depth, attention.py:323-324) as fp16."""
+        ctx_list = context if isinstance(context, (list, tuple)) else [context]
+        ctx16 = []
+        for c in ctx_list:
+            if c is None:
+                ctx16.append(None)
+                continue
+            assert c.shape[0] == N, "context batch must match x"
+            c = c.to(dev)
+            if c.dtype == torch.float16 and c.is_contiguous():
+                ctx16.append(c)
+            else:
+                c32 = c.float().contiguous()
+                t = torch.empty(c32.shape, dtype=torch.float16, device=dev)
+                ops.cast_f16(c32, t)
+                ctx16.append(t)
+        return ctx16
 
     # ---- block executors ----------------------------------------------------------------------------
     def _run(self, blk, h, skip, st, share=False):
@@ -570,12 +594,12 @@ class UNetModel(nn.Module):
             elif kind == "down":
                 N, H, W, C = h.shape
                 o = torch.empty(N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, d["w"].shape[0], dtype=h.dtype, device=h.device)
-                ops.conv3x3(h, d["w"], o.view(-1, o.shape[-1]), bias=d["b"], stride=2)
+                o._gn = ops.conv3x3(h, d["w"], o.view(-1, o.shape[-1]), bias=d["b"], stride=2, stats=True)
                 h = o
             elif kind == "up":
                 N, H, W, C = h.shape
                 o = torch.empty(N, 2 * H, 2 * W, d["w"].shape[0], dtype=h.dtype, device=h.device)
-                ops.conv3x3(h, d["w"], o.view(-1, o.shape[-1]), bias=d["b"], upsample=1)
+                o._gn = ops.conv3x3(h, d["w"], o.view(-1, o.shape[-1]), bias=d["b"], upsample=1, stats=True)
                 h = o
         return h
 
@@ -587,23 +611,26 @@ class UNetModel(nn.Module):
         if skip is not None:
             x = torch.empty(N, H, W, cin, dtype=h.dtype, device=h.device)
             ops.concat_channels(h, skip, x)
+            ga, gb = getattr(h, "_gn", None), getattr(skip, "_gn", None)     # statistics of a concat = its parts' statistics
+            x._gn = ops.GnStats(ga.parts + gb.parts, ga.S) if (ga is not None and gb is not None and ga.S == gb.S) else None
         else:
             x = h
         assert x.shape[-1] == cin
         a = torch.empty_like(x)
-        ops.groupnorm(x, d["gn1_w"], d["gn1_b"], a, N, HW, 1e-5, True, st["ws"])
+        ops.groupnorm(x, d["gn1_w"], d["gn1_b"], a, N, HW, 1e-5, True, st["ws"], stats=getattr(x, "_gn", None))
         h1 = torch.empty(N, H, W, cout, dtype=h.dtype, device=h.device)
         emb = st["emb_all"]
-        ops.conv3x3(a, d["c1_w"], h1.view(-1, cout), bias=d["c1_b"], rowadd=emb[:, d["emb_off"]:], ld_rowadd=emb.stride(0))
+        g1 = ops.conv3x3(a, d["c1_w"], h1.view(-1, cout), bias=d["c1_b"], rowadd=emb[:, d["emb_off"]:], ld_rowadd=emb.stride(0),
+                         stats=True)
         b = torch.empty_like(h1)
-        ops.groupnorm(h1, d["gn2_w"], d["gn2_b"], b, N, HW, 1e-5, True, st["ws"])
+        ops.groupnorm(h1, d["gn2_w"], d["gn2_b"], b, N, HW, 1e-5, True, st["ws"], stats=g1)
         if "skip_w" in d:
             res = torch.empty(N * HW, cout, dtype=h.dtype, device=h.device)
             ops.gemm(x.view(-1, cin), d["skip_w"], res, bias=d["skip_b"])
         else:
             res = x.view(-1, cin)
         out = torch.empty(N, H, W, cout, dtype=h.dtype, device=h.device)
-        ops.conv3x3(b, d["c2_w"], out.view(-1, cout), bias=d["c2_b"], residual=res)
+        out._gn = ops.conv3x3(b, d["c2_w"], out.view(-1, cout), bias=d["c2_b"], residual=res, stats=True)
         return out
 
     def _attn(self, ad, xq, ctx, N, n_q, st, self_attn, residual, out, expert=False, q_pre=None):
@@ -652,6 +679,10 @@ class UNetModel(nn.Module):
         out = torch.empty((2 * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         out[: t.shape[0]].copy_(t)
         out[t.shape[0]:].copy_(t)
+        g = getattr(t, "_gn", None)
+        if g is not None:                                       # per-image epilogue statistics travel with the images
+            n = t.shape[0]
+            out._gn = ops.GnStats([(torch.cat([b[:n], b[:n]]), c) for b, c in g.parts], g.S)
         return out
 
     def _transformer(self, d, h, st, share=False):
@@ -665,7 +696,7 @@ class UNetModel(nn.Module):
         inner = d["inner"]
         dev = h.device
         g = torch.empty_like(h)
-        ops.groupnorm(h, d["gn_w"], d["gn_b"], g, N, n, 1e-6, False, st["ws"])
+        ops.groupnorm(h, d["gn_w"], d["gn_b"], g, N, n, 1e-6, False, st["ws"], stats=getattr(h, "_gn", None))
         t = torch.empty(M, inner, dtype=torch.float16, device=dev)
         ops.gemm(g.view(M, C), d["pin_w"], t, bias=d["pin_b"])
         for i, b in enumerate(d["blocks"]):
@@ -704,5 +735,5 @@ class UNetModel(nn.Module):
             ops.gemm(ffh, b["ff2_w"], t4, bias=b["ff2_b"], residual=t3)
             t = t4
         out = torch.empty(N, H, W, C, dtype=torch.float16, device=dev)
-        ops.gemm(t, d["pout_w"], out.view(M, C), bias=d["pout_b"], residual=h.view(M, C))
+        out._gn = ops.gemm(t, d["pout_w"], out.view(M, C), bias=d["pout_b"], residual=h.view(M, C), rows_per_batch=n, stats_images=N)
         return out

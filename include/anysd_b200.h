@@ -85,6 +85,13 @@ size_t anysd_groupnorm_workspace_bytes(int N, int G, int C);
 int anysd_groupnorm_nhwc_f16(const void* x1, int C1, const void* x2, int C2, const float* gamma,
                              const float* beta, void* y, int N, int HW, int G, float eps, int fuse_silu,
                              void* workspace, size_t workspace_bytes, anysd_stream_t stream);
+/* GroupNorm whose statistics were produced by the epilogue(s) of the contraction(s) that wrote x (anysd_gemm_params::stats):
+ * a fixed-order fold of the slab partials per (image, group) in double, then ONE streaming pass y = [silu](x a + b).
+ * x: NHWC fp16 [N, HW, C]; its channels [0, C1) come with stats1 ([>= N, S, C1, 2]) and, when the tensor is a channel concat
+ * (openaimodel.py:780), channels [C1, C) with stats2 ([>= N, S, C - C1, 2]); stats2 NULL <=> C1 == C. */
+int anysd_groupnorm_apply_nhwc_f16(const void* x, int C, const float* stats1, int C1, const float* stats2, int S,
+                                   const float* gamma, const float* beta, void* y, int N, int HW, int G, float eps,
+                                   int fuse_silu, void* workspace, size_t workspace_bytes, anysd_stream_t stream);
 /* nn.LayerNorm(dim) (attention.py:262-264), one row per token. */
 int anysd_layernorm_f16(const void* x, const float* gamma, const float* beta, void* y, long long M, int C,
                         float eps, anysd_stream_t stream);
@@ -98,7 +105,8 @@ int anysd_layernorm_f16(const void* x, const float* gamma, const float* beta, vo
  *                          :148-150 (Downsample, stride 2), :104-117 (Upsample: nearest x2 folded in)
  * out[m, n] = act(sum_k A[m,k] W[n,k] + bias[n] + rowadd[m / rows_per_batch, n]) + residual[m, n]
  * fp16 operands, fp32 accumulate.  act: 0 none, 1 SiLU, 2 GEGLU (W rows interleaved (a_j, gate_j);
- * out has N/2 columns: (acc_a + b_a) * gelu_erf(acc_g + b_g)). */
+ * out has N/2 columns: (acc_a + b_a) * gelu_erf(acc_g + b_g)), 3 GELU (erf; nn.GELU of the CLIP-H MLP and the Resampler
+ * FeedForward), 4 QuickGELU (x sigmoid(1.702 x), the CLIP-L MLP). */
 typedef struct {
     const void* A;          /* dense: fp16 [M, lda]; conv: NHWC fp16 image [Nimg, H, W, Cin] */
     const void* W;          /* fp16 [N, ldw], row n = output channel, K contiguous ((ky,kx,ci) for conv) */
@@ -119,8 +127,17 @@ typedef struct {
     size_t workspace_bytes;
     int conv_pad;           /* conv: 0 = zero pad 1 on every side; 1 = pad right / bottom only (the first-stage Downsample,
                                ldm/modules/diffusionmodules/model.py:83-85: F.pad(x, (0,1,0,1)) + conv3x3 stride 2 pad 0) */
+    float* stats;           /* optional: GroupNorm statistics of the OUTPUT, written by the epilogue (the consumer's GroupNorm32,
+                               util.py:202-219, then needs no statistics pass): fp32 [stats_images, S, N, 2] = per image, per
+                               32-row slab (S = rows_per_batch / 32 = anysd_gemm_stats_slabs()), per channel {sum, sum of
+                               squares} of the fp32 results.  rows_per_batch must be the rows of one image.  Every cell is
+                               written exactly once in a fixed order: deterministic, independent of the batch.  NULL: off. */
+    int stats_images;       /* image slots in `stats` (>= number of images, rounded up to the conv's images-per-tile) */
 } anysd_gemm_params;
 int anysd_gemm_f16(const anysd_gemm_params* p, anysd_stream_t stream);
+/* Slabs per image of the statistics layout for this contraction, or 0 when the shape cannot produce them (rows of one
+ * image not a multiple of 32, conv patches not tiling the image exactly, GEGLU / fp32 output, non-tcgen05 shape). */
+int anysd_gemm_stats_slabs(const anysd_gemm_params* p);
 
 /* ---- attention ---------------------------------------------------------------------------
  * CrossAttention.forward (attention.py:163-194) / xformers memory_efficient_attention (:233):
@@ -195,6 +212,17 @@ int anysd_softmax_rows_f32(const float* S, long long ld_s, void* P, long long ld
  * sample / logvar: fp32 [B, Z, HW], either may be NULL. */
 int anysd_gaussian_posterior_f32(const float* moments, const float* noise, float* sample, float* logvar, float scale,
                                  int B, long long z_hw, anysd_stream_t stream);
+
+/* ==== condition encoders: the CLIP towers and the Resampler run on the kernels above; two helpers ====
+ * CLIPTextEmbeddings (transformers modeling_clip.py; FrozenCLIPEmbedder, ldm/modules/encoders/modules.py:107-150):
+ * out[b, i, :] = tok_table[ids[b, i], :] + pos_table[i, :]; fp16 tables [vocab, D] / [>= n, D], out fp16 [B*n, D]. */
+int anysd_embed_tokens_f16(const long long* ids, const void* tok_table, const void* pos_table, void* out, int B, int n, int D,
+                           int vocab, anysd_stream_t stream);
+/* softmax(q k^T scale [+ causal mask]) v per (batch, head) for SHORT sequences (n_kv <= 256): the causal 77-token
+ * self-attention of the CLIP text tower (the tcgen05 attention has no mask path).  Row-major fp16 q [B*n_q, ld_q] with head h
+ * at columns [h d, (h+1) d), same for k, v ([B*n_kv, ld_k|ld_v]) and out; causal != 0: key j masked for query i when j > i. */
+int anysd_attention_small_f16(const void* q, const void* k, const void* v, void* out, int B, int heads, int n_q, int n_kv, int d,
+                              int ld_q, int ld_k, int ld_v, int ld_o, float scale, int causal, anysd_stream_t stream);
 
 /* ==== training step (train.py:629-710) =====================================================
  * The reference back-propagates mse_loss(MoE(...), noise) through the frozen UNet with torch autograd

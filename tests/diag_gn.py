@@ -37,6 +37,15 @@ def main():
         mb = x.numel() * 2 / 1e6
         print(f"groupnorm fused={os.environ.get('ANYSD_GN_FUSED', '1')} N={N} HW={HW} C={C}: warm {t * 1e6:7.1f} us  cold {t2 * 1e6:7.1f} us "
               f"({2 * mb / t2 / 1e6:5.2f} TB/s algorithmic, {mb:.0f} MB tensor)", flush=True)
+        # statistics from a producer's epilogue (here: an identity-sized 1x1 contraction), then finalize + streaming apply
+        if C <= 1280:
+            w = (torch.eye(C, device="cuda") * 1.0).half()
+            st = ops.gemm(x.view(N * HW, C), w, y.view(N * HW, C), rows_per_batch=HW, stats_images=N)
+            if st is not None:
+                fa = lambda: ops.groupnorm(x, g, b, y, N, HW, 1e-5, True, ws, stats=st)
+                ta = timeit(fa)
+                ta2 = timeit(lambda: (big.zero_(), fa())) - timeit(lambda: big.zero_())
+                print(f"   epilogue-stats apply: warm {ta * 1e6:7.1f} us  cold {ta2 * 1e6:7.1f} us ({2 * mb / ta2 / 1e6:5.2f} TB/s algorithmic)", flush=True)
     for M, C in ((65536, 320), (16384, 640), (4096, 1280)):
         x = torch.randn(M, C, device="cuda").half()
         y = torch.empty_like(x)

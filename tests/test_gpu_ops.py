@@ -380,3 +380,61 @@ def test_attention_aux_cols_unsupported_is_loud(ops):
     out = torch.empty_like(t)
     with pytest.raises(Exception):
         ops.attention(t, t, t, out, B, heads, n, n, d, heads * d, heads * d, heads * d, heads * d, aux_cols=True)
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W", [(2, 64, 320, 64, 64), (3, 128, 64, 8, 8), (2, 64, 192, 16, 32), (1, 64, 64, 96, 96)])
+def test_conv_epilogue_groupnorm_statistics(ops, N, Cin, Cout, H, W):
+    """anysd_gemm_params::stats: the conv epilogue's per-(image, 32-row slab, channel) {sum, sum of squares} of its fp32
+    results (incl. bias, time-embedding row, residual) fold to the per-image channel moments; an odd batch on an 8x8 map
+    (two images per 128-row tile) exercises the padded image slot."""
+    from anyedit_b200.unet import _pack_conv3
+    x, w, b = randn(11, N, Cin, H, W), randn(12, Cout, Cin, 3, 3, scale=0.05), randn(13, Cout)
+    res, row = randn(14, N, Cout, H, W), randn(15, N, Cout)
+    out = torch.empty(N, H, W, Cout, dtype=torch.float16, device="cuda")
+    st = ops.conv3x3(to_nhwc16(x), _pack_conv3(w, "cuda"), out.view(-1, Cout), bias=b.cuda(), rowadd=row.cuda().contiguous(),
+                     residual=to_nhwc16(res).view(-1, Cout), stats=True)
+    assert st is not None and st.S == H * W // 32 and len(st.parts) == 1
+    ref = F.conv2d(x.half().float(), w.half().float(), b, padding=1) + row[:, :, None, None] + res.half().float()
+    buf = st.parts[0][0][:N].double().cpu()                              # [N, S, C, 2]
+    got = buf.sum(1)
+    want = torch.stack([ref.double().sum((2, 3)), (ref.double() ** 2).sum((2, 3))], -1)
+    assert rel(got[..., 0], want[..., 0]) < 2e-4 and rel(got[..., 1], want[..., 1]) < 2e-4
+    assert rel(from_nhwc(out, N, H, W), ref) < 1e-3
+
+
+def test_gemm_epilogue_statistics_and_groupnorm_apply(ops):
+    """Dense contraction (a SpatialTransformer proj_out: bias + residual) with statistics, then GroupNorm fed by them --
+    single source and channel concat (two producers) -- against F.group_norm of the fp16 tensor the GEMM wrote."""
+    N, HW, K, C1, C2 = 3, 256, 320, 320, 640
+    ws = ops.groupnorm_workspace(N, 32, 0, "cuda")
+    outs, stats = [], []
+    for seed, Cc in ((21, C1), (22, C2)):
+        A, Wt, b, r = randn(seed, N * HW, K), randn(seed + 5, Cc, K, scale=K ** -0.5), randn(seed + 9, Cc), randn(seed + 13, N * HW, Cc)
+        o = torch.empty(N * HW, Cc, dtype=torch.float16, device="cuda")
+        st = ops.gemm(A.half().cuda(), Wt.half().cuda(), o, bias=b.cuda(), residual=r.half().cuda(), rows_per_batch=HW, stats_images=N)
+        assert st is not None and st.S == HW // 32
+        ref = A.half().float() @ Wt.half().float().t() + b + r.half().float()
+        assert rel(o, ref) < 1e-3
+        outs.append(o)
+        stats.append(st)
+    for silu, eps in ((True, 1e-5), (False, 1e-6)):
+        gam, bet = randn(31, C1) * 0.2 + 1, randn(32, C1) * 0.1
+        y = torch.empty(N, HW, C1, dtype=torch.float16, device="cuda")
+        ops.groupnorm(outs[0].view(N, HW, C1), gam.cuda(), bet.cuda(), y, N, HW, eps, silu, ws, stats=stats[0])
+        xr = outs[0].float().cpu().view(N, HW, C1).permute(0, 2, 1)
+        ref = F.group_norm(xr, 32, gam, bet, eps)
+        ref = F.silu(ref) if silu else ref
+        assert rel(y.float().cpu().permute(0, 2, 1), ref) < 1e-3
+    # channel concat [C1 | C2] = 960 channels, 30 per group: group 10 straddles the two sources
+    cat = torch.empty(N * HW, C1 + C2, dtype=torch.float16, device="cuda")
+    ops.concat_channels(outs[0], outs[1], cat)
+    gam, bet = randn(33, C1 + C2) * 0.2 + 1, randn(34, C1 + C2) * 0.1
+    y = torch.empty(N, HW, C1 + C2, dtype=torch.float16, device="cuda")
+    both = ops.GnStats(stats[0].parts + stats[1].parts, stats[0].S)
+    ops.groupnorm(cat.view(N, HW, -1), gam.cuda(), bet.cuda(), y, N, HW, 1e-5, True, ws, stats=both)
+    xr = cat.float().cpu().view(N, HW, -1).permute(0, 2, 1)
+    ref = F.silu(F.group_norm(xr, 32, gam, bet, 1e-5))
+    assert rel(y.float().cpu().permute(0, 2, 1), ref) < 1e-3
+    # a shape that cannot produce statistics says so (rows of one image not a multiple of 32)
+    o = torch.empty(3 * 48, C1, dtype=torch.float16, device="cuda")
+    assert ops.gemm(randn(41, 3 * 48, K).half().cuda(), randn(42, C1, K).half().cuda(), o, rows_per_batch=48, stats_images=3) is None
