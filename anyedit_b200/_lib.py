@@ -25,6 +25,8 @@ class GemmParams(C.Structure):
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("conv_pad", C.c_int),
         ("stats", C.c_void_p), ("stats_images", C.c_int),
+        ("splitk_workspace", C.c_void_p), ("splitk_workspace_bytes", C.c_size_t),
+        ("splitk_counters", C.c_void_p), ("splitk_counters_bytes", C.c_size_t),
     ]
 
 
@@ -83,6 +85,7 @@ SIGNATURES = {
     "anysd_layernorm_f16": (_I, [_VP, _VP, _VP, _VP, _LL, _I, _F, _VP]),
     "anysd_gemm_f16": (_I, [C.POINTER(GemmParams), _VP]),
     "anysd_gemm_stats_slabs": (_I, [C.POINTER(GemmParams)]),
+    "anysd_gemm_splitk_workspace_bytes": (_SZ, [C.POINTER(GemmParams)]),
     "anysd_groupnorm_apply_nhwc_f16": (_I, [_VP, _I, _VP, _I, _VP, _I, _VP, _VP, _VP, _I, _I, _I, _F, _I, _VP, _SZ, _VP]),
     "anysd_attention_f16": (_I, [C.POINTER(AttnParams), _VP]),
     "anysd_cfg_ddim_step_f32": (_I, [_VP, _VP, _VP, _VP, _F, _I, _I, _VP, _VP, _LL, _I, _VP]),

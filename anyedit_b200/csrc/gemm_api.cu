@@ -11,6 +11,7 @@ bool tc5_supported(const anysd_gemm_params* q);
 int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st);
 bool tc5p_supported(const anysd_gemm_params* q);
 int tc5p_stats_slabs(const anysd_gemm_params* q);
+size_t tc5p_splitk_bytes(const anysd_gemm_params* q);
 }
 
 using namespace anysd;
@@ -72,4 +73,12 @@ extern "C" int anysd_gemm_stats_slabs(const anysd_gemm_params* p) {
     if (force && strcmp(force, "tc5p")) return 0;
     if (p->conv && (p->Cin <= 0 || p->K != 9 * p->Cin)) return 0;
     return tc5p_supported(p) ? tc5p_stats_slabs(p) : 0;
+}
+
+extern "C" size_t anysd_gemm_splitk_workspace_bytes(const anysd_gemm_params* p) {
+    if (p == nullptr || !p->A || !p->W || !p->out) return 0;
+    static const char* force = getenv("ANYSD_GEMM");
+    if (force && strcmp(force, "tc5p")) return 0;
+    if (p->conv && (p->Cin <= 0 || p->K != 9 * p->Cin)) return 0;
+    return tc5p_supported(p) ? tc5p_splitk_bytes(p) : 0;
 }

@@ -48,6 +48,12 @@ struct PArgs {
     // per-(32-row slab, channel) {sum, sum of squares} of the OUTPUT for the consumer's GroupNorm (anysd_gemm_params::stats)
     float* stats;
     int stats_hw, stats_spi, stats_nimg;     // rows per image, slabs per image (= hw / 32), image slots in the buffer
+    // split-K (few output tiles, long K: the 8x8 level): a work unit = (tile, k-range); every unit dumps its raw fp32
+    // accumulators, the LAST unit of a tile to arrive (per epilogue warp, atomic counter) adds the partials in split order
+    // -- a fixed order, so the result does not depend on the arrival order -- and runs the normal epilogue
+    int splits, kb_per_split, num_units;
+    float* sk_ws;                            // [tile][cta of the pair][split][128 rows][bn] fp32
+    unsigned int* sk_cnt;                    // [tile][cta of the pair][8 epilogue warps], zero between launches
 };
 
 // ---- PTX wrappers (same forms as gemm_tc5.cu) -------------------------------------------------------
@@ -230,7 +236,11 @@ __device__ __forceinline__ TileCoord tile_coord(const PArgs& p, int tile, int ra
     return c;
 }
 
-template <bool CONV, int CTAS>
+// X ("extended"): the epilogue statistics, split-K and the GELU / QuickGELU activations are compiled in only when a launch
+// asks for one of them -- the plain variant keeps the epilogue of the HBM- / issue-bound K = 320 projections and GEGLU
+// contractions free of their branches and registers ([measured] the merged kernel ran the 161 linear launches of a forward
+// in 6.9 ms instead of 6.2 ms).
+template <bool CONV, int CTAS, bool X>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const PArgs p) {
@@ -293,9 +303,13 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             // ===== TMA producer: runs ahead across tile boundaries =====
             uint32_t g = 0;
-            for (int tile = cta_first; tile < p.num_tiles; tile += cta_stride) {
+            for (int unit = cta_first; unit < p.num_units; unit += cta_stride) {
+                const bool sp = X && p.splits > 1;
+                const int tile = sp ? unit / p.splits : unit;
+                const int kb0 = sp ? (unit - tile * p.splits) * p.kb_per_split : 0;
+                const int kb1 = sp ? (kb0 + p.kb_per_split < p.num_kb ? kb0 + p.kb_per_split : p.num_kb) : p.num_kb;
                 const TileCoord c = tile_coord<CONV, CTAS>(p, tile, rank);
-                for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+                for (int kb = kb0; kb < kb1; ++kb, ++g) {
                     const int s = g % P_STAGES;
                     const uint32_t ph = (g / P_STAGES) & 1;
                     pm_wait(empty_bar(s), ph ^ 1);
@@ -331,14 +345,18 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0 && leader) {
             // ===== MMA issuer (the leader CTA issues for the pair) =====
             uint32_t g = 0, t = 0;
-            for (int tile = cta_first; tile < p.num_tiles; tile += cta_stride, ++t) {
+            for (int unit = cta_first; unit < p.num_units; unit += cta_stride, ++t) {
+                const bool sp = X && p.splits > 1;
+                const int tile = sp ? unit / p.splits : unit;
+                const int kb0 = sp ? (unit - tile * p.splits) * p.kb_per_split : 0;
+                const int kb1 = sp ? (kb0 + p.kb_per_split < p.num_kb ? kb0 + p.kb_per_split : p.num_kb) : p.num_kb;
                 const TileCoord c = tile_coord<CONV, CTAS>(p, tile, 0);
                 const uint32_t buf = t & 1, bph = (t >> 1) & 1;
                 pm_wait(tempty_bar(buf), bph ^ 1);           // epilogue(s) have drained this accumulator
                 p_fence_after();
                 const uint32_t idesc = (1u << 4) | ((uint32_t)(c.nw >> 3) << 17) | ((uint32_t)((P_BM * CTAS) >> 4) << 24);
                 const uint32_t d = tmem_base + buf * P_BN;
-                for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+                for (int kb = kb0; kb < kb1; ++kb, ++g) {
                     const int s = g % P_STAGES;
                     const uint32_t ph = (g / P_STAGES) & 1;
                     pm_wait(full_bar(s), ph);
@@ -347,8 +365,8 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const uint64_t ad = p_sdesc(sa), bd = p_sdesc(sb);
 #pragma unroll
                     for (int k = 0; k < P_BK / 16; ++k) {
-                        if (CTAS == 2) p_umma2(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                        else p_umma(d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        if (CTAS == 2) p_umma2(d, ad + 2 * k, bd + 2 * k, idesc, ((kb - kb0) | k) ? 1u : 0u);
+                        else p_umma(d, ad + 2 * k, bd + 2 * k, idesc, ((kb - kb0) | k) ? 1u : 0u);
                     }
                     if (CTAS == 2) p_commit2(empty_bar(s)); else p_commit(empty_bar(s));
                 }
@@ -389,13 +407,15 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         };
         // this warp's first slab: residual prefetch before anything else
         uint32_t t = 0, q = 0;                                // tile counter, per-warp slab counter
+        const bool split = X && p.splits > 1;
         if (p.has_res && lane == 0) {
-            for (int tl = cta_first; tl < p.num_tiles; tl += cta_stride) {
-                const TileCoord c0 = tile_coord<CONV, CTAS>(p, tl, rank);
+            for (int ul = cta_first; ul < p.num_units; ul += cta_stride) {
+                const TileCoord c0 = tile_coord<CONV, CTAS>(p, split ? ul / p.splits : ul, rank);
                 if (set < nsub_of(c0)) { slab_load(0, c0, set); break; }
             }
         }
-        for (int tile = cta_first; tile < p.num_tiles; tile += cta_stride, ++t) {
+        for (int unit = cta_first; unit < p.num_units; unit += cta_stride, ++t) {
+            const int tile = split ? unit / p.splits : unit;
             const TileCoord c = tile_coord<CONV, CTAS>(p, tile, rank);
             const uint32_t buf = t & 1, bph = (t >> 1) & 1;
             const int nsub = nsub_of(c);
@@ -413,6 +433,48 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float* radd = p.rowadd ? p.rowadd + (size_t)img * p.ld_rowadd : nullptr;
             pm_wait(tfull_bar(buf), bph);
             p_fence_after();
+            // ---- split-K: dump this unit's raw accumulators, find out whether this warp is the last of the tile's units ----
+            bool sk_last = true;
+            const float* sk_tile = nullptr;
+            if (split) {
+                const int ks = unit - tile * p.splits;
+                float* wst = p.sk_ws + ((size_t)(tile * CTAS + rank) * p.splits) * (size_t)(P_BM * p.bn);
+                sk_tile = wst;
+                float* mine = wst + (size_t)ks * (P_BM * p.bn) + (size_t)row * p.bn;
+                for (int j = set; j < nsub; j += 2) {
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t r[32];
+                        const int ac = j * P_SUB + half * 32;
+                        __syncwarp();
+                        p_tmem_ld32(tmem_base + buf * P_BN + ((uint32_t)(lg * 32) << 16) + ac, r);
+                        p_tmem_wait_ld();
+                        if (ac < c.nw) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                __stcg(reinterpret_cast<float4*>(mine + ac) + i,
+                                       make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                                   __uint_as_float(r[4 * i + 3])));
+                        }
+                    }
+                }
+                p_fence_before();                              // accumulator read: hand the TMEM buffer back now
+                __syncwarp();
+                if (lane == 0) {
+                    if (CTAS == 2) pm_arrive_remote(tempty_bar(buf), 0); else pm_arrive(tempty_bar(buf));
+                }
+                __threadfence();                               // partials visible before the arrival is counted
+                __syncwarp();
+                unsigned int old = 0;
+                unsigned int* cnt = p.sk_cnt + (size_t)(tile * CTAS + rank) * 8 + ew;
+                if (lane == 0) {
+                    old = atomicAdd(cnt, 1u);
+                    if (old == (unsigned)p.splits - 1) *cnt = 0;   // re-arm for the next launch (stream-ordered)
+                }
+                old = __shfl_sync(0xffffffffu, old, 0);
+                sk_last = old == (unsigned)p.splits - 1;
+                __threadfence();                               // ... and the other units' partials visible to the adder
+            }
             for (int j = set; j < nsub; j += 2, ++q) {
                 const uint32_t b = q & 1;
                 if (lane == 0) {
@@ -421,8 +483,8 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (j + 2 < nsub) {
                             slab_load(b ^ 1, c, j + 2);
                         } else {
-                            for (int tl = tile + cta_stride; tl < p.num_tiles; tl += cta_stride) {
-                                const TileCoord c2 = tile_coord<CONV, CTAS>(p, tl, rank);
+                            for (int ul = unit + cta_stride; ul < p.num_units; ul += cta_stride) {
+                                const TileCoord c2 = tile_coord<CONV, CTAS>(p, split ? ul / p.splits : ul, rank);
                                 if (set < nsub_of(c2)) { slab_load(b ^ 1, c2, set); break; }
                             }
                         }
@@ -431,6 +493,7 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 __syncwarp();
                 unsigned char* stg = wstg_ptr + b * SLAB + lane * 128;
                 if (p.has_res) pm_wait(rbar(b), (q >> 1) & 1);
+                if (!sk_last) continue;                        // another unit finishes this tile (barrier phases stay in step)
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {         // 2 x 32 output columns
                     float v[32];
@@ -465,14 +528,30 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             v[16 + i] = __uint_as_float(r1[2 * i]) * p_gelu(__uint_as_float(r1[2 * i + 1]));
                         }
                     } else {
-                        uint32_t r[32];
                         const int ac = j * P_SUB + oc;
-                        __syncwarp();
-                        p_tmem_ld32(tmem_base + buf * P_BN + ((uint32_t)(lg * 32) << 16) + ac, r);
-                        p_tmem_wait_ld();
                         const int nb = c.n0 + ac;
+                        if (split) {
+                            // the tile's partials in split order (fixed: independent of which unit arrived last)
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+                            if (ac < c.nw) {
+                                for (int ks = 0; ks < p.splits; ++ks) {
+                                    const float4* src = reinterpret_cast<const float4*>(sk_tile + (size_t)ks * (P_BM * p.bn) + (size_t)row * p.bn + ac);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) {
+                                        const float4 f = __ldcg(src + i);
+                                        v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+                                    }
+                                }
+                            }
+                        } else {
+                            uint32_t r[32];
+                            __syncwarp();
+                            p_tmem_ld32(tmem_base + buf * P_BN + ((uint32_t)(lg * 32) << 16) + ac, r);
+                            p_tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                        }
                         if (nb + 32 <= p.N) {
                             if (p.bias) {
 #pragma unroll
@@ -500,10 +579,10 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (p.act == 1) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
-                        } else if (p.act == 3) {              // nn.GELU() (CLIP-H MLP, Resampler FeedForward)
+                        } else if (X && p.act == 3) {         // nn.GELU() (CLIP-H MLP, Resampler FeedForward)
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = p_gelu(v[i]);
-                        } else if (p.act == 4) {              // QuickGELU (CLIP-L MLP)
+                        } else if (X && p.act == 4) {         // QuickGELU (CLIP-L MLP)
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = quick_gelu_f(v[i]);
                         }
@@ -522,7 +601,7 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                         *slot = pack8(vv);
                     }
-                    if (p.stats != nullptr) {
+                    if (X && p.stats != nullptr) {
                         // GroupNorm statistics of what was just produced (fp32, before the fp16 rounding): per channel over
                         // this warp's 32 rows.  Each (slab, channel) cell is written exactly once per launch, by one warp.
                         const int r0 = CONV ? 0 : c.m0 + lg * 32;
@@ -549,11 +628,13 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 __syncwarp();
                 if (lane == 0) slab_store(b, c, j);
             }
-            // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp
-            p_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (CTAS == 2) pm_arrive_remote(tempty_bar(buf), 0); else pm_arrive(tempty_bar(buf));
+            // accumulator fully read by this warp: hand the TMEM buffer back to the MMA warp (split-K did so above)
+            if (!split) {
+                p_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CTAS == 2) pm_arrive_remote(tempty_bar(buf), 0); else pm_arrive(tempty_bar(buf));
+                }
             }
         }
         if (lane == 0) p_store_wait<0>();                      // smem must outlive the last store
@@ -587,24 +668,76 @@ static EncodeTiledFnP p_get_encode() {
     return fn;
 }
 
+// Encoded tensor maps are kept in a small direct-mapped table keyed by everything that goes into the encoding: a sampling
+// loop launches the same few hundred (pointer, shape) combinations over and over (the caching allocator hands the same
+// blocks back), and cuTensorMapEncodeTiled is a few microseconds of host time per map, four maps per launch.
+struct PMapKey {
+    const void* ptr;
+    uint64_t d0, d1, d2, d3, ld;
+    uint32_t b0, b1, b2, b3, es, rank;
+    bool operator==(const PMapKey& o) const {
+        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && ld == o.ld && b0 == o.b0 && b1 == o.b1 &&
+               b2 == o.b2 && b3 == o.b3 && es == o.es && rank == o.rank;
+    }
+};
+struct PMapSlot {
+    PMapKey key;
+    CUtensorMap map;
+    bool valid;
+};
+constexpr int P_MAP_SLOTS = 4096;
+static thread_local PMapSlot* p_map_table = nullptr;
+static PMapSlot* p_map_slot(const PMapKey& k) {
+    if (p_map_table == nullptr) p_map_table = (PMapSlot*)calloc(P_MAP_SLOTS, sizeof(PMapSlot));
+    uint64_t h = (uint64_t)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
+    h ^= (k.d0 * 31 + k.d1) * 0xC2B2AE3D27D4EB4Full + (k.d2 * 131 + k.d3 * 17 + k.ld) * 0x165667B19E3779F9ull;
+    h ^= ((uint64_t)k.b0 << 40) ^ ((uint64_t)k.b1 << 28) ^ ((uint64_t)k.b2 << 16) ^ ((uint64_t)k.b3 << 4) ^ k.es ^ ((uint64_t)k.rank << 60);
+    return p_map_table ? &p_map_table[(h >> 20) % P_MAP_SLOTS] : nullptr;
+}
+
 static bool p_map_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t bi, uint32_t bo) {
+    const PMapKey key = {ptr, inner, outer, 0, 0, ld, bi, bo, 0, 0, 1, 2};
+    PMapSlot* slot = p_map_slot(key);
+    if (slot && slot->valid && slot->key == key) {
+        *tm = slot->map;
+        return true;
+    }
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {ld * 2};
     cuuint32_t box[2] = {bi, bo};
     cuuint32_t es[2] = {1, 1};
-    return p_get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    const bool ok = p_get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (ok && slot) {
+        slot->key = key;
+        slot->map = *tm;
+        slot->valid = true;
+    }
+    return ok;
 }
 // NHWC tensor [N, H, W, C] with row pitch ld (elements per pixel), box 64 x BW x BH x NB, element stride s in W/H
 static bool p_map_nhwc(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, int ld, int BW, int BH, int NB, int s) {
+    const PMapKey key = {ptr, (uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)ld, 64u, (uint32_t)BW, (uint32_t)BH, (uint32_t)NB,
+                         (uint32_t)s, 4};
+    PMapSlot* slot = p_map_slot(key);
+    if (slot && slot->valid && slot->key == key) {
+        *tm = slot->map;
+        return true;
+    }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
     cuuint32_t box[4] = {64u, (cuuint32_t)(BW * s), (cuuint32_t)(BH * s), (cuuint32_t)NB};
     cuuint32_t es[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
-    return p_get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    const bool ok = p_get_encode()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    if (ok && slot) {
+        slot->key = key;
+        slot->map = *tm;
+        slot->valid = true;
+    }
+    return ok;
 }
 
 static int p_pow2_ceil(int v) {
@@ -637,6 +770,25 @@ int tc5p_stats_slabs(const anysd_gemm_params* q) {
     return hw / 32;
 }
 
+static void p_select(const anysd_gemm_params* q, int tiles_m, int num_kb, int* ctas_out, int* bn_out, int* splits_out);
+static size_t p_splitk_bytes(int tiles_m, int N, int ctas, int bn, int splits);
+// scratch the caller should provide for this contraction to run split-K (0: the schedule does not split it)
+size_t tc5p_splitk_bytes(const anysd_gemm_params* q) {
+    int tiles_m, num_kb;
+    if (q->conv) {
+        int Ho, Wo, BW, BH, NB;
+        p_conv_patch(q, &Ho, &Wo, &BW, &BH, &NB);
+        tiles_m = cdiv(Wo, BW) * cdiv(Ho, BH) * cdiv(q->Nimg, NB);
+        num_kb = 9 * (q->Cin / P_BK);
+    } else {
+        tiles_m = cdiv(q->M, P_BM);
+        num_kb = cdiv(q->K, P_BK);
+    }
+    int ctas, bn, splits;
+    p_select(q, tiles_m, num_kb, &ctas, &bn, &splits);
+    return p_splitk_bytes(tiles_m, q->N, ctas, bn, splits);
+}
+
 bool tc5p_supported(const anysd_gemm_params* q) {
     if (q->out_dtype != ANYSD_F16) return false;
     if (q->N % 8 != 0 || q->K % 8 != 0) return false;
@@ -656,7 +808,7 @@ bool tc5p_supported(const anysd_gemm_params* q) {
     return p_get_encode() != nullptr;
 }
 
-template <bool CONV, int CTAS>
+template <bool CONV, int CTAS, bool X>
 static int p_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
                     const PArgs& a, cudaStream_t st) {
     static bool done[64];
@@ -664,7 +816,7 @@ static int p_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     cudaGetDevice(&dev);
     dev &= 63;
     if (!done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc5p_kernel<CONV, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc5p_kernel<CONV, CTAS, X>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              PCfg<CTAS>::SMEM);
         if (e != cudaSuccess) {
             set_error("tcgen05 gemm: smem opt-in failed: %s", cudaGetErrorString(e));
@@ -673,7 +825,7 @@ static int p_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
         done[dev] = true;
     }
     int grid = sm_count();
-    if (grid > a.num_tiles * CTAS) grid = a.num_tiles * CTAS;
+    if (grid > a.num_units * CTAS) grid = a.num_units * CTAS;
     grid -= grid % CTAS;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -687,7 +839,7 @@ static int p_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CTAS == 2 ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc5p_kernel<CONV, CTAS>, tmA, tmB, tmO, tmR, a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc5p_kernel<CONV, CTAS, X>, tmA, tmB, tmO, tmR, a);
     if (e != cudaSuccess) {
         set_error("tcgen05 gemm launch failed: %s", cudaGetErrorString(e));
         return ANYSD_ECUDA;
@@ -702,6 +854,67 @@ static void p_conv_patch(const anysd_gemm_params* q, int* Ho, int* Wo, int* BW, 
     *BW = p_pick_extent(*Wo, 128);
     *BH = p_pick_extent(*Ho, 128 / *BW);
     *NB = 128 / (*BW * *BH);
+}
+
+// K split: a function of the PER-IMAGE geometry only -- never of the batch -- because splitting changes the fp32 summation
+// order: a layer either always runs as `splits` ordered partial sums or never does, so every output bit stays independent
+// of how many images share the batch (and of the grid).  Layers with at most one 128-row tile per image (8x8 maps and
+// smaller) and a very long K are the ones that leave most SMs idle at sampling batch sizes.  [measured, B200, batch 16,
+// tests/diag_splitk.py] conv 2560->1280 @8x8 (360 k-blocks): 110.7 us unsplit, 86.2 / 78.6 / 106.9 us with 2 / 3 / 4
+// partials; conv 1280->1280 @8x8 (180 k-blocks): 49.5 us unsplit, 52.3 / 55.4 us with 2 / 3 (the dump + ordered add costs
+// more than the idle SMs); dense M = 1024 contractions lose 30-50 %.  Hence: 3 partials from 256 k-blocks on, convs only.
+// ANYSD_GEMM_SPLITK=0|n forces a count (experiments).
+static int p_geometry_splits(const anysd_gemm_params* q, int num_kb) {
+    static const char* force_sk = getenv("ANYSD_GEMM_SPLITK");
+    if (q->act == 2 || q->out_dtype != ANYSD_F16) return 1;
+    int rows_per_image = q->rows_per_batch;
+    if (q->conv) {
+        int Ho, Wo, BW, BH, NB;
+        p_conv_patch(q, &Ho, &Wo, &BW, &BH, &NB);
+        rows_per_image = Ho * Wo;
+    }
+    if (rows_per_image <= 0 || rows_per_image > P_BM) return 1;
+    if (force_sk) {
+        const int f = atoi(force_sk);
+        return (f <= 1 || num_kb / f < 8) ? 1 : (f > 8 ? 8 : f);
+    }
+    return (q->conv && num_kb >= 256) ? 3 : 1;
+}
+
+// Tile shape selection.  Candidates: CTA pairs (cta_group::2, 256-row tiles, less L2 traffic per FLOP) or single CTAs, tile
+// width 256 / 192 / 128 / 64 (GEGLU pairs need >= 128).  Cost model = scheduling rounds of the work units (tiles x splits) on
+// the 148 SMs x per-unit time ~ (bn + 270) x (k-blocks of the unit + 8 when split: the partial dump and the ordered add):
+// deep levels (8 row tiles x 5 column tiles, K = 11520 .. 23040) otherwise leave most of the machine idle while every busy
+// SM streams a full K operand pair through its L2 port; mid levels suffer from wave quantisation.
+// ANYSD_GEMM_CTAS=1|2 / ANYSD_GEMM_BN force a choice.
+static void p_select(const anysd_gemm_params* q, int tiles_m, int num_kb, int* ctas_out, int* bn_out, int* splits_out) {
+    static const char* force = getenv("ANYSD_GEMM_CTAS");
+    static const char* force_bn = getenv("ANYSD_GEMM_BN");
+    const int sp = splits_out ? p_geometry_splits(q, num_kb) : 1;
+    int ctas = 1, bn = 256;
+    double best = -1;
+    for (int c = 2; c >= 1; --c) {
+        if (c == 2 && (tiles_m < 2 || sm_count() < 2)) continue;
+        if (force && (force[0] == '1' || force[0] == '2') && c != force[0] - '0') continue;
+        static const int widths[4] = {256, 192, 128, 64};     // 192 balances N = 320 (192 + 128) and divides 960 / 1920
+        for (int wi = 0; wi < 4; ++wi) {
+            const int w = widths[wi];
+            if (w < (q->act == 2 ? 128 : 64) || (q->act == 2 && w == 192)) continue;
+            if (force_bn && atoi(force_bn) != w) continue;
+            const long units = (long)cdiv(tiles_m, c) * cdiv(q->N, w) * sp;
+            const long slots = sm_count() / c;
+            const long rounds = (units + slots - 1) / slots;
+            const double cost = (double)rounds * (w + 270) * ((double)cdiv(num_kb, sp) + (sp > 1 ? 8.0 : 0.0));
+            if (best < 0 || cost < best) { best = cost; ctas = c; bn = w; }
+        }
+    }
+    *ctas_out = ctas;
+    *bn_out = bn;
+    if (splits_out) *splits_out = sp;
+}
+static size_t p_splitk_bytes(int tiles_m, int N, int ctas, int bn, int splits) {
+    if (splits <= 1) return 0;
+    return (size_t)cdiv(tiles_m, ctas) * cdiv(N, bn) * ctas * splits * P_BM * bn * sizeof(float);
 }
 
 int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
@@ -768,29 +981,13 @@ int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
         ok = ok && p_map_2d(&tmO, q->out, (uint64_t)n_out, (uint64_t)q->M, (uint64_t)q->ldo, P_SUB, 32);
         if (q->residual) ok = ok && p_map_2d(&tmR, q->residual, (uint64_t)n_out, (uint64_t)q->M, (uint64_t)q->ldr, P_SUB, 32);
     }
-    // Tile shape selection.  Candidates: CTA pairs (cta_group::2, 256-row tiles, less L2 traffic per FLOP) or
-    // single CTAs, tile width 256 / 128 / 64 (GEGLU pairs need >= 128).  Cost model = scheduling rounds on the
-    // 148 SMs x per-tile time ~ (bn + 270): deep levels (8 row tiles x 5 column tiles) otherwise leave most of the
-    // machine idle, mid levels suffer from wave quantisation.  ANYSD_GEMM_CTAS=1|2 / ANYSD_GEMM_BN force a choice.
-    static const char* force = getenv("ANYSD_GEMM_CTAS");
-    static const char* force_bn = getenv("ANYSD_GEMM_BN");
-    int ctas = 1, bn = 256;
-    {
-        long best = -1;
-        for (int c = 2; c >= 1; --c) {
-            if (c == 2 && (a.tiles_m < 2 || sm_count() < 2)) continue;
-            if (force && (force[0] == '1' || force[0] == '2') && c != force[0] - '0') continue;
-            static const int widths[4] = {256, 192, 128, 64};     // 192 balances N = 320 (192 + 128) and divides 960 / 1920
-            for (int wi = 0; wi < 4; ++wi) {
-                const int w = widths[wi];
-                if (w < (q->act == 2 ? 128 : 64) || (q->act == 2 && w == 192)) continue;
-                if (force_bn && atoi(force_bn) != w) continue;
-                const long tiles = (long)cdiv(a.tiles_m, c) * cdiv(q->N, w);
-                const long rounds = (tiles + sm_count() / c - 1) / (sm_count() / c);
-                const long cost = rounds * (w + 270);   // fitted: a 128-wide tile costs 0.76x a 256-wide one
-                if (best < 0 || cost < best) { best = cost; ctas = c; bn = w; }
-            }
-        }
+    int ctas = 1, bn = 256, splits = 1;
+    p_select(q, a.tiles_m, a.num_kb, &ctas, &bn, &splits);
+    const size_t sk_need = p_splitk_bytes(a.tiles_m, q->N, ctas, bn, splits);
+    if (splits > 1 && (q->splitk_workspace == nullptr || q->splitk_workspace_bytes < sk_need || q->splitk_counters == nullptr ||
+                       (size_t)cdiv(a.tiles_m, ctas) * cdiv(q->N, bn) * ctas * 8 * sizeof(unsigned int) > q->splitk_counters_bytes)) {
+        splits = 1;                                   // no scratch from the caller: the plain schedule
+        p_select(q, a.tiles_m, a.num_kb, &ctas, &bn, nullptr);
     }
     a.bn = bn;
     a.tiles_n = cdiv(q->N, bn);
@@ -802,8 +999,18 @@ int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
     }
     if (!q->residual) tmR = tmO;
     a.num_tiles = cdiv(a.tiles_m, ctas) * a.tiles_n;
-    if (q->conv) return ctas == 2 ? p_launch<true, 2>(tmA, tmB, tmO, tmR, a, st) : p_launch<true, 1>(tmA, tmB, tmO, tmR, a, st);
-    return ctas == 2 ? p_launch<false, 2>(tmA, tmB, tmO, tmR, a, st) : p_launch<false, 1>(tmA, tmB, tmO, tmR, a, st);
+    a.splits = splits;
+    a.kb_per_split = cdiv(a.num_kb, splits);
+    a.num_units = a.num_tiles * splits;
+    a.sk_ws = (float*)q->splitk_workspace;
+    a.sk_cnt = (unsigned int*)q->splitk_counters;
+    const bool ext = a.stats != nullptr || a.splits > 1 || a.act >= 3;
+    if (ext) {
+        if (q->conv) return ctas == 2 ? p_launch<true, 2, true>(tmA, tmB, tmO, tmR, a, st) : p_launch<true, 1, true>(tmA, tmB, tmO, tmR, a, st);
+        return ctas == 2 ? p_launch<false, 2, true>(tmA, tmB, tmO, tmR, a, st) : p_launch<false, 1, true>(tmA, tmB, tmO, tmR, a, st);
+    }
+    if (q->conv) return ctas == 2 ? p_launch<true, 2, false>(tmA, tmB, tmO, tmR, a, st) : p_launch<true, 1, false>(tmA, tmB, tmO, tmR, a, st);
+    return ctas == 2 ? p_launch<false, 2, false>(tmA, tmB, tmO, tmR, a, st) : p_launch<false, 1, false>(tmA, tmB, tmO, tmR, a, st);
 }
 
 }  // namespace anysd

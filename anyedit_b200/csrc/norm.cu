@@ -14,7 +14,13 @@ constexpr int GN_MAX_SPLITS = 64;
 constexpr int GN_U = 8;            // 16-byte loads a thread keeps in flight
 
 // x * sigmoid(x) with two MUFU ops (ex2, rcp) instead of an IEEE division: ~1e-7 relative, far below the fp16 store
-__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// (inline PTX: __fdividef / __expf expand to ~11 instructions with range checks; this is FMUL, MUFU.EX2, FADD, MUFU.RCP, FMUL)
+__device__ __forceinline__ float silu_fast(float v) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return v * r;
+}
 
 struct GnGeom {
     int CV;    // 8-channel vectors per row (C/8)

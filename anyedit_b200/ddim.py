@@ -380,6 +380,10 @@ def _halves_share_prefix(uc, c):
         return False
     if c.get("c_adm") is not None or uc.get("c_adm") is not None:
         return False
+    if ("c_task" in c) != ("c_task" in uc):
+        return False
+    if "c_task" in c and not torch.equal(c["c_task"], uc["c_task"].to(c["c_task"].device)):      # AnySD edit codes feed the embedding
+        return False
     a, b = c.get("c_concat") or [], uc.get("c_concat") or []
     if len(a) != len(b):
         return False
@@ -558,16 +562,22 @@ class _Stepper:
                     # encoding) and other threads' CUDA calls must not invalidate the capture
                     with torch.cuda.graph(g, capture_error_mode="relaxed"):
                         self._body(scale, nb)
-                except Exception as e:                    # capture refused / invalidated: this stepper stays eager
-                    import warnings
-                    warnings.warn(f"anyedit_b200: CUDA-graph capture of the DDIM step failed ({type(e).__name__}: "
-                                  f"{str(e).splitlines()[0][:160]}); continuing without a graph")
+                except Exception as e:
+                    # A refused / invalidated capture is an ERROR: a serving loop that silently fell back to eager stepping
+                    # would lose ~20 % throughput with nothing but a warning.  ANYSD_ALLOW_EAGER=1 opts into the fallback.
                     ops.launch_count = n0
-                    self.want_graph, self.graph = False, None
                     try:
                         torch.cuda.synchronize()
                     except Exception:
                         pass
+                    if os.environ.get("ANYSD_ALLOW_EAGER", "0")[:1] != "1":
+                        raise RuntimeError(f"anyedit_b200: CUDA-graph capture of the sampling step failed ({type(e).__name__}: "
+                                           f"{str(e).splitlines()[0][:200]}); set ANYSD_ALLOW_EAGER=1 to continue without a graph, or "
+                                           "construct the sampler with use_cuda_graph=False") from e
+                    import warnings
+                    warnings.warn(f"anyedit_b200: CUDA-graph capture of the sampling step failed ({type(e).__name__}: "
+                                  f"{str(e).splitlines()[0][:160]}); ANYSD_ALLOW_EAGER=1: continuing without a graph")
+                    self.want_graph, self.graph = False, None
                     self._eager(scale, nb)
                     return self.x_prev.clone(), self.pred_x0.clone()
                 self.graph_launches = ops.launch_count - n0    # kernels recorded into the graph

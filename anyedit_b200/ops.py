@@ -186,6 +186,9 @@ def layernorm(x, gamma, beta, y, eps=1e-5):
 _GN_EPILOGUE = os.environ.get("ANYSD_GN_EPILOGUE", "1")[:1] != "0"      # GroupNorm statistics from the producer's epilogue
 
 
+GN_EPILOGUE_MIN_ROWS = 1024          # pixels per image from which the producer's epilogue emits the statistics (see _want_stats)
+
+
 class GnStats:
     """Epilogue statistics of one activation tensor: ``parts`` = [(fp32 [images, S, C_i, 2], C_i), ...] in channel order
     (two parts for a channel concat), ``S`` = slabs per image."""
@@ -198,7 +201,10 @@ class GnStats:
 def _want_stats(p, images, dev, reuse=None):
     """Allocate the statistics buffer when the launch can fill it (anysd_gemm_stats_slabs); returns GnStats or None.
     ``reuse``: a GnStats of the same geometry whose buffer is refilled (persistent outputs read by a captured graph)."""
-    if not _GN_EPILOGUE:
+    # [measured, tests/diag_gn.py, batch 16] finalize + streaming apply vs the one-launch statistics + apply kernel:
+    # 31 vs 42 us (64x64 map, 320 ch), 21 vs 29 us (32x32, 640 ch), 69 vs 103 us (64x64, 960 ch) -- but 23 vs 19 us at 16x16
+    # and 15 vs 14 us at 8x8, where two launches cost more than the statistics pass they replace: maps of >= 1024 pixels only
+    if not _GN_EPILOGUE or p.rows_per_batch < GN_EPILOGUE_MIN_ROWS:
         return None
     S = _lib.load().anysd_gemm_stats_slabs(C.byref(p))
     if S <= 0:
@@ -211,6 +217,27 @@ def _want_stats(p, images, dev, reuse=None):
         buf = torch.empty(slots, S, p.N, 2, dtype=torch.float32, device=dev)
     p.stats, p.stats_images = buf.data_ptr(), slots
     return reuse if reuse is not None else GnStats([(buf, p.N)], S)
+
+
+_SPLITK = os.environ.get("ANYSD_GEMM_SPLITK", "1")[:1] != "0"
+_splitk_counters = {}
+
+
+def _want_splitk(p, dev):
+    """Scratch for split-K when the schedule wants it (few output tiles, long K): fp32 partial tiles + the per-device arrival
+    counters (zeroed once; every launch re-arms them).  Returns the scratch tensor (kept alive by the caller's frame)."""
+    if not _SPLITK:
+        return None
+    need = _lib.load().anysd_gemm_splitk_workspace_bytes(C.byref(p))
+    if need == 0:
+        return None
+    cnt = _splitk_counters.get(dev)
+    if cnt is None:
+        cnt = _splitk_counters[dev] = torch.zeros(16384, dtype=torch.int32, device=dev)
+    ws = torch.empty(need // 4, dtype=torch.float32, device=dev)
+    p.splitk_workspace, p.splitk_workspace_bytes = ws.data_ptr(), need
+    p.splitk_counters, p.splitk_counters_bytes = cnt.data_ptr(), cnt.numel() * 4
+    return ws
 
 
 def gemm(A, W, out, bias=None, rowadd=None, rows_per_batch=0, residual=None, act=0, M=None, K=None, lda=None,
@@ -237,6 +264,7 @@ def gemm(A, W, out, bias=None, rowadd=None, rows_per_batch=0, residual=None, act
     p.out_dtype = _DT[out.dtype]
     p.conv = 0
     st = _want_stats(p, stats_images, out.device) if stats_images > 0 else None
+    _sk = _want_splitk(p, out.device)
     with _Traced("gemm", 2.0 * p.M * p.N * p.K, f"M={p.M} N={p.N} K={p.K} act={p.act} res={int(residual is not None)}"):
         _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "gemm")
     _count()
@@ -278,6 +306,7 @@ def conv3x3(x, W, out, bias=None, rowadd=None, residual=None, stride=1, upsample
     # algorithmic FLOPs (trace only): zero-padded channels do not count
     fl = 2.0 * p.M * (logical_cout or p.N) * 9 * (logical_cin or Cin)
     st = _want_stats(p, Nimg, out.device, reuse=stats) if stats else None
+    _sk = _want_splitk(p, out.device)
     with _Traced("conv3x3", fl, f"N={p.Nimg} {p.H}x{p.Wd} {p.Cin}->{p.N} s={p.stride} up={p.upsample} res={int(residual is not None)}"):
         _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "conv3x3")
     _count()

@@ -490,14 +490,16 @@ class UNetModel(nn.Module):
         emb_all = self._embeddings(P, N, timesteps, y, anysd, dev)
         ctx16 = self._context16(context, N, dev)
         st = {"N": N, "ws": ws, "emb_all": emb_all, "ctx": ctx16, "anysd": anysd, "layer": 0, "xl": 0,
-              "kvc": getattr(self, "_ctx_kv", None) if anysd is None else None}
+              "kvc": getattr(self, "_ctx_kv", None)}
 
         # -- input conv --
         # Shared CFG halves (set by the DDIM stepper when x, c_concat, t and y of the uncond / cond halves are
         # identical, ddim.py:190-210): only the cross-attention context differs, so everything before the first
         # cross-attention K/V is computed for one half and duplicated -- bit-identical (every kernel is
         # batch-independent), ~3 % of a forward at the SD-1.5 geometry (the first self-attention is the big part).
-        share = bool(getattr(self, "_shared_halves", False)) and N % 2 == 0 and y is None and control is None and anysd is None
+        # (with the AnySD hook the stepper has checked that the two halves carry the same edit codes: the task-embedding add
+        # is then identical too; the visual tokens only enter at the cross-attention, after the shared prefix)
+        share = bool(getattr(self, "_shared_halves", False)) and N % 2 == 0 and y is None and control is None
         Nx = N // 2 if share else N
         xin = torch.zeros(Nx, H, W, self._cin_pad, **f16) if self._cin_pad != Cin else torch.empty(Nx, H, W, Cin, **f16)
         ops.nchw_to_nhwc(x[:Nx].contiguous(), xin, 0)

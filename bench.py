@@ -371,6 +371,10 @@ def main():
         tt = torch.full((2 * B,), 500, device=dev, dtype=torch.long)
         for _ in range(2):
             ops.trace.clear()
+            torch.cuda.synchronize()
+            # the host needs longer to issue an eager forward (~440 launches) than the GPU to run it: without a head start
+            # the event intervals would include launch latency.  ~25 ms of spinning keeps the device behind the host.
+            torch.cuda._sleep(int(5e7))
             model.apply_model(x_in, tt, cond2)       # eager (no graph): events around every contraction launch
         torch.cuda.synchronize()
         agg = {}

@@ -133,11 +133,21 @@ typedef struct {
                                squares} of the fp32 results.  rows_per_batch must be the rows of one image.  Every cell is
                                written exactly once in a fixed order: deterministic, independent of the batch.  NULL: off. */
     int stats_images;       /* image slots in `stats` (>= number of images, rounded up to the conv's images-per-tile) */
+    void* splitk_workspace; /* optional scratch for split-K (few output tiles, long K): anysd_gemm_splitk_workspace_bytes() bytes */
+    size_t splitk_workspace_bytes;
+    void* splitk_counters;  /* optional: >= 64 KB of device memory, ZERO before the first use (every launch re-arms it); may be
+                               shared by all stream-ordered launches of a device.  Without both, the plain schedule runs. */
+    size_t splitk_counters_bytes;
 } anysd_gemm_params;
 int anysd_gemm_f16(const anysd_gemm_params* p, anysd_stream_t stream);
 /* Slabs per image of the statistics layout for this contraction, or 0 when the shape cannot produce them (rows of one
  * image not a multiple of 32, conv patches not tiling the image exactly, GEGLU / fp32 output, non-tcgen05 shape). */
 int anysd_gemm_stats_slabs(const anysd_gemm_params* p);
+/* Bytes of `splitk_workspace` with which this contraction runs split-K (0: the schedule does not split it).  Whether a layer is
+ * split depends on its per-image geometry only (<= 128 output rows per image and a long K), never on the batch; the partial
+ * sums are added in split order by whichever unit finishes last.  The result therefore depends neither on the batch nor on the
+ * arrival order -- but a caller that withholds the scratch gets the unsplit summation order (differs in fp32 rounding). */
+size_t anysd_gemm_splitk_workspace_bytes(const anysd_gemm_params* p);
 
 /* ---- attention ---------------------------------------------------------------------------
  * CrossAttention.forward (attention.py:163-194) / xformers memory_efficient_attention (:233):

@@ -70,9 +70,9 @@ def main():
         out, inter = sampler.sample(S, 1, (4, h, h), {"c_concat": [c_cat], "c_crossattn": [c_txt]}, verbose=False, x_T=x_T,
                                     eta=0.0, unconditional_guidance_scale=scale, log_every_t=log_every_t,
                                     unconditional_conditioning={"c_concat": [c_cat], "c_crossattn": [u_txt]})
+        extra = {"pred_x0": torch.stack(inter["pred_x0"]).numpy()} if h <= 64 else {}      # (96x96: keep the fixture ~1 MB)
         np.savez(os.path.join(HERE, f"{name}.npz"), final=out.numpy(), x_inter=torch.stack(inter["x_inter"]).numpy(),
-                 pred_x0=torch.stack(inter["pred_x0"]).numpy(), S=S, seed=seed, scale=scale, log_every_t=log_every_t,
-                 in_sum=checksum(x_T, c_cat, c_txt, u_txt), wsum=wsum)
+                 S=S, seed=seed, scale=scale, log_every_t=log_every_t, in_sum=checksum(x_T, c_cat, c_txt, u_txt), wsum=wsum, **extra)
         print(f"{name} done in {time.time() - t0:.0f} s", flush=True)
 
     if "c1" in which:

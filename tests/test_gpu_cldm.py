@@ -87,16 +87,16 @@ def test_controlled_unet_and_denoiser_vs_reference(nets):
                                                              unconditional_guidance_scale=4.0, unconditional_conditioning=unc)
         outs.append(o)
     assert torch.equal(outs[0], outs[1])
-    # two-call guidance by hand, with the product's own update arithmetic
+    # two-call guidance (ddim_hacked.py:181-232: the model is called once per branch), then the product's own fused update
+    from anyedit_b200 import ops
     smp = DDIMSampler(den, use_cuda_graph=False)
     smp.make_schedule(5, verbose=False)
-    x = x_T
+    x = x_T.clone()
     for i, step in enumerate(np.flip(smp.ddim_timesteps)):
         index = 5 - i - 1
         t = torch.full((2,), int(step), device="cuda", dtype=torch.long)
-        e_c, e_u = den.apply_model(x, t, cond), den.apply_model(x, t, unc)
-        e = e_u + 4.0 * (e_c - e_u)
-        c = smp.ddim_coef_host[index]
-        pred = (x - c[0] * e) / c[1]
-        x = c[2] * pred + c[3] * e
+        eps = torch.cat([den.apply_model(x, t, unc), den.apply_model(x, t, cond)]).float().contiguous()
+        x_prev = torch.empty_like(x)
+        ops.cfg_ddim_step(x, eps, smp.ddim_coef[index], 4.0, True, x_prev)
+        x = x_prev
     assert torch.equal(outs[0], x)

@@ -29,6 +29,15 @@ def ops():
     return o
 
 
+@pytest.fixture
+def stats_everywhere(ops):
+    """The product asks for epilogue statistics from 1024 pixels per image on (a measured break-even); the kernel path itself
+    works from 32: the op tests exercise it on small maps too."""
+    old, ops.GN_EPILOGUE_MIN_ROWS = ops.GN_EPILOGUE_MIN_ROWS, 0
+    yield
+    ops.GN_EPILOGUE_MIN_ROWS = old
+
+
 def randn(seed, *shape, scale=1.0):
     g = torch.Generator().manual_seed(seed)
     return torch.randn(*shape, generator=g) * scale
@@ -383,7 +392,7 @@ def test_attention_aux_cols_unsupported_is_loud(ops):
 
 
 @pytest.mark.parametrize("N,Cin,Cout,H,W", [(2, 64, 320, 64, 64), (3, 128, 64, 8, 8), (2, 64, 192, 16, 32), (1, 64, 64, 96, 96)])
-def test_conv_epilogue_groupnorm_statistics(ops, N, Cin, Cout, H, W):
+def test_conv_epilogue_groupnorm_statistics(ops, stats_everywhere, N, Cin, Cout, H, W):
     """anysd_gemm_params::stats: the conv epilogue's per-(image, 32-row slab, channel) {sum, sum of squares} of its fp32
     results (incl. bias, time-embedding row, residual) fold to the per-image channel moments; an odd batch on an 8x8 map
     (two images per 128-row tile) exercises the padded image slot."""
@@ -402,7 +411,7 @@ def test_conv_epilogue_groupnorm_statistics(ops, N, Cin, Cout, H, W):
     assert rel(from_nhwc(out, N, H, W), ref) < 1e-3
 
 
-def test_gemm_epilogue_statistics_and_groupnorm_apply(ops):
+def test_gemm_epilogue_statistics_and_groupnorm_apply(ops, stats_everywhere):
     """Dense contraction (a SpatialTransformer proj_out: bias + residual) with statistics, then GroupNorm fed by them --
     single source and channel concat (two producers) -- against F.group_norm of the fp16 tensor the GEMM wrote."""
     N, HW, K, C1, C2 = 3, 256, 320, 320, 640
@@ -438,3 +447,36 @@ def test_gemm_epilogue_statistics_and_groupnorm_apply(ops):
     # a shape that cannot produce statistics says so (rows of one image not a multiple of 32)
     o = torch.empty(3 * 48, C1, dtype=torch.float16, device="cuda")
     assert ops.gemm(randn(41, 3 * 48, K).half().cuda(), randn(42, C1, K).half().cuda(), o, rows_per_batch=48, stats_images=3) is None
+
+
+def test_split_k_contractions(ops, stats_everywhere):
+    """Few output tiles + very long K (the 8x8 level's 2560 -> 1280 convs: 40..80 tiles over K = 23040 on 148 SMs): the schedule
+    splits K across CTAs; the partial sums are added in split order by whichever unit arrives last, so two runs agree bit for
+    bit and the result matches the unsplit arithmetic to fp32 summation-order noise."""
+    import ctypes as C
+    from anyedit_b200 import _lib
+    from anyedit_b200.unet import _pack_conv3
+    # conv 8x8, 2560 -> 1280, batch 16 (M = 1024), bias + residual + epilogue statistics
+    N, Cin, Cout, H, W = 16, 2560, 1280, 8, 8
+    x, w, b, res = randn(51, N, Cin, H, W), randn(52, Cout, Cin, 3, 3, scale=0.01), randn(53, Cout), randn(54, N, Cout, H, W)
+    xin, wp, rin = to_nhwc16(x), _pack_conv3(w, "cuda"), to_nhwc16(res).view(-1, Cout)
+    outs = []
+    for _ in range(2):
+        out = torch.empty(N, H, W, Cout, dtype=torch.float16, device="cuda")
+        st = ops.conv3x3(xin, wp, out.view(-1, Cout), bias=b.cuda(), residual=rin, stats=True)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    p = _lib.GemmParams()
+    p.A, p.W, p.out = xin.data_ptr(), wp.data_ptr(), outs[0].data_ptr()
+    p.M, p.N, p.K, p.lda, p.ldw, p.ldo = N * H * W, Cout, 9 * Cin, Cin, 9 * Cin, Cout
+    p.out_dtype, p.conv, p.Nimg, p.H, p.Wd, p.Cin, p.stride, p.rows_per_batch = _lib.F16, 1, N, H, W, Cin, 1, H * W
+    assert _lib.load().anysd_gemm_splitk_workspace_bytes(C.byref(p)) > 0, "the 8x8 conv is expected to run split-K"
+    ref = F.conv2d(x.half().float(), w.half().float(), b, padding=1) + res.half().float()
+    assert rel(from_nhwc(outs[0], N, H, W), ref) < 1e-3
+    got = st.parts[0][0][:N].double().cpu().sum(1)
+    assert rel(got[..., 0], ref.double().sum((2, 3))) < 2e-4
+    # dense: M = 1024, N = 1280, K = 5120 with residual (the deep level's FF output projection)
+    A, Wt, bb, r = randn(61, 1024, 5120), randn(62, 1280, 5120, scale=5120 ** -0.5), randn(63, 1280), randn(64, 1024, 1280)
+    o = torch.empty(1024, 1280, dtype=torch.float16, device="cuda")
+    ops.gemm(A.half().cuda(), Wt.half().cuda(), o, bias=bb.cuda(), residual=r.half().cuda())
+    assert rel(o, A.half().float() @ Wt.half().float().t() + bb + r.half().float()) < 1e-3

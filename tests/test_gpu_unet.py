@@ -508,3 +508,40 @@ def test_three_way_ip2p_guidance():
     e = rel(outs[0], ref)
     print(f"[three-way IP2P guidance, 10 steps] final-latent rel-L2 vs oracle = {e:.3e}")
     assert e < LATENT_TOL_CFG, e
+
+
+def test_anysd_sampling_shared_halves_and_kept_kv_bit_identical(monkeypatch):
+    """BASELINE configs[2] path (AnySDDenoiser: task embedding + router + expert streams) through the sampler: the shared
+    CFG prefix and the kept text K/V are bit-identical to the plain path; different edit codes in the two halves switch the
+    sharing off."""
+    from anyedit_b200.anysd import AnySDDenoiser, MoE
+    from anyedit_b200.ddim import DDIMSampler
+    from oracle import anysd_oracle, weights
+    net, sd, cfg = _build("tiny_a", 11)
+    E, T, B = 3, 6, 3
+    moe = MoE(net, None, expert_num=E, num_tasks=T).cuda()
+    shapes = anysd_oracle.adapter_shapes({k: tuple(v.shape) for k, v in sd.items()}, T, E, cfg["context_dim"])
+    moe.load_state_dict(weights.make_state_dict(shapes, 77, gain=2.0), strict=False)
+    den = AnySDDenoiser(moe).cuda()
+    gen = torch.Generator().manual_seed(19)
+    x_T, c_cat = torch.randn(B, 4, 16, 16, generator=gen).cuda(), torch.randn(B, 4, 16, 16, generator=gen).cuda()
+    c_txt, u_txt = torch.randn(B, 7, 64, generator=gen).cuda(), torch.randn(B, 7, 64, generator=gen).cuda()
+    vis, code = torch.randn(B, 5, 64, generator=gen).cuda(), torch.tensor([0, 5, 2]).cuda()
+    cond = {"c_concat": [c_cat], "c_crossattn": [c_txt], "c_visual": [vis], "c_task": code}
+    unc = {"c_concat": [c_cat], "c_crossattn": [u_txt], "c_visual": [vis], "c_task": code}
+    outs = {}
+    for share in ("1", "0"):
+        monkeypatch.setenv("ANYSD_SHARE_CFG", share)
+        monkeypatch.setenv("ANYSD_CTX_KV", share)
+        for graph in (True, False):
+            smp = DDIMSampler(den, use_cuda_graph=graph)
+            outs[(share, graph)], _ = smp.sample(5, B, (4, 16, 16), cond, verbose=False, x_T=x_T, eta=0.0, unconditional_guidance_scale=7.5,
+                                                 unconditional_conditioning=unc)
+            assert next(iter(smp._graphs.values())).shared == (share == "1")
+    ref = outs[("0", False)]
+    assert all(torch.equal(v, ref) for v in outs.values())
+    monkeypatch.setenv("ANYSD_SHARE_CFG", "1")
+    smp = DDIMSampler(den, use_cuda_graph=False)
+    smp.sample(5, B, (4, 16, 16), cond, verbose=False, x_T=x_T, eta=0.0, unconditional_guidance_scale=7.5,
+               unconditional_conditioning={**unc, "c_task": torch.tensor([1, 1, 1]).cuda()})
+    assert next(iter(smp._graphs.values())).shared is False
