@@ -30,7 +30,9 @@ struct PCfg {
     static constexpr int B_BYTES = (P_BN / CTAS) * P_BK * 2;
     static constexpr int STAGE_BYTES = P_A_BYTES + B_BYTES;
     static constexpr int STAGES = CTAS == 2 ? 4 : 3;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + P_NSTG * P_STG_BYTES + 1024 + 256;
+    // + 1024 alignment slack + 512 (mbarriers, TMEM slot) + the epilogue parameters of a tile staged by warp 3, double-buffered:
+    // 2 x 256 bias, 2 x 256 folded-LayerNorm column sums, 2 x 128 x {-mean, rstd} row coefficients
+    static constexpr int SMEM = STAGES * STAGE_BYTES + P_NSTG * P_STG_BYTES + 1024 + 512 + 2048 + 2048 + 2048;
 };
 
 struct PArgs {
@@ -54,6 +56,14 @@ struct PArgs {
     int splits, kb_per_split, num_units;
     float* sk_ws;                            // [tile][cta of the pair][split][128 rows][bn] fp32
     unsigned int* sk_cnt;                    // [tile][cta of the pair][8 epilogue warps], zero between launches
+    // LayerNorm around the contraction (anysd_gemm_params::row_stats / ln_stats; template parameter L):
+    //   producer side: per-row {sum, sum of squares} of the OUTPUT per 64-column slab -> row_stats[slab][M] (float2)
+    //   consumer side: A is the un-normalised x, W carries gamma, out = rstd_m (acc - mean_m colsum_n) + bias_n
+    float* row_stats;
+    const float* ln_stats;                   // [ln_slabs][M] float2 = the producer's row_stats
+    const float* ln_colsum;                  // [N]
+    int ln_slabs;
+    float ln_eps, ln_inv_k;
 };
 
 // ---- PTX wrappers (same forms as gemm_tc5.cu) -------------------------------------------------------
@@ -240,7 +250,9 @@ __device__ __forceinline__ TileCoord tile_coord(const PArgs& p, int tile, int ra
 // asks for one of them -- the plain variant keeps the epilogue of the HBM- / issue-bound K = 320 projections and GEGLU
 // contractions free of their branches and registers ([measured] the merged kernel ran the 161 linear launches of a forward
 // in 6.9 ms instead of 6.2 ms).
-template <bool CONV, int CTAS, bool X>
+// L ("LayerNorm"): the row-statistics output and the folded-LayerNorm input, dense contractions only (same reasoning: the
+// variants that do not use them do not pay for them).
+template <bool CONV, int CTAS, bool X, bool L>
 __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const PArgs p) {
@@ -261,6 +273,16 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto res_bar = [&](int b) { return bar_base + 8u * (2 * P_STAGES + 4 + b); };
     volatile uint32_t* tmem_slot =
         reinterpret_cast<volatile uint32_t*>(smem + P_STAGES * P_STAGE_BYTES + P_NSTG * P_STG_BYTES + 8 * (2 * P_STAGES + 4 + 16));
+    auto cpfull_bar = [&](int b) { return bar_base + 256u + 8u * b; };       // epilogue parameters of tile t staged / consumed
+    auto cpempty_bar = [&](int b) { return bar_base + 272u + 8u * b; };
+    unsigned char* cp_base = smem + P_STAGES * P_STAGE_BYTES + P_NSTG * P_STG_BYTES + 512;
+    float* cp_bias = reinterpret_cast<float*>(cp_base);                      // [2][256]
+    float* cp_cs = reinterpret_cast<float*>(cp_base + 2048);                 // [2][256]  (L)
+    float2* ln_buf = reinterpret_cast<float2*>(cp_base + 4096);              // [2][128] {-mean, rstd}  (L)
+    // bias / column sums / row coefficients reach the epilogue through shared memory: every tile touches new columns, so a
+    // direct __ldg is an L2 round trip that 8 warps x every 32-column step would each sit out ([measured] the folded-LayerNorm
+    // epilogue with direct loads: GEGLU 65536 x 2560 x 320 in 222 us instead of 142)
+    const bool staged = p.bias != nullptr || (L && p.ln_stats != nullptr);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -280,6 +302,10 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             pm_init(tempty_bar(b), 8 * CTAS);   // one arrive per epilogue warp of every CTA of the pair
         }
         for (int b = 0; b < 16; ++b) pm_init(res_bar(b), 1);      // 8 epilogue warps x 2 residual slabs
+        for (int b = 0; b < 2; ++b) {
+            pm_init(cpfull_bar(b), 1);
+            pm_init(cpempty_bar(b), 8);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -373,6 +399,47 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (CTAS == 2) p_commit2(tfull_bar(buf)); else p_commit(tfull_bar(buf));
             }
         }
+    } else if (warp == 3) {
+        // ===== parameter stager: bias (and, L, the folded LayerNorm's column sums and per-row {-mean, rstd}) of the tile's columns /
+        // rows into shared memory, up to two tiles ahead of the epilogue.  The row moments are folded slab by slab in index
+        // order, the final combine runs in double. =====
+        if (staged) {
+            const bool ln_in = L && p.ln_stats != nullptr;
+            const bool sp = X && p.splits > 1;
+            uint32_t t = 0;
+            for (int unit = cta_first; unit < p.num_units; unit += cta_stride, ++t) {
+                const TileCoord c = tile_coord<CONV, CTAS>(p, sp ? unit / p.splits : unit, rank);
+                const uint32_t b = t & 1, ph = (t >> 1) & 1;
+                pm_wait(cpempty_bar(b), ph ^ 1);
+                for (int i = lane; i < p.bn; i += 32) {
+                    const int n = c.n0 + i;
+                    cp_bias[b * P_BN + i] = (p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f;
+                    if (ln_in) cp_cs[b * P_BN + i] = n < p.N ? __ldg(p.ln_colsum + n) : 0.f;
+                }
+                if (ln_in) {
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int r = rr * 32 + lane;
+                        int m = c.m0 + r;
+                        if (m >= p.M) m = p.M - 1;
+                        const float2* sp2 = reinterpret_cast<const float2*>(p.ln_stats) + m;
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 5
+                        for (int sl = 0; sl < p.ln_slabs; ++sl) {
+                            const float2 f = __ldg(sp2 + (size_t)sl * p.M);
+                            s1 += f.x;
+                            s2 += f.y;
+                        }
+                        const double mean = (double)s1 * (double)p.ln_inv_k;
+                        double var = (double)s2 * (double)p.ln_inv_k - mean * mean;
+                        if (var < 0.0) var = 0.0;
+                        ln_buf[b * P_BM + r] = make_float2(-(float)mean, rsqrtf((float)var + p.ln_eps));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) pm_arrive(cpfull_bar(b));
+            }
+        }
     } else if (warp >= 4) {
         // ===== epilogue: 8 INDEPENDENT warps (no CTA-wide barriers).  TMEM lane group = warp % 4 (hardware rule),
         // lane = accumulator row.  Warps 4..7 take the even 64-column sub-tiles, warps 8..11 the odd ones.  Each warp
@@ -431,6 +498,17 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
             }
             const float* radd = p.rowadd ? p.rowadd + (size_t)img * p.ld_rowadd : nullptr;
+            // this tile's staged parameters (warp 3); folded LayerNorm: this thread's row coefficients
+            float ln_nmean = 0.f, ln_rstd = 1.f;
+            const bool ln_in = L && p.ln_stats != nullptr;
+            if (staged) pm_wait(cpfull_bar(buf), bph);
+            const float* tb = cp_bias + buf * P_BN;
+            const float* tcs = cp_cs + buf * P_BN;
+            if (ln_in) {
+                const float2 cf = ln_buf[buf * P_BM + row];
+                ln_nmean = cf.x;
+                ln_rstd = cf.y;
+            }
             pm_wait(tfull_bar(buf), bph);
             p_fence_after();
             // ---- split-K: dump this unit's raw accumulators, find out whether this warp is the last of the tile's units ----
@@ -494,6 +572,7 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 unsigned char* stg = wstg_ptr + b * SLAB + lane * 128;
                 if (p.has_res) pm_wait(rbar(b), (q >> 1) & 1);
                 if (!sk_last) continue;                        // another unit finishes this tile (barrier phases stay in step)
+                float rs1 = 0.f, rs2 = 0.f;                    // L: this row's {sum, sum of squares} over the 64-column slab
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {         // 2 x 32 output columns
                     float v[32];
@@ -506,12 +585,27 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         p_tmem_ld32(tmem_base + buf * P_BN + ((uint32_t)(lg * 32) << 16) + ac, r0);
                         p_tmem_ld32(tmem_base + buf * P_BN + ((uint32_t)(lg * 32) << 16) + ac + 32, r1);
                         p_tmem_wait_ld();
-                        const int nb = c.n0 + ac;
-                        if (p.bias) {                           // N % 128 == 0 for GEGLU: the 64 columns are in range
+                        if (ln_in) {                            // folded LayerNorm (bias always present: beta W^T + b)
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + i);
-                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 32) + i);
+                                const float4 b0 = *(reinterpret_cast<const float4*>(tb + ac) + i);
+                                const float4 b1 = *(reinterpret_cast<const float4*>(tb + ac + 32) + i);
+                                const float4 c0 = *(reinterpret_cast<const float4*>(tcs + ac) + i);
+                                const float4 c1 = *(reinterpret_cast<const float4*>(tcs + ac + 32) + i);
+                                r0[4 * i] = __float_as_uint(fmaf(ln_rstd, fmaf(ln_nmean, c0.x, __uint_as_float(r0[4 * i])), b0.x));
+                                r0[4 * i + 1] = __float_as_uint(fmaf(ln_rstd, fmaf(ln_nmean, c0.y, __uint_as_float(r0[4 * i + 1])), b0.y));
+                                r0[4 * i + 2] = __float_as_uint(fmaf(ln_rstd, fmaf(ln_nmean, c0.z, __uint_as_float(r0[4 * i + 2])), b0.z));
+                                r0[4 * i + 3] = __float_as_uint(fmaf(ln_rstd, fmaf(ln_nmean, c0.w, __uint_as_float(r0[4 * i + 3])), b0.w));
+                                r1[4 * i] = __float_as_uint(fmaf(ln_rstd, fmaf(ln_nmean, c1.x, __uint_as_float(r1[4 * i])), b1.x));
+                                r1[4 * i + 1] = __float_as_uint(fmaf(ln_rstd, fmaf(ln_nmean, c1.y, __uint_as_float(r1[4 * i + 1])), b1.y));
+                                r1[4 * i + 2] = __float_as_uint(fmaf(ln_rstd, fmaf(ln_nmean, c1.z, __uint_as_float(r1[4 * i + 2])), b1.z));
+                                r1[4 * i + 3] = __float_as_uint(fmaf(ln_rstd, fmaf(ln_nmean, c1.w, __uint_as_float(r1[4 * i + 3])), b1.w));
+                            }
+                        } else if (p.bias) {                    // N % 128 == 0 for GEGLU: the 64 columns are in range
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 b0 = *(reinterpret_cast<const float4*>(tb + ac) + i);
+                                const float4 b1 = *(reinterpret_cast<const float4*>(tb + ac + 32) + i);
                                 r0[4 * i] = __float_as_uint(__uint_as_float(r0[4 * i]) + b0.x);
                                 r0[4 * i + 1] = __float_as_uint(__uint_as_float(r0[4 * i + 1]) + b0.y);
                                 r0[4 * i + 2] = __float_as_uint(__uint_as_float(r0[4 * i + 2]) + b0.z);
@@ -552,28 +646,35 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
                         }
-                        if (nb + 32 <= p.N) {
-                            if (p.bias) {
+                        // bias (and the folded LayerNorm's column sums) from the staged copy: zero beyond column N
+                        if (ln_in) {                           // folded LayerNorm: rstd (acc - mean colsum) + (beta W^T + b)
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + i);
-                                    v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
-                                }
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 bb = *(reinterpret_cast<const float4*>(tb + ac) + i);
+                                const float4 cc = *(reinterpret_cast<const float4*>(tcs + ac) + i);
+                                v[4 * i] = fmaf(ln_rstd, fmaf(ln_nmean, cc.x, v[4 * i]), bb.x);
+                                v[4 * i + 1] = fmaf(ln_rstd, fmaf(ln_nmean, cc.y, v[4 * i + 1]), bb.y);
+                                v[4 * i + 2] = fmaf(ln_rstd, fmaf(ln_nmean, cc.z, v[4 * i + 2]), bb.z);
+                                v[4 * i + 3] = fmaf(ln_rstd, fmaf(ln_nmean, cc.w, v[4 * i + 3]), bb.w);
                             }
-                            if (radd) {
+                        } else if (p.bias) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 bb = *(reinterpret_cast<const float4*>(tb + ac) + i);
+                                v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+                            }
+                        }
+                        if (radd) {
+                            if (nb + 32 <= p.N) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     const float4 bb = __ldg(reinterpret_cast<const float4*>(radd + nb) + i);
                                     v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
                                 }
-                            }
-                        } else {
+                            } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                if (nb + i < p.N) {
-                                    if (p.bias) v[i] += __ldg(p.bias + nb + i);
-                                    if (radd) v[i] += __ldg(radd + nb + i);
-                                }
+                                for (int i = 0; i < 32; ++i)
+                                    if (nb + i < p.N) v[i] += __ldg(radd + nb + i);
                             }
                         }
                         if (p.act == 1) {
@@ -600,6 +701,13 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             for (int i = 0; i < 8; ++i) vv[i] += rr[i];
                         }
                         *slot = pack8(vv);
+                        if (L && p.row_stats != nullptr) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                rs1 += vv[i];
+                                rs2 = fmaf(vv[i], vv[i], rs2);
+                            }
+                        }
                     }
                     if (X && p.stats != nullptr) {
                         // GroupNorm statistics of what was just produced (fp32, before the fp16 rounding): per channel over
@@ -624,6 +732,11 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             reinterpret_cast<float2*>(p.stats)[((size_t)img * p.stats_spi + sii) * p.N + col] = make_float2(s1, s2);
                     }
                 }
+                if (L && p.row_stats != nullptr) {             // one cell per (64-column slab, row): written once, by one thread
+                    const int m = c.m0 + row;
+                    if (m < p.M)
+                        reinterpret_cast<float2*>(p.row_stats)[(size_t)((c.n0 >> 6) + j) * p.M + m] = make_float2(rs1, rs2);
+                }
                 p_fence_async_smem();                          // generic-proxy writes -> visible to the TMA store
                 __syncwarp();
                 if (lane == 0) slab_store(b, c, j);
@@ -635,6 +748,10 @@ gemm_tc5p_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (lane == 0) {
                     if (CTAS == 2) pm_arrive_remote(tempty_bar(buf), 0); else pm_arrive(tempty_bar(buf));
                 }
+            }
+            if (staged) {                                      // ... and the staged parameters back to warp 3
+                __syncwarp();
+                if (lane == 0) pm_arrive(cpempty_bar(buf));
             }
         }
         if (lane == 0) p_store_wait<0>();                      // smem must outlive the last store
@@ -789,6 +906,25 @@ size_t tc5p_splitk_bytes(const anysd_gemm_params* q) {
     return p_splitk_bytes(tiles_m, q->N, ctas, bn, splits);
 }
 
+// LayerNorm around a contraction (row_stats output / ln_stats input): NULL when this kernel can do it, else the reason.
+const char* tc5p_ln_unsupported(const anysd_gemm_params* q) {
+    if (q->conv) return "dense contractions only";
+    if (q->out_dtype != ANYSD_F16) return "fp16 output only";
+    if (q->row_stats != nullptr) {
+        if (q->act != 0) return "row statistics need act = 0";
+        if (q->N % 64 != 0) return "row statistics need N % 64 == 0";
+        if ((uintptr_t)q->row_stats % 8) return "row_stats must be 8-byte aligned";
+    }
+    if (q->ln_stats != nullptr) {
+        if (q->K % 64 != 0) return "folded LayerNorm needs K % 64 == 0";
+        if (q->bias == nullptr || q->ln_colsum == nullptr) return "folded LayerNorm needs bias (beta W^T + b) and ln_colsum";
+        if (((uintptr_t)q->ln_stats % 8) || ((uintptr_t)q->ln_colsum % 16)) return "ln_stats / ln_colsum misaligned";
+        if (q->N % 32 != 0) return "folded LayerNorm needs N % 32 == 0";
+        if (q->act != 0 && q->act != 1 && q->act != 2) return "folded LayerNorm: act must be 0, 1 or 2";
+    }
+    return nullptr;
+}
+
 bool tc5p_supported(const anysd_gemm_params* q) {
     if (q->out_dtype != ANYSD_F16) return false;
     if (q->N % 8 != 0 || q->K % 8 != 0) return false;
@@ -808,7 +944,7 @@ bool tc5p_supported(const anysd_gemm_params* q) {
     return p_get_encode() != nullptr;
 }
 
-template <bool CONV, int CTAS, bool X>
+template <bool CONV, int CTAS, bool X, bool L = false>
 static int p_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmR,
                     const PArgs& a, cudaStream_t st) {
     static bool done[64];
@@ -816,7 +952,7 @@ static int p_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     cudaGetDevice(&dev);
     dev &= 63;
     if (!done[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc5p_kernel<CONV, CTAS, X>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc5p_kernel<CONV, CTAS, X, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              PCfg<CTAS>::SMEM);
         if (e != cudaSuccess) {
             set_error("tcgen05 gemm: smem opt-in failed: %s", cudaGetErrorString(e));
@@ -839,7 +975,7 @@ static int p_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CTAS == 2 ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc5p_kernel<CONV, CTAS, X>, tmA, tmB, tmO, tmR, a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc5p_kernel<CONV, CTAS, X, L>, tmA, tmB, tmO, tmR, a);
     if (e != cudaSuccess) {
         set_error("tcgen05 gemm launch failed: %s", cudaGetErrorString(e));
         return ANYSD_ECUDA;
@@ -866,7 +1002,7 @@ static void p_conv_patch(const anysd_gemm_params* q, int* Ho, int* Wo, int* BW, 
 // ANYSD_GEMM_SPLITK=0|n forces a count (experiments).
 static int p_geometry_splits(const anysd_gemm_params* q, int num_kb) {
     static const char* force_sk = getenv("ANYSD_GEMM_SPLITK");
-    if (q->act == 2 || q->out_dtype != ANYSD_F16) return 1;
+    if (q->act == 2 || q->out_dtype != ANYSD_F16 || q->row_stats != nullptr || q->ln_stats != nullptr) return 1;
     int rows_per_image = q->rows_per_batch;
     if (q->conv) {
         int Ho, Wo, BW, BH, NB;
@@ -931,6 +1067,20 @@ int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
         a.stats = q->stats;
         a.stats_hw = q->rows_per_batch;
         a.stats_nimg = q->stats_images;
+    }
+    a.row_stats = q->row_stats;
+    a.ln_stats = q->ln_stats;
+    a.ln_colsum = q->ln_colsum;
+    a.ln_slabs = q->K / 64;
+    a.ln_eps = q->ln_eps;
+    a.ln_inv_k = 1.0f / (float)q->K;
+    const bool ln = q->row_stats != nullptr || q->ln_stats != nullptr;
+    if (ln) {
+        const char* why = tc5p_ln_unsupported(q);
+        if (why) {
+            set_error("gemm: LayerNorm fold / row statistics: %s (M=%d N=%d K=%d act=%d)", why, q->M, q->N, q->K, q->act);
+            return ANYSD_EUNSUPPORTED;
+        }
     }
     a.bias = q->bias;
     a.rowadd = q->rowadd;
@@ -1005,6 +1155,13 @@ int launch_gemm_tc5p(const anysd_gemm_params* q, cudaStream_t st) {
     a.sk_ws = (float*)q->splitk_workspace;
     a.sk_cnt = (unsigned int*)q->splitk_counters;
     const bool ext = a.stats != nullptr || a.splits > 1 || a.act >= 3;
+    if (ln) {
+        if (ext) {
+            set_error("gemm: LayerNorm fold / row statistics cannot be combined with GroupNorm statistics, split-K or GELU epilogues");
+            return ANYSD_EUNSUPPORTED;
+        }
+        return ctas == 2 ? p_launch<false, 2, false, true>(tmA, tmB, tmO, tmR, a, st) : p_launch<false, 1, false, true>(tmA, tmB, tmO, tmR, a, st);
+    }
     if (ext) {
         if (q->conv) return ctas == 2 ? p_launch<true, 2, true>(tmA, tmB, tmO, tmR, a, st) : p_launch<true, 1, true>(tmA, tmB, tmO, tmR, a, st);
         return ctas == 2 ? p_launch<false, 2, true>(tmA, tmB, tmO, tmR, a, st) : p_launch<false, 1, true>(tmA, tmB, tmO, tmR, a, st);

@@ -240,11 +240,19 @@ def _want_splitk(p, dev):
     return ws
 
 
+def row_stats_buffer(M, C, device):
+    """fp32 [C / 64, M, 2]: the per-row moments a contraction's epilogue writes for the LayerNorm folded into its consumer."""
+    assert C % 64 == 0
+    return torch.empty(C // 64, M, 2, dtype=torch.float32, device=device)
+
+
 def gemm(A, W, out, bias=None, rowadd=None, rows_per_batch=0, residual=None, act=0, M=None, K=None, lda=None,
-         N=None, ldw=None, ld_rowadd=None, stats_images=0):
+         N=None, ldw=None, ld_rowadd=None, stats_images=0, row_stats=None, ln=None):
     """out[M, N'] = epilogue(A[M, K] @ W[N, K]^T); see anysd_gemm_params.
     ``stats_images`` > 0 (with ``rows_per_batch`` = rows of one image): also produce the GroupNorm statistics of ``out`` in the
-    epilogue; returns a GnStats (None when the shape cannot)."""
+    epilogue; returns a GnStats (None when the shape cannot).
+    ``row_stats`` (row_stats_buffer(M, N)): per-row moments of ``out`` for a LayerNorm folded into the consumer.
+    ``ln`` = (row statistics of A, column sums of the gamma-scaled W, eps): LayerNorm(A) @ W^T + b with A un-normalised."""
     _cuda(A, W, out)
     p = GemmParams()
     p.A, p.W, p.out = A.data_ptr(), W.data_ptr(), out.data_ptr()
@@ -263,8 +271,16 @@ def gemm(A, W, out, bias=None, rowadd=None, rows_per_batch=0, residual=None, act
     p.act = act
     p.out_dtype = _DT[out.dtype]
     p.conv = 0
+    if row_stats is not None:
+        assert row_stats.dtype == torch.float32 and row_stats.is_contiguous() and row_stats.numel() == (p.N // 64) * p.M * 2
+        p.row_stats = row_stats.data_ptr()
+    if ln is not None:
+        lst, lcs, leps = ln
+        assert lst.dtype == torch.float32 and lst.is_contiguous() and lst.numel() == (p.K // 64) * p.M * 2, "ln statistics shape"
+        assert lcs.dtype == torch.float32 and lcs.is_contiguous() and lcs.numel() == p.N and bias is not None
+        p.ln_stats, p.ln_colsum, p.ln_eps = lst.data_ptr(), lcs.data_ptr(), float(leps)
     st = _want_stats(p, stats_images, out.device) if stats_images > 0 else None
-    _sk = _want_splitk(p, out.device)
+    _sk = _want_splitk(p, out.device) if (row_stats is None and ln is None) else None
     with _Traced("gemm", 2.0 * p.M * p.N * p.K, f"M={p.M} N={p.N} K={p.K} act={p.act} res={int(residual is not None)}"):
         _lib.check(_lib.load().anysd_gemm_f16(C.byref(p), _stream()), "gemm")
     _count()

@@ -14,6 +14,7 @@ Supported configuration = what the AnySD / SD-1.5 / anydoor.yaml geometries use:
 ``resblock_updown`` or ``n_embed``; anything else raises ``NotImplementedError`` at construction.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -150,6 +151,14 @@ class _Embedding(nn.Module):
 
 
 # ---- packed (kernel-layout) weights -------------------------------------------------------------
+
+# LayerNorm folded into the contractions either side of it (row moments from the producer's epilogue, gamma / beta folded into the
+# consumer's weights: anysd_gemm_params::row_stats / ln_stats).  OFF by default: [measured, B200, tests/diag_lnfold.py,
+# profiles/r2_lnfold_*.txt] the consumers are epilogue-bound contractions (K = 320 .. 1280) and the two extra FMAs + the
+# column-sum operand per accumulator cost them more (GEGLU 65536 x 2560 x 320: 140 -> 167 us even with every parameter
+# staged in shared memory) than the 21 us layernorm launch they replace; ANYSD_LN_FOLD=1 switches it on.
+_LN_FOLD = os.environ.get("ANYSD_LN_FOLD", "0")[:1] == "1"
+
 
 def _h(t, dev):
     return t.detach().to(device=dev, dtype=torch.float16).contiguous()
@@ -635,9 +644,11 @@ class UNetModel(nn.Module):
         out._gn = ops.conv3x3(b, d["c2_w"], out.view(-1, cout), bias=d["c2_b"], residual=res, stats=True)
         return out
 
-    def _attn(self, ad, xq, ctx, N, n_q, st, self_attn, residual, out, expert=False, q_pre=None):
+    def _attn(self, ad, xq, ctx, N, n_q, st, self_attn, residual, out, expert=False, q_pre=None, ln=None, out_stats=False):
         """CrossAttention.forward (attention.py:163-194) + residual add of the caller (:272-273).
-        ``q_pre``: the query projection computed by the caller (shared CFG halves), ``xq`` is then unused."""
+        ``q_pre``: the query projection computed by the caller (shared CFG halves), ``xq`` is then unused.
+        ``ln`` = (row moments of xq, folded pack): xq is the UN-normalised input of the block's LayerNorm, which is folded into
+        the query (/ fused q|k|v) projection; ``out_stats``: the output projection leaves ``out._ln`` for the next LayerNorm."""
         C = ad["heads"] * ad["d"]
         hs = ad["hs"]
         Cp = ad["heads"] * hs                     # projection width with padded heads (== C unless d % 16 != 0)
@@ -645,7 +656,10 @@ class UNetModel(nn.Module):
         a = torch.empty(N * n_q, C, dtype=torch.float16, device=dev)
         if self_attn:
             qkv = torch.empty(N * n_q, 3 * Cp, dtype=torch.float16, device=dev)
-            ops.gemm(xq, ad["qkv_w"], qkv, bias=ad["qkv_b"])
+            if ln is not None:
+                ops.gemm(xq, ln[1]["w"], qkv, bias=ln[1]["b"], ln=(ln[0], ln[1]["cs"], 1e-5))
+            else:
+                ops.gemm(xq, ad["qkv_w"], qkv, bias=ad["qkv_b"])
             ops.attention(qkv, qkv[:, Cp:], qkv[:, 2 * Cp:], a, N, ad["heads"], n_q, n_q, ad["d"],
                           3 * Cp, 3 * Cp, 3 * Cp, C, head_stride=hs, aux_cols=ad["aux"])
         else:
@@ -654,7 +668,10 @@ class UNetModel(nn.Module):
                 q = q_pre
             else:
                 q = torch.empty(N * n_q, Cp, dtype=torch.float16, device=dev)
-                ops.gemm(xq, ad["q_w"], q)
+                if ln is not None:
+                    ops.gemm(xq, ln[1]["w"], q, bias=ln[1]["b"], ln=(ln[0], ln[1]["cs"], 1e-5))
+                else:
+                    ops.gemm(xq, ad["q_w"], q)
             # context K/V: constant over the steps of one sampling run, so the DDIM stepper keeps them (st["kvc"]:
             # mode "fill" computes into persistent buffers, mode "use" skips the projection)
             kvc, xl = st.get("kvc"), st.get("xl", 0)
@@ -673,7 +690,30 @@ class UNetModel(nn.Module):
                 st["anysd"]["experts"](st["layer"], q, a, N, n_q, ad["heads"], ad["d"], hs, ad["aux"])
             if expert:
                 st["layer"] += 1
-        ops.gemm(a, ad["o_w"], out, bias=ad["o_b"], residual=residual)
+        if out_stats:
+            out._ln = ops.row_stats_buffer(N * n_q, C, dev)
+        ops.gemm(a, ad["o_w"], out, bias=ad["o_b"], residual=residual, row_stats=out._ln if out_stats else None)
+
+    @staticmethod
+    def _ln_folded(b):
+        """The three LayerNorms of a BasicTransformerBlock (attention.py:262-264) folded into the projections that consume them:
+        W' = W diag(gamma) (fp16), colsum_n = sum_k W'[n, k] (of the fp16 values: the mean term then cancels exactly against the
+        accumulator), bias' = b + W beta.  Built on first use from the kernel-layout packs, dropped with them."""
+        fb = b.get("_fold")
+        if fb is None:
+            def fold(w16, bias, gamma, beta):
+                w32 = w16.float()
+                wf = (w32 * gamma[None, :]).to(torch.float16).contiguous()
+                bb = w32 @ beta
+                if bias is not None:
+                    bb = bb + bias
+                return {"w": wf, "cs": wf.float().sum(1).contiguous(), "b": bb.contiguous()}
+            a1 = b["attn1"]
+            fb = {"a1": fold(a1["qkv_w"], a1["qkv_b"], b["ln1_w"], b["ln1_b"]) if b["self"] else fold(a1["q_w"], None, b["ln1_w"], b["ln1_b"]),
+                  "a2": fold(b["attn2"]["q_w"], None, b["ln2_w"], b["ln2_b"]),
+                  "ff1": fold(b["ff1_w"], b["ff1_b"], b["ln3_w"], b["ln3_b"])}
+            b["_fold"] = fb
+        return fb
 
     @staticmethod
     def _dup_rows(t):
@@ -685,6 +725,9 @@ class UNetModel(nn.Module):
         if g is not None:                                       # per-image epilogue statistics travel with the images
             n = t.shape[0]
             out._gn = ops.GnStats([(torch.cat([b[:n], b[:n]]), c) for b, c in g.parts], g.S)
+        r = getattr(t, "_ln", None)
+        if r is not None:                                       # per-row moments [slabs, rows, 2] likewise
+            out._ln = torch.cat([r, r], 1).contiguous()
         return out
 
     def _transformer(self, d, h, st, share=False):
@@ -700,7 +743,10 @@ class UNetModel(nn.Module):
         g = torch.empty_like(h)
         ops.groupnorm(h, d["gn_w"], d["gn_b"], g, N, n, 1e-6, False, st["ws"], stats=getattr(h, "_gn", None))
         t = torch.empty(M, inner, dtype=torch.float16, device=dev)
-        ops.gemm(g.view(M, C), d["pin_w"], t, bias=d["pin_b"])
+        fold0 = _LN_FOLD and inner % 64 == 0
+        if fold0:
+            t._ln = ops.row_stats_buffer(M, inner, dev)
+        ops.gemm(g.view(M, C), d["pin_w"], t, bias=d["pin_b"], row_stats=t._ln if fold0 else None)
         for i, b in enumerate(d["blocks"]):
             ctx = st["ctx"][i] if i < len(st["ctx"]) else st["ctx"][-1]
             if share and not b["self"]:
@@ -708,33 +754,53 @@ class UNetModel(nn.Module):
                 # nothing more can be shared, widen to the full batch here
                 t, h = self._dup_rows(t), self._dup_rows(h)
                 N, M, share = 2 * N, 2 * M, False
-            ln = torch.empty_like(t)
-            ops.layernorm(t, b["ln1_w"], b["ln1_b"], ln)
-            t2 = torch.empty_like(t)
-            if b["self"]:
-                self._attn(b["attn1"], ln, None, N, n, st, True, t, t2)
+            fold = _LN_FOLD and inner % 64 == 0
+            if fold:
+                # LayerNorm folded into the contractions either side of it (anysd_gemm_params::row_stats / ln_stats): the
+                # producer of t / t2 / t3 has left per-row moments, the consumer takes the un-normalised rows
+                fb = self._ln_folded(b)
+                t2 = torch.empty_like(t)
+                self._attn(b["attn1"], t, None if b["self"] else ctx, N, n, st, b["self"], t, t2, ln=(t._ln, fb["a1"]), out_stats=True)
             else:
-                self._attn(b["attn1"], ln, ctx, N, n, st, False, t, t2)
-            ln2 = torch.empty_like(t)
-            ops.layernorm(t2, b["ln2_w"], b["ln2_b"], ln2)
+                ln = torch.empty_like(t)
+                ops.layernorm(t, b["ln1_w"], b["ln1_b"], ln)
+                t2 = torch.empty_like(t)
+                if b["self"]:
+                    self._attn(b["attn1"], ln, None, N, n, st, True, t, t2)
+                else:
+                    self._attn(b["attn1"], ln, ctx, N, n, st, False, t, t2)
+                ln2 = torch.empty_like(t)
+                ops.layernorm(t2, b["ln2_w"], b["ln2_b"], ln2)
             if ctx is None:   # "if no context is given, cross-attention defaults to self-attention"
                 raise NotImplementedError("attn2 without context (self-attention fallback) is not used on the AnySD path")
             q_pre = None
             if share:
                 ad = b["attn2"]
                 q_half = torch.empty(M, ad["heads"] * ad["hs"], dtype=torch.float16, device=dev)
-                ops.gemm(ln2, ad["q_w"], q_half)
+                if fold:
+                    ops.gemm(t2, fb["a2"]["w"], q_half, bias=fb["a2"]["b"], ln=(t2._ln, fb["a2"]["cs"], 1e-5))
+                else:
+                    ops.gemm(ln2, ad["q_w"], q_half)
                 q_pre, t2, h = self._dup_rows(q_half), self._dup_rows(t2), self._dup_rows(h)
                 N, M, share = 2 * N, 2 * M, False
                 t = None                                        # (half-batch tensor, not used again)
             t3 = torch.empty_like(t2)
-            self._attn(b["attn2"], ln2, ctx, N, n, st, False, t2, t3, expert=True, q_pre=q_pre)
-            ln3 = torch.empty_like(t3)
-            ops.layernorm(t3, b["ln3_w"], b["ln3_b"], ln3)
-            ffh = torch.empty(M, b["ff2_w"].shape[1], dtype=torch.float16, device=dev)
-            ops.gemm(ln3, b["ff1_w"], ffh, bias=b["ff1_b"], act=2)
+            if fold:
+                self._attn(b["attn2"], t2, ctx, N, n, st, False, t2, t3, expert=True, q_pre=q_pre,
+                           ln=None if q_pre is not None else (t2._ln, fb["a2"]), out_stats=True)
+                ffh = torch.empty(M, b["ff2_w"].shape[1], dtype=torch.float16, device=dev)
+                ops.gemm(t3, fb["ff1"]["w"], ffh, bias=fb["ff1"]["b"], act=2, ln=(t3._ln, fb["ff1"]["cs"], 1e-5))
+            else:
+                self._attn(b["attn2"], ln2, ctx, N, n, st, False, t2, t3, expert=True, q_pre=q_pre)
+                ln3 = torch.empty_like(t3)
+                ops.layernorm(t3, b["ln3_w"], b["ln3_b"], ln3)
+                ffh = torch.empty(M, b["ff2_w"].shape[1], dtype=torch.float16, device=dev)
+                ops.gemm(ln3, b["ff1_w"], ffh, bias=b["ff1_b"], act=2)
             t4 = torch.empty_like(t3)
-            ops.gemm(ffh, b["ff2_w"], t4, bias=b["ff2_b"], residual=t3)
+            nxt = fold and i + 1 < len(d["blocks"])              # depth > 1: the next block's norm1 reads this output
+            if nxt:
+                t4._ln = ops.row_stats_buffer(M, inner, dev)
+            ops.gemm(ffh, b["ff2_w"], t4, bias=b["ff2_b"], residual=t3, row_stats=t4._ln if nxt else None)
             t = t4
         out = torch.empty(N, H, W, C, dtype=torch.float16, device=dev)
         out._gn = ops.gemm(t, d["pout_w"], out.view(M, C), bias=d["pout_b"], residual=h.view(M, C), rows_per_batch=n, stats_images=N)

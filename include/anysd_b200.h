@@ -138,6 +138,16 @@ typedef struct {
     void* splitk_counters;  /* optional: >= 64 KB of device memory, ZERO before the first use (every launch re-arms it); may be
                                shared by all stream-ordered launches of a device.  Without both, the plain schedule runs. */
     size_t splitk_counters_bytes;
+    /* LayerNorm folded into the contractions either side of it (nn.LayerNorm norm1/2/3 of BasicTransformerBlock,
+       attention.py:262-264, 271-274): the PRODUCER of x emits per-row moments from its epilogue, the CONSUMER takes the
+       un-normalised x as A with gamma folded into W and applies  out = act(rstd_m (acc - mean_m colsum_n) + bias_n) + residual
+       -- algebraically LayerNorm(x) W^T + b without the normalised tensor ever being written or re-read. */
+    float* row_stats;       /* optional OUTPUT: fp32 [N / 64, M, 2] = per 64-column slab, per row {sum, sum of squares} of the fp32
+                               results (after bias / residual).  Dense, fp16 output, act 0, N % 64 == 0.  Every cell written once. */
+    const float* ln_stats;  /* optional INPUT: the row_stats ([K / 64, M, 2]) of A's producer; K % 64 == 0.  Then W must hold
+                               W[n,k] gamma[k], bias[n] = b[n] + sum_k beta[k] W[n,k] (required) and */
+    const float* ln_colsum; /* fp32 [N]: sum_k of the fp16 values of the packed W row n (16-byte aligned) */
+    float ln_eps;
 } anysd_gemm_params;
 int anysd_gemm_f16(const anysd_gemm_params* p, anysd_stream_t stream);
 /* Slabs per image of the statistics layout for this contraction, or 0 when the shape cannot produce them (rows of one

@@ -50,6 +50,9 @@ def run(B, heads, n, nkv, d, check=True):
 
 if __name__ == "__main__":
     print("ANYSD_ATTN =", os.environ.get("ANYSD_ATTN"))
+    if "--l0" in sys.argv:                       # only the d = 40 / 4096-token level (experiments on the paired kernel)
+        run(16, 8, 4096, 4096, 40, check="--nocheck" not in sys.argv)
+        sys.exit(0)
     for c in ((1, 2, 128, 128, 64), (1, 2, 256, 256, 40), (2, 8, 300, 77, 40), (1, 8, 256, 256, 80), (1, 8, 256, 256, 160)):
         run(*c)
     if "--quick" not in sys.argv:

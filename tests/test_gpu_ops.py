@@ -344,12 +344,13 @@ def test_attention_padded_heads(ops, B, heads, nq, nkv, d):
 
 @pytest.mark.parametrize("B,heads,nq,nkv,d,amp", [(1, 8, 256, 256, 40, 1.0), (2, 8, 300, 300, 40, 1.0), (2, 8, 100, 77, 40, 1.0),
                                                   (1, 8, 1024, 1024, 40, 6.0), (1, 3, 130, 513, 24, 3.0),
-                                                  (1, 2, 128, 2048, 40, 12.0)])
+                                                  (1, 2, 128, 2048, 40, 12.0), (2, 4, 512, 2048, 40, 12.0), (1, 2, 256, 4096, 40, 1.0)])
 def test_attention_aux_cols(ops, B, heads, nq, nkv, d, amp):
     """anysd_attn_params::aux_cols -- q pre-scaled by scale*log2(e), K carrying 1.0 in padding columns d, d+1 and V
     in column d (what anyedit_b200.unet packs for d = 40): same softmax(q k^T scale) v as the plain contract.  `amp`
     widens the score range so the in-kernel reference moves many times (rewrites of q's padding columns); keys are
-    sorted by growing norm in the last case so the maximum keeps rising tile after tile."""
+    sorted by growing norm in the amp = 12 cases so the maximum keeps rising tile after tile.  n_q % 256 == 0 with >= 1024
+    keys runs the paired kernel (two query tiles per CTA, attention_tc5x2_kernel), the rest the one-tile kernel."""
     from anyedit_b200.unet import LOG2E, aux_cols_for, head_stride_for
     from oracle import unet_oracle
     assert aux_cols_for(d)
@@ -480,3 +481,60 @@ def test_split_k_contractions(ops, stats_everywhere):
     o = torch.empty(1024, 1280, dtype=torch.float16, device="cuda")
     ops.gemm(A.half().cuda(), Wt.half().cuda(), o, bias=bb.cuda(), residual=r.half().cuda())
     assert rel(o, A.half().float() @ Wt.half().float().t() + bb + r.half().float()) < 1e-3
+
+
+@pytest.mark.parametrize("M,C,N,act,res_mean", [(300, 320, 1152, 0, 0.0), (4096, 320, 2560, 2, 3.0), (1000, 640, 640, 0, -8.0),
+                                                (256, 1280, 3840, 0, 1.0)])
+def test_layernorm_folded_into_contractions(ops, M, C, N, act, res_mean):
+    """nn.LayerNorm between two contractions (attention.py:262-264, 271-274) without its own pass: the producer's epilogue
+    leaves per-row moments (row_stats), the consumer takes the un-normalised rows with gamma folded into W (ln_stats).
+    Reference: fp32 LayerNorm of the stored fp16 rows, then the fp32 contraction (+ GEGLU).  ``res_mean`` gives the rows a
+    mean of several standard deviations: the E[x^2] - mean^2 combine must survive it."""
+    a = randn(1, M, 192).half()
+    wp = randn(2, C, 192, scale=192 ** -0.5).half()
+    bp = randn(3, C)
+    res = (randn(4, M, C) + res_mean).half()
+    gamma, beta = 1.0 + 0.2 * randn(5, C), 0.1 * randn(6, C)
+    w = randn(7, N, C, scale=C ** -0.5)
+    bias = 0.1 * randn(8, N)
+    # producer: x = a wp^T + bp + res, with the row moments of x from the epilogue
+    x = torch.empty(M, C, dtype=torch.float16, device="cuda")
+    rs = ops.row_stats_buffer(M, C, "cuda")
+    rs.fill_(float("nan"))
+    ops.gemm(a.cuda(), wp.cuda(), x, bias=bp.cuda(), residual=res.cuda(), row_stats=rs)
+    x32 = a.float() @ wp.float().t() + bp + res.float()
+    assert rel(x, x32) < 6e-4
+    s = rs.sum(0).cpu().double()
+    assert torch.isfinite(s).all()
+    assert float((s[:, 0] - x32.double().sum(1)).abs().max()) < 2e-3 * C ** 0.5 * (1 + abs(res_mean))
+    assert rel(s[:, 1], (x32.double() ** 2).sum(1)) < 1e-5
+    # consumer: LayerNorm(x) w^T + bias (+ GEGLU), gamma / beta folded on the host exactly as UNetModel._ln_folded does
+    w16 = w.half()
+    wf = (w16.float() * gamma[None, :]).half()
+    cs = wf.float().sum(1)
+    bf = w16.float() @ beta + bias
+    n_out = N // 2 if act == 2 else N
+    out = torch.empty(M, n_out, dtype=torch.float16, device="cuda")
+    ops.gemm(x, wf.cuda(), out, bias=bf.cuda(), act=act, ln=(rs, cs.cuda(), 1e-5))
+    xs = x.float().cpu()
+    ref = F.layer_norm(xs, (C,), gamma, beta, 1e-5) @ w16.float().t() + bias
+    if act == 2:                               # interleaved (a_j, gate_j) rows
+        ref = ref[:, 0::2] * F.gelu(ref[:, 1::2])
+    e = rel(out, ref)
+    # the same computation through the separate LayerNorm kernel (fp16 normalised rows): the fold must not be worse
+    ln = torch.empty_like(x)
+    ops.layernorm(x, gamma.cuda(), beta.cuda(), ln)
+    out2 = torch.empty_like(out)
+    ops.gemm(ln, w16.cuda(), out2, bias=bias.cuda(), act=act)
+    e2 = rel(out2, ref)
+    print(f"folded LayerNorm M={M} C={C} N={N} act={act}: {e:.2e} (separate kernel {e2:.2e})")
+    assert e < 6e-4 and e < 1.3 * e2 + 1e-4
+
+
+def test_layernorm_fold_unsupported_is_loud(ops):
+    x = torch.zeros(64, 96, dtype=torch.float16, device="cuda")          # K % 64 != 0
+    w = torch.zeros(64, 96, dtype=torch.float16, device="cuda")
+    out = torch.empty(64, 64, dtype=torch.float16, device="cuda")
+    rs = torch.zeros(1, 64, 2, device="cuda")
+    with pytest.raises(Exception):
+        ops.gemm(x, w, out, bias=torch.zeros(64, device="cuda"), ln=(rs, torch.zeros(64, device="cuda"), 1e-5))

@@ -94,6 +94,26 @@ def test_unet_sd15_geometry_vs_oracle():
     assert e < FWD_TOL, e
 
 
+def test_unet_sd15_layernorm_fold_switch(monkeypatch):
+    """ANYSD_LN_FOLD=1 (LayerNorm folded into the contractions either side of it; off by default): the same
+    forward within the fp16 tolerance of the default path and of the oracle."""
+    from anyedit_b200 import unet as unet_mod
+    from oracle import unet_oracle
+    net, sd, cfg = _build("sd15", 3)
+    gen = torch.Generator().manual_seed(99)
+    x = torch.randn(2, 8, 16, 16, generator=gen)
+    ctx = torch.randn(2, 77, 768, generator=gen)
+    t = torch.tensor([981, 441])
+    base = net(x.cuda(), t.cuda(), context=ctx.cuda())
+    monkeypatch.setattr(unet_mod, "_LN_FOLD", True)
+    fold = net(x.cuda(), t.cuda(), context=ctx.cuda())
+    ref = unet_oracle.unet_forward(sd, x, t, ctx, None, num_heads=cfg["num_heads"])
+    e_fold, e_base = rel(fold, ref), rel(base, ref)
+    print(f"[sd15 16x16] LayerNorm fold: rel-L2 vs oracle {e_fold:.3e} (separate kernel {e_base:.3e}), fold vs default {rel(fold, base):.3e}")
+    assert not torch.equal(fold, base)                # the switch did take the other path
+    assert e_fold < FWD_TOL and e_fold < 1.3 * e_base
+
+
 def _denoiser(net, key="hybrid"):
     from anyedit_b200.diffusion import LatentDenoiser
     return LatentDenoiser(net, conditioning_key=key).cuda()
