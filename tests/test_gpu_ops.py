@@ -538,3 +538,21 @@ def test_layernorm_fold_unsupported_is_loud(ops):
     rs = torch.zeros(1, 64, 2, device="cuda")
     with pytest.raises(Exception):
         ops.gemm(x, w, out, bias=torch.zeros(64, device="cuda"), ln=(rs, torch.zeros(64, device="cuda"), 1e-5))
+
+
+def test_gelu_epilogue_accuracy(ops):
+    """The GELU of the contraction epilogues (act 2 GEGLU, act 3 nn.GELU) is the exact erf form evaluated as a fitted logistic
+    (gemm_tc5p.cu: p_gelu): |x Phi(x) - kernel| <= 1.2e-5 + fp16 rounding over the whole range, including the saturated tails."""
+    x = torch.cat([torch.linspace(-12, 12, 64 * 1024 - 6), torch.tensor([-1e4, -60.0, -0.0, 0.0, 60.0, 1e4])]).half()
+    A = x.view(-1, 64).cuda()                                  # values pass through an identity contraction
+    W = torch.eye(64, dtype=torch.float16, device="cuda")
+    out = torch.empty_like(A)
+    ops.gemm(A, W, out, act=3)
+    ref = F.gelu(x.double()).view(-1, 64)
+    got = out.double().cpu()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs()
+    bound = 1.2e-5 + ref.abs() * 2.0 ** -11 + 6e-8            # fit + fp16 rounding of the result (+ the subnormal step)
+    worst = float((err / bound).max())
+    print(f"gelu epilogue: max |err| {float(err.max()):.2e}, max err / bound {worst:.3f}")
+    assert worst <= 1.0
