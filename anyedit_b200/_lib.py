@@ -41,6 +41,7 @@ class AttnParams(C.Structure):
         ("scale", C.c_float), ("gate", C.c_void_p), ("gate_stride", C.c_int), ("accumulate", C.c_int),
         ("head_stride", C.c_int),
         ("aux_cols", C.c_int),
+        ("lse", C.c_void_p),
     ]
 
 
@@ -56,7 +57,8 @@ class AttnBwdParams(C.Structure):          # mirrors anysd_attn_bwd_params field
                 ("head_stride", C.c_int), ("qk_scale", C.c_float),
                 ("gate", C.c_void_p), ("gate_stride", C.c_int), ("d_gate", C.c_void_p),
                 ("accumulate_dq", C.c_int), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-                ("out", C.c_void_p), ("o_batch_stride", C.c_longlong), ("ld_o", C.c_int)]
+                ("out", C.c_void_p), ("o_batch_stride", C.c_longlong), ("ld_o", C.c_int),
+                ("lse", C.c_void_p), ("dout_padded", C.c_void_p)]
 
 
 class ExpertAttnParams(C.Structure):       # mirrors anysd_expert_attn_params field for field

@@ -557,6 +557,11 @@ static int launch_bwd(const BwdArgs& a, int B, cudaStream_t st, bool need_dkv) {
 
 using namespace anysd;
 
+namespace anysd {
+bool attention_bwd_tc5_supported(const anysd_attn_bwd_params* q);
+int launch_attention_bwd_tc5(const anysd_attn_bwd_params* q, cudaStream_t st);
+}
+
 extern "C" size_t anysd_attention_bwd_workspace_bytes(int B, int heads, int n_q) {
     if (B <= 0 || heads <= 0 || n_q <= 0) return 0;
     return (size_t)2 * B * heads * n_q * sizeof(float);
@@ -585,6 +590,10 @@ extern "C" int anysd_attention_bwd_f16(const anysd_attn_bwd_params* p, anysd_str
     ANYSD_REQUIRE(p->workspace_bytes >= anysd_attention_bwd_workspace_bytes(p->B, p->heads, p->n_q), ANYSD_EINVAL,
                   "attention_bwd: workspace too small");
     ANYSD_REQUIRE(p->heads <= 65535 && p->B <= 65535, ANYSD_EINVAL, "attention_bwd: grid too large");
+    ANYSD_REQUIRE(p->out == nullptr || (p->gate == nullptr && p->ld_o % 8 == 0 && ((uintptr_t)p->out % 16) == 0 && p->o_batch_stride % 8 == 0),
+                  ANYSD_EINVAL, "attention_bwd: `out` must be the un-gated output of this attention, 16-byte aligned, ld_o %% 8 == 0");
+    // tcgen05 kernels when the forward's log-sum-exp came along and the shape allows (attention_bwd_tc5.cu)
+    if (attention_bwd_tc5_supported(p)) return launch_attention_bwd_tc5(p, (cudaStream_t)stream);
     BwdArgs a;
     a.q = (const __half*)p->q; a.k = (const __half*)p->k; a.v = (const __half*)p->v; a.dout = (const __half*)p->d_out;
     a.dq = (__half*)p->dq; a.dk = (__half*)p->dk; a.dv = (__half*)p->dv;

@@ -1,0 +1,506 @@
+// Attention backward on tcgen05 (train.py:694-709: the training step back-propagates through CrossAttention.forward,
+// attention.py:163-194).  Second generation of attention_bwd.cu for the shape that carries the cost of the step: the long
+// self-attention of the highest-resolution level (d = 40 padded to 48, 4096 tokens), where the mma.sync kernels spend
+// 37 of the step's 102 ms.  Same mathematics (attention_bwd.cu's header), different machine mapping:
+//
+//   the forward stores the base-2 log-sum-exp of every score row (anysd_attn_params::lse), so the probabilities are one
+//   exp2 away from a recomputed score -- no log-sum-exp pass;
+//   `bwd_prep_kernel`      D_i = dO_i . O_i (needs the forward output) and dO re-laid into the padded head layout of q / k / v
+//                          (zero padding columns: they are K-extent of the dO V^T product);
+//   `bwd_dq_tc5_kernel`    CTA = 128 query rows: S = Q K^T and dP = dO V^T into two TMEM accumulators, one thread per query
+//                          row turns them into dS = c P (dP - D) (fp16, swizzled smem), dQ += dS K accumulates in TMEM across
+//                          the key loop (K consumed as an MN-major B operand straight from its row-major tile);
+//   `bwd_dkv_tc5_kernel`   CTA = 128 key rows: every product transposed (S^T = K Q^T, dP^T = V dO^T: key rows are the M
+//                          dimension), one thread per KEY row writes P^T and dS^T rows -- K-major A operands as they come --
+//                          dV += P^T dO and dK += dS^T Q accumulate in TMEM across the query loop (dO / Q as MN-major B).
+//   No cross-CTA reduction, no atomics: deterministic.
+// Operand forms (descriptors, swizzle, MN-major B) are exactly those of the forward kernel (attention_tc5.cu).
+// Supported: d_ext = ceil16(d) <= 64 with head_stride == d_ext, n_q and n_kv multiples of 128, stacked batches, no gate;
+// everything else stays on attention_bwd.cu.
+#include <math.h>
+#include <stdlib.h>
+
+#include "attention_tc5.cuh"
+
+namespace anysd {
+
+constexpr int BT_ATOM = 128 * 128;          // 16 KB: [128 rows x 64 halves], 128-byte swizzle
+constexpr int BT_THREADS = 192;             // warp 0 TMA, warp 1 MMA issuer, warps 2..5 one thread per row
+
+struct BtArgs {
+    __half* dq; __half* dk; __half* dv;
+    long long dqbs, dkbs, dvbs;
+    int lddq, lddk, lddv;
+    int n_q, n_kv, d, d_ext, hs, heads;
+    float c_nat, c_log2;
+    const float* lse;       // [B, heads, n_q] base-2 log-sum-exp of the forward
+    const float* D;         // [B, heads, n_q]
+    int accumulate_dq;
+};
+
+// ---- D = dO . O and the padded copy of dO ------------------------------------------------------------------------------
+// one thread per (row, head): d / 8 16-byte vectors of dO and O in, hs / 8 vectors out (zeros behind column d)
+__global__ void bwd_prep_kernel(const __half* __restrict__ dout, long long dobs, int lddo, const __half* __restrict__ o, long long obs,
+                                int ldo, __half* __restrict__ dpad, float* __restrict__ D, int B, int n_q, int heads, int d, int hs) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * n_q * heads;
+    if (t >= total) return;
+    const int h = (int)(t % heads);
+    const long long r = t / heads;
+    const int b = (int)(r / n_q), i = (int)(r % n_q);
+    const uint4* g = reinterpret_cast<const uint4*>(dout + (size_t)b * dobs + (size_t)i * lddo + (size_t)h * d);
+    const uint4* oo = reinterpret_cast<const uint4*>(o + (size_t)b * obs + (size_t)i * ldo + (size_t)h * d);
+    uint4* dst = reinterpret_cast<uint4*>(dpad + ((size_t)r * heads + h) * hs);
+    float acc = 0.f;
+    for (int v = 0; v < d / 8; ++v) {
+        const uint4 a = __ldg(g + v), c = __ldg(oo + v);
+        float fa[8], fc[8];
+        unpack8(a, fa);
+        unpack8(c, fc);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(fa[k], fc[k], acc);
+        dst[v] = a;
+    }
+    for (int v = d / 8; v < hs / 8; ++v) dst[v] = make_uint4(0u, 0u, 0u, 0u);
+    D[((size_t)b * heads + h) * n_q + i] = acc;
+}
+
+// ---- dQ ------------------------------------------------------------------------------------------------------------------
+//   TMEM (512 columns): S 0..127 | dP 128..255 | dQ 256..
+//   smem: Q | dO | 2 x (K, V) | dS (two atoms)
+//   barriers: 0 qdo_full | 1,2 kv_full | 3,4 kv_empty | 5 sdp_full | 6 s_free | 7 ds_full | 8 dq_done
+__global__ void __launch_bounds__(BT_THREADS, 1)
+bwd_dq_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                  const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const BtArgs p) {
+    extern __shared__ __align__(1024) unsigned char bt_smem_raw[];
+    const uint32_t base = smem_u32(bt_smem_raw);
+    if (base & 1023u) __trap();
+    unsigned char* smem = bt_smem_raw;
+    constexpr uint32_t q_off = 0, do_off = BT_ATOM, kv_off = 2 * BT_ATOM, ds_off = kv_off + 4 * BT_ATOM, bar_off = ds_off + 2 * BT_ATOM;
+    const uint32_t bars = base + bar_off;
+    auto BAR = [&](int i) { return bars + 8u * i; };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * 9);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
+    const int nt = p.n_kv / 128;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDO) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i <= 5; ++i) am_init(BAR(i), 1);
+        am_init(BAR(6), 4);
+        am_init(BAR(7), 4);
+        am_init(BAR(8), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    a_fence_before();
+    __syncthreads();
+    a_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int col0 = h * p.hs;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            am_expect_tx(BAR(0), 2 * BT_ATOM);
+            a_tma_2d(base + q_off, &tmQ, BAR(0), col0, b * p.n_q + q0);
+            a_tma_2d(base + do_off, &tmDO, BAR(0), col0, b * p.n_q + q0);
+            for (int j = 0; j < nt; ++j) {
+                const int s = j & 1;
+                am_wait_relaxed(BAR(3 + s), (((uint32_t)j >> 1) & 1) ^ 1);
+                am_expect_tx(BAR(1 + s), 2 * BT_ATOM);
+                const uint32_t kb = base + kv_off + s * 2 * BT_ATOM;
+                a_tma_2d(kb, &tmK, BAR(1 + s), col0, b * p.n_kv + j * 128);
+                a_tma_2d(kb + BT_ATOM, &tmV, BAR(1 + s), col0, b * p.n_kv + j * 128);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc_o = (1u << 4) | (1u << 16) /*B is MN-major*/ | ((uint32_t)(p.d_ext >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const int ksteps = p.d_ext / 16;
+            const uint64_t qd = a_desc_k(base + q_off), dod = a_desc_k(base + do_off), dsd = a_desc_k(base + ds_off);
+            auto issue_sdp = [&](int j) {
+                const uint32_t kb = base + kv_off + (j & 1) * 2 * BT_ATOM;
+                const uint64_t kd = a_desc_k(kb), vd = a_desc_k(kb + BT_ATOM);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < ksteps) a_umma(tmem, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);               // S = Q K^T
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < ksteps) a_umma(tmem + 128, dod + 2 * k, vd + 2 * k, idesc_s, k ? 1u : 0u);        // dP = dO V^T
+                a_commit(BAR(5));
+            };
+            am_wait(BAR(0), 0);
+            am_wait(BAR(1), 0);
+            a_fence_after();
+            issue_sdp(0);
+            for (int j = 0; j < nt; ++j) {
+                if (j + 1 < nt) {
+                    am_wait(BAR(1 + ((j + 1) & 1)), ((uint32_t)(j + 1) >> 1) & 1);
+                    am_wait_relaxed(BAR(6), j & 1);                   // S(j), dP(j) are in registers
+                    a_fence_after();
+                    issue_sdp(j + 1);
+                }
+                am_wait_relaxed(BAR(7), j & 1);                       // dS(j) written
+                a_fence_after();
+                const uint64_t kmn = a_desc_mn(base + kv_off + (j & 1) * 2 * BT_ATOM, BT_ATOM);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)                           // dQ += dS(j) K(j): 16 keys per step
+                    a_umma(tmem + 256, dsd + (k >> 2) * (BT_ATOM >> 4) + (k & 3) * 2, kmn + 128 * k, idesc_o, (j | k) ? 1u : 0u);
+                a_commit(BAR(8));                                     // dS free
+                a_commit(BAR(3 + (j & 1)));                           // K/V stage free
+            }
+        }
+    } else {
+        const int lg = warp & 3, row = lg * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
+        const size_t ri = ((size_t)b * p.heads + h) * p.n_q + q0 + row;
+        const float lse = p.lse[ri];
+        const float nDc = -p.D[ri] * p.c_nat;
+        unsigned char* dsrow = smem + ds_off + row * 128;
+        for (int j = 0; j < nt; ++j) {
+            am_wait(BAR(5), j & 1);
+            a_fence_after();
+            uint32_t pk[64];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t s[32], dp[32];
+                __syncwarp();
+                a_ld32(tmem + lane_addr + c * 32, s);
+                a_ld32(tmem + 128 + lane_addr + c * 32, dp);
+                a_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float p0 = a_ex2(fmaf(__uint_as_float(s[2 * i]), p.c_log2, -lse));
+                    const float p1 = a_ex2(fmaf(__uint_as_float(s[2 * i + 1]), p.c_log2, -lse));
+                    const float d0 = p0 * fmaf(__uint_as_float(dp[2 * i]), p.c_nat, nDc);
+                    const float d1 = p1 * fmaf(__uint_as_float(dp[2 * i + 1]), p.c_nat, nDc);
+                    __half2 hh = __floats2half2_rn(d0, d1);
+                    pk[c * 16 + i] = *reinterpret_cast<uint32_t*>(&hh);
+                }
+            }
+            a_fence_before();
+            __syncwarp();
+            if (lane == 0) am_arrive(BAR(6));
+            if (j > 0) {
+                am_wait(BAR(8), (j - 1) & 1);                         // dQ += dS(j-1) K retired: the dS tile is free
+                a_fence_after();
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                uint4 u = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                *reinterpret_cast<uint4*>(dsrow + (c >> 3) * BT_ATOM + (((c & 7) ^ (row & 7)) << 4)) = u;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            a_fence_before();
+            __syncwarp();
+            if (lane == 0) am_arrive(BAR(7));
+        }
+        am_wait(BAR(8), (nt - 1) & 1);
+        a_fence_after();
+        __half* orow = p.dq + (size_t)b * p.dqbs + (size_t)(q0 + row) * p.lddq + (size_t)h * p.hs;
+        for (int c = 0; c < p.d_ext; c += 16) {
+            uint32_t o[16];
+            __syncwarp();
+            a_ld16(tmem + 256 + lane_addr + c, o);
+            a_wait_ld();
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8) {
+                const int col = c + g8 * 8;
+                if (col >= p.hs) break;
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = (col + i < p.d) ? __uint_as_float(o[g8 * 8 + i]) : 0.f;     // K's aux columns are not q
+                uint4* dst = reinterpret_cast<uint4*>(orow + col);
+                if (p.accumulate_dq) {
+                    float prev[8];
+                    unpack8(*dst, prev);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] += prev[i];
+                }
+                *dst = pack8(f);
+            }
+        }
+    }
+    a_fence_before();
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// ---- dK, dV ------------------------------------------------------------------------------------------------------------
+//   TMEM (512 columns): S^T 0..127 | dP^T 128..255 | dV 256.. | dK 320..
+//   smem: K | V | 2 x (Q, dO) | P^T (two atoms) | dS^T (two atoms) | 2 x (lse[128], D c[128])
+//   barriers: 0 kv_full | 1,2 qdo_full | 3,4 qdo_empty | 5 sdp_full | 6 s_free | 7 ds_full | 8 acc_done
+__global__ void __launch_bounds__(BT_THREADS, 1)
+bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const BtArgs p) {
+    extern __shared__ __align__(1024) unsigned char bt_smem_raw[];
+    const uint32_t base = smem_u32(bt_smem_raw);
+    if (base & 1023u) __trap();
+    unsigned char* smem = bt_smem_raw;
+    constexpr uint32_t k_off = 0, v_off = BT_ATOM, qdo_off = 2 * BT_ATOM, pt_off = qdo_off + 4 * BT_ATOM, dst_off = pt_off + 2 * BT_ATOM,
+                       vec_off = dst_off + 2 * BT_ATOM, bar_off = vec_off + 2 * 1024;
+    const uint32_t bars = base + bar_off;
+    auto BAR = [&](int i) { return bars + 8u * i; };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * 9);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * 128;
+    const int nt = p.n_q / 128;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDO) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i <= 5; ++i) am_init(BAR(i), 1);
+        am_init(BAR(6), 4);
+        am_init(BAR(7), 4);
+        am_init(BAR(8), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    a_fence_before();
+    __syncthreads();
+    a_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int col0 = h * p.hs;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            am_expect_tx(BAR(0), 2 * BT_ATOM);
+            a_tma_2d(base + k_off, &tmK, BAR(0), col0, b * p.n_kv + k0);
+            a_tma_2d(base + v_off, &tmV, BAR(0), col0, b * p.n_kv + k0);
+            const float* lse_g = p.lse + ((size_t)b * p.heads + h) * p.n_q;
+            const float* D_g = p.D + ((size_t)b * p.heads + h) * p.n_q;
+            for (int i = 0; i < nt; ++i) {
+                const int s = i & 1;
+                am_wait_relaxed(BAR(3 + s), (((uint32_t)i >> 1) & 1) ^ 1);
+                am_expect_tx(BAR(1 + s), 2 * BT_ATOM + 1024);
+                const uint32_t qb = base + qdo_off + s * 2 * BT_ATOM;
+                a_tma_2d(qb, &tmQ, BAR(1 + s), col0, b * p.n_q + i * 128);
+                a_tma_2d(qb + BT_ATOM, &tmDO, BAR(1 + s), col0, b * p.n_q + i * 128);
+                // the tile's 128 log-sum-exps and 128 D: two 512-byte bulk copies on the same barrier
+                const uint32_t vb = base + vec_off + s * 1024;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 512, [%2];"
+                             ::"r"(vb), "l"(lse_g + i * 128), "r"(BAR(1 + s)) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 512, [%2];"
+                             ::"r"(vb + 512), "l"(D_g + i * 128), "r"(BAR(1 + s)) : "memory");
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc_o = (1u << 4) | (1u << 16) /*B is MN-major*/ | ((uint32_t)(p.d_ext >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const int ksteps = p.d_ext / 16;
+            const uint64_t kd = a_desc_k(base + k_off), vd = a_desc_k(base + v_off);
+            const uint64_t ptd = a_desc_k(base + pt_off), dstd = a_desc_k(base + dst_off);
+            auto issue_sdp = [&](int i) {
+                const uint32_t qb = base + qdo_off + (i & 1) * 2 * BT_ATOM;
+                const uint64_t qd = a_desc_k(qb), dod = a_desc_k(qb + BT_ATOM);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < ksteps) a_umma(tmem, kd + 2 * k, qd + 2 * k, idesc_s, k ? 1u : 0u);               // S^T = K Q^T
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k < ksteps) a_umma(tmem + 128, vd + 2 * k, dod + 2 * k, idesc_s, k ? 1u : 0u);        // dP^T = V dO^T
+                a_commit(BAR(5));
+            };
+            am_wait(BAR(0), 0);
+            am_wait(BAR(1), 0);
+            a_fence_after();
+            issue_sdp(0);
+            for (int i = 0; i < nt; ++i) {
+                if (i + 1 < nt) {
+                    am_wait(BAR(1 + ((i + 1) & 1)), ((uint32_t)(i + 1) >> 1) & 1);
+                    am_wait_relaxed(BAR(6), i & 1);                   // S^T(i), dP^T(i) are in registers
+                    a_fence_after();
+                    issue_sdp(i + 1);
+                }
+                am_wait_relaxed(BAR(7), i & 1);                       // P^T(i), dS^T(i) written
+                a_fence_after();
+                const uint32_t qb = base + qdo_off + (i & 1) * 2 * BT_ATOM;
+                const uint64_t qmn = a_desc_mn(qb, BT_ATOM), domn = a_desc_mn(qb + BT_ATOM, BT_ATOM);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)                           // dV += P^T(i) dO(i): 16 queries per step
+                    a_umma(tmem + 256, ptd + (k >> 2) * (BT_ATOM >> 4) + (k & 3) * 2, domn + 128 * k, idesc_o, (i | k) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)                           // dK += dS^T(i) Q(i)
+                    a_umma(tmem + 320, dstd + (k >> 2) * (BT_ATOM >> 4) + (k & 3) * 2, qmn + 128 * k, idesc_o, (i | k) ? 1u : 0u);
+                a_commit(BAR(8));                                     // P^T / dS^T free
+                a_commit(BAR(3 + (i & 1)));                           // Q / dO stage free
+            }
+        }
+    } else {
+        const int lg = warp & 3, row = lg * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
+        unsigned char* ptrow = smem + pt_off + row * 128;
+        unsigned char* dsrow = smem + dst_off + row * 128;
+        for (int i = 0; i < nt; ++i) {
+            am_wait(BAR(1 + (i & 1)), ((uint32_t)i >> 1) & 1);        // this stage's lse / D vectors (and Q, dO) have landed
+            am_wait(BAR(5), i & 1);
+            a_fence_after();
+            const float4* lv = reinterpret_cast<const float4*>(smem + vec_off + (i & 1) * 1024);
+            const float4* dv4 = lv + 32;
+            uint32_t pp[64], pd[64];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t s[32], dp[32];
+                __syncwarp();
+                a_ld32(tmem + lane_addr + c * 32, s);
+                a_ld32(tmem + 128 + lane_addr + c * 32, dp);
+                a_wait_ld();
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const float4 l4 = lv[c * 8 + v], d4 = dv4[c * 8 + v];
+                    const float p0 = a_ex2(fmaf(__uint_as_float(s[4 * v]), p.c_log2, -l4.x));
+                    const float p1 = a_ex2(fmaf(__uint_as_float(s[4 * v + 1]), p.c_log2, -l4.y));
+                    const float p2 = a_ex2(fmaf(__uint_as_float(s[4 * v + 2]), p.c_log2, -l4.z));
+                    const float p3 = a_ex2(fmaf(__uint_as_float(s[4 * v + 3]), p.c_log2, -l4.w));
+                    const float e0 = p0 * ((__uint_as_float(dp[4 * v]) - d4.x) * p.c_nat);
+                    const float e1 = p1 * ((__uint_as_float(dp[4 * v + 1]) - d4.y) * p.c_nat);
+                    const float e2 = p2 * ((__uint_as_float(dp[4 * v + 2]) - d4.z) * p.c_nat);
+                    const float e3 = p3 * ((__uint_as_float(dp[4 * v + 3]) - d4.w) * p.c_nat);
+                    __half2 a0 = __floats2half2_rn(p0, p1), a1 = __floats2half2_rn(p2, p3);
+                    __half2 b0 = __floats2half2_rn(e0, e1), b1 = __floats2half2_rn(e2, e3);
+                    pp[c * 16 + 2 * v] = *reinterpret_cast<uint32_t*>(&a0);
+                    pp[c * 16 + 2 * v + 1] = *reinterpret_cast<uint32_t*>(&a1);
+                    pd[c * 16 + 2 * v] = *reinterpret_cast<uint32_t*>(&b0);
+                    pd[c * 16 + 2 * v + 1] = *reinterpret_cast<uint32_t*>(&b1);
+                }
+            }
+            a_fence_before();
+            __syncwarp();
+            if (lane == 0) am_arrive(BAR(6));
+            if (i > 0) {
+                am_wait(BAR(8), (i - 1) & 1);                         // the products of tile i-1 retired: P^T / dS^T are free
+                a_fence_after();
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const uint32_t off = (c >> 3) * BT_ATOM + (((c & 7) ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(ptrow + off) = make_uint4(pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
+                *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(pd[4 * c], pd[4 * c + 1], pd[4 * c + 2], pd[4 * c + 3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            a_fence_before();
+            __syncwarp();
+            if (lane == 0) am_arrive(BAR(7));
+        }
+        am_wait(BAR(8), (nt - 1) & 1);
+        a_fence_after();
+        __half* vrow = p.dv + (size_t)b * p.dvbs + (size_t)(k0 + row) * p.lddv + (size_t)h * p.hs;
+        __half* krow = p.dk + (size_t)b * p.dkbs + (size_t)(k0 + row) * p.lddk + (size_t)h * p.hs;
+        for (int c = 0; c < p.d_ext; c += 16) {
+            uint32_t ov[16], ok[16];
+            __syncwarp();
+            a_ld16(tmem + 256 + lane_addr + c, ov);
+            a_ld16(tmem + 320 + lane_addr + c, ok);
+            a_wait_ld();
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8) {
+                const int col = c + g8 * 8;
+                if (col >= p.hs) break;
+                float fv[8], fk[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    fv[t] = (col + t < p.d) ? __uint_as_float(ov[g8 * 8 + t]) : 0.f;
+                    fk[t] = (col + t < p.d) ? __uint_as_float(ok[g8 * 8 + t]) : 0.f;
+                }
+                *reinterpret_cast<uint4*>(vrow + col) = pack8(fv);
+                *reinterpret_cast<uint4*>(krow + col) = pack8(fk);
+            }
+        }
+    }
+    a_fence_before();
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------------
+bool attention_bwd_tc5_supported(const anysd_attn_bwd_params* q) {
+    static const char* off = getenv("ANYSD_ATTN_BWD");
+    if (off && off[0] == 'm') return false;                     // ANYSD_ATTN_BWD=mma: the mma.sync kernels (A/B switch)
+    const int hs = q->head_stride > 0 ? q->head_stride : q->d;
+    const int d_ext = (q->d + 15) / 16 * 16;
+    if (q->lse == nullptr || q->out == nullptr || q->dout_padded == nullptr || q->gate != nullptr || q->d_gate != nullptr) return false;
+    if (d_ext > 64 || hs != d_ext || q->d % 8 != 0) return false;
+    if (q->n_q % 128 != 0 || q->n_kv % 128 != 0) return false;
+    if (q->ld_q % 8 || q->ld_k % 8 || q->ld_v % 8 || q->ld_dq % 8 || (q->dk && (q->ld_dk % 8 || q->ld_dv % 8))) return false;
+    if (((uintptr_t)q->q % 16) || ((uintptr_t)q->k % 16) || ((uintptr_t)q->v % 16) || ((uintptr_t)q->dq % 16) ||
+        ((uintptr_t)q->dout_padded % 16) || (q->dk && (((uintptr_t)q->dk % 16) || ((uintptr_t)q->dv % 16))))
+        return false;
+    if (q->q_batch_stride != (long long)q->n_q * q->ld_q || q->k_batch_stride != (long long)q->n_kv * q->ld_k ||
+        q->v_batch_stride != (long long)q->n_kv * q->ld_v)
+        return false;
+    if ((q->dq_batch_stride % 8) || (q->dk && ((q->dk_batch_stride % 8) || (q->dv_batch_stride % 8)))) return false;
+    return a_get_encode() != nullptr;
+}
+
+int launch_attention_bwd_tc5(const anysd_attn_bwd_params* q, cudaStream_t st) {
+    const int hs = q->head_stride > 0 ? q->head_stride : q->d;
+    BtArgs a;
+    a.dq = (__half*)q->dq; a.dk = (__half*)q->dk; a.dv = (__half*)q->dv;
+    a.dqbs = q->dq_batch_stride; a.dkbs = q->dk_batch_stride; a.dvbs = q->dv_batch_stride;
+    a.lddq = q->ld_dq; a.lddk = q->ld_dk; a.lddv = q->ld_dv;
+    a.n_q = q->n_q; a.n_kv = q->n_kv; a.d = q->d; a.d_ext = (q->d + 15) / 16 * 16; a.hs = hs; a.heads = q->heads;
+    a.c_nat = q->qk_scale; a.c_log2 = q->qk_scale * 1.4426950408889634f;
+    a.lse = q->lse;
+    float* D = (float*)q->workspace;                            // [B, heads, n_q] (the workspace holds twice that)
+    a.D = D;
+    a.accumulate_dq = q->accumulate_dq;
+    __half* dpad = (__half*)q->dout_padded;
+    const long long total = (long long)q->B * q->n_q * q->heads;
+    bwd_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __half*)q->d_out, q->do_batch_stride, q->ld_do, (const __half*)q->out,
+                                                                     q->o_batch_stride, q->ld_o, dpad, D, q->B, q->n_q, q->heads, q->d, hs);
+    int rc = check_launch("attention_bwd (prep)");
+    if (rc) return rc;
+    const uint64_t width = (uint64_t)q->heads * hs;
+    CUtensorMap tmQ, tmDO, tmK, tmV;
+    bool ok = a_map(&tmQ, q->q, width, (uint64_t)q->B * q->n_q, q->ld_q, 128) &&
+              a_map(&tmDO, dpad, width, (uint64_t)q->B * q->n_q, (uint64_t)q->heads * hs, 128) &&
+              a_map(&tmK, q->k, width, (uint64_t)q->B * q->n_kv, q->ld_k, 128) &&
+              a_map(&tmV, q->v, width, (uint64_t)q->B * q->n_kv, q->ld_v, 128);
+    if (!ok) {
+        set_error("attention_bwd (tcgen05): cuTensorMapEncodeTiled failed (B=%d n_q=%d n_kv=%d d=%d)", q->B, q->n_q, q->n_kv, q->d);
+        return ANYSD_ECUDA;
+    }
+    const int smem_dq = 8 * BT_ATOM + 256, smem_dkv = 10 * BT_ATOM + 2048 + 256;
+    static int attr[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!attr[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(bwd_dq_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bwd_dkv_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv);
+        if (e != cudaSuccess) {
+            set_error("attention_bwd (tcgen05): smem opt-in failed: %s", cudaGetErrorString(e));
+            return ANYSD_ECUDA;
+        }
+        attr[dev] = 1;
+    }
+    bwd_dq_tc5_kernel<<<dim3(q->n_q / 128, q->heads, q->B), BT_THREADS, smem_dq, st>>>(tmQ, tmDO, tmK, tmV, a);
+    rc = check_launch("attention_bwd dq (tcgen05)");
+    if (rc) return rc;
+    if (q->dk != nullptr) {
+        bwd_dkv_tc5_kernel<<<dim3(q->n_kv / 128, q->heads, q->B), BT_THREADS, smem_dkv, st>>>(tmQ, tmDO, tmK, tmV, a);
+        rc = check_launch("attention_bwd dk/dv (tcgen05)");
+    }
+    return rc;
+}
+
+}  // namespace anysd

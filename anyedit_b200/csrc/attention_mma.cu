@@ -257,6 +257,7 @@ extern "C" int anysd_attention_f16(const anysd_attn_params* p, anysd_stream_t st
     static const char* force = getenv("ANYSD_ATTN");
     const bool want_tc5 = !force || !strcmp(force, "tc5");
     if (want_tc5 && attention_tc5_supported(p)) return launch_attention_tc5(p, (cudaStream_t)stream);
+    ANYSD_REQUIRE(p->lse == nullptr, ANYSD_EUNSUPPORTED, "attention: the log-sum-exp output needs the tcgen05 kernel");
     ANYSD_REQUIRE(!p->aux_cols, ANYSD_EUNSUPPORTED,
                   "attention: aux_cols needs the tcgen05 kernel (d %% 16 == 8, head_stride >= d + 8, stacked batches)");
     return launch_attention_mma(p, (cudaStream_t)stream);

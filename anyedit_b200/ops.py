@@ -330,8 +330,9 @@ def conv3x3(x, W, out, bias=None, rowadd=None, residual=None, stride=1, upsample
 
 
 def attention(q, k, v, out, B, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o, q_bs=None, k_bs=None, v_bs=None,
-              o_bs=None, scale=None, gate=None, gate_stride=1, accumulate=False, head_stride=0, aux_cols=False):
-    """softmax(q k^T * scale) v per (batch, head); q/k/v may be column slices of fused projections."""
+              o_bs=None, scale=None, gate=None, gate_stride=1, accumulate=False, head_stride=0, aux_cols=False, lse=None):
+    """softmax(q k^T * scale) v per (batch, head); q/k/v may be column slices of fused projections.
+    ``lse`` (fp32 [B, heads, n_q]): also store the base-2 log-sum-exp of every score row (for the backward)."""
     _cuda(q, k, v, out)
     p = AttnParams()
     p.q, p.k, p.v, p.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
@@ -347,6 +348,9 @@ def attention(q, k, v, out, B, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_o, q_bs
     p.accumulate = int(bool(accumulate))
     p.head_stride = head_stride
     p.aux_cols = int(bool(aux_cols))
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * heads * n_q
+        p.lse = lse.data_ptr()
     with _Traced("attention", 4.0 * B * heads * n_q * n_kv * d, f"B={B} h={heads} nq={n_q} nkv={n_kv} d={d}"):
         _lib.check(_lib.load().anysd_attention_f16(C.byref(p), _stream()), "attention")
     _count()
@@ -500,7 +504,7 @@ def layernorm_bwd(x, gamma, dy, dx, eps=1e-5):
 
 
 def attention_bwd(q, k, v, d_out, dq, dk, dv, B, heads, n_q, n_kv, d, ld_q, ld_k, ld_v, ld_do, ld_dq, ld_dk=0, ld_dv=0,
-                  qk_scale=None, gate=None, gate_stride=1, d_gate=None, accumulate_dq=False, head_stride=0, out=None, ld_o=0):
+                  qk_scale=None, gate=None, gate_stride=1, d_gate=None, accumulate_dq=False, head_stride=0, out=None, ld_o=0, lse=None):
     """Backward of `attention` (recomputing the probabilities).  dk/dv None: frozen K/V.  out: this attention's own
     un-gated forward output (saves one sweep over K/V)."""
     _cuda(q, k, v, d_out, dq)
@@ -523,6 +527,12 @@ def attention_bwd(q, k, v, d_out, dq, dk, dv, B, heads, n_q, n_kv, d, ld_q, ld_k
     nbytes = _lib.load().anysd_attention_bwd_workspace_bytes(B, heads, n_q)
     ws = torch.empty(nbytes // 4, dtype=torch.float32, device=q.device)
     p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
+    dpad = None
+    if lse is not None and out is not None:        # the tcgen05 kernels (shape permitting; the library decides)
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * heads * n_q
+        hs = head_stride if head_stride > 0 else d
+        dpad = torch.empty(B * n_q * heads * hs, dtype=torch.float16, device=q.device)
+        p.lse, p.dout_padded = lse.data_ptr(), dpad.data_ptr()
     with _Traced("attention_bwd", 0.0, f"B={B} h={heads} nq={n_q} nkv={n_kv} d={d} dkv={int(dk is not None)}"):
         _lib.check(_lib.load().anysd_attention_bwd_f16(C.byref(p), _stream()), "attention_bwd")
     _count(2 if dk is not None else 1)

@@ -184,6 +184,9 @@ typedef struct {
                                The kernel writes its running reference into q's padding inside shared memory, so the
                                scores leave the tensor core already shifted (exp2 only) and the softmax denominator is
                                column d of P.V.  Same result as aux_cols = 0 up to fp32 rounding. */
+    float* lse;             /* optional OUTPUT (tcgen05 kernels only, gate == NULL): fp32 [B, heads, n_q], the base-2 log-sum-exp of
+                               every score row, lse2_i = log2 sum_j 2^(scale log2(e) q_i.k_j) -- what anysd_attention_bwd_f16 needs
+                               to recompute the probabilities without its own pass over K (train.py:694-709 backward). */
 } anysd_attn_params;
 int anysd_attention_f16(const anysd_attn_params* p, anysd_stream_t stream);
 
@@ -304,6 +307,10 @@ typedef struct {
                                gate, nothing accumulated into it): D = dO . O then costs one pass instead of a second
                                sweep over K/V.  NULL: recomputed. */
     long long o_batch_stride; int ld_o;
+    const float* lse;       /* optional: the forward's anysd_attn_params::lse ([B, heads, n_q], base 2).  With `lse`, `out` and */
+    void* dout_padded;      /* `dout_padded` (scratch, fp16 [B, n_q, heads * head_stride]) the backward runs on the tcgen05 kernels
+                               (attention_bwd_tc5.cu) when the shape allows: ceil16(d) <= 64 == head_stride, n_q and n_kv multiples
+                               of 128, stacked batches, no gate; otherwise both are ignored. */
 } anysd_attn_bwd_params;
 size_t anysd_attention_bwd_workspace_bytes(int B, int heads, int n_q);
 int anysd_attention_bwd_f16(const anysd_attn_bwd_params* p, anysd_stream_t stream);

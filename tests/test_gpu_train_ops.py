@@ -97,6 +97,71 @@ def test_attention_backward(ops, B, heads, nq, nkv, d, self_attn, gated, ln2):
     assert e < 4e-3, ("dq accumulate", e)
 
 
+@pytest.mark.parametrize("B,heads,nq,nkv,d,aux", [(2, 3, 256, 256, 40, True), (1, 2, 128, 512, 40, True), (1, 2, 384, 128, 24, False),
+                                                  (1, 8, 1024, 1024, 40, True)])
+def test_attention_backward_tcgen05(ops, monkeypatch, B, heads, nq, nkv, d, aux):
+    """The tcgen05 backward (attention_bwd_tc5.cu): the forward hands over its base-2 log-sum-exp (anysd_attn_params::lse), the
+    backward recomputes P = 2^(s - lse) and forms dS, dQ, dK, dV on the tensor cores.  Checked against autograd, against the
+    mma.sync kernels on the same inputs, and the log-sum-exp against torch.logsumexp."""
+    from anyedit_b200.unet import head_stride_for
+    hs = head_stride_for(d)
+    assert hs == (d + 15) // 16 * 16
+    C, Cp = heads * d, heads * hs
+    scale = d ** -0.5
+    q, k, v = h16(randn(11, B, nq, heads, d)), h16(randn(12, B, nkv, heads, d)), h16(randn(13, B, nkv, heads, d))
+    if aux:
+        q = h16(q * scale * math.log2(math.e))
+    c = math.log(2.0) if aux else scale
+    dO = h16(randn(14, B, nq, heads, d) * 0.1)
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    s = torch.einsum("bihd,bjhd->bhij", qr, kr) * c
+    o = torch.einsum("bhij,bjhd->bihd", s.softmax(-1), vr)
+    o.backward(dO)
+
+    def pad(t, ones=0):
+        out = torch.zeros(B, t.shape[1], heads, hs, dtype=torch.float16)
+        out[..., :d] = t
+        out[..., d:d + ones] = 1.0
+        return out.reshape(B, t.shape[1], Cp).cuda().contiguous()
+
+    q16, k16, v16 = pad(q), pad(k, 2 if aux else 0), pad(v, 1 if aux else 0)
+    out = torch.empty(B, nq, C, dtype=torch.float16, device="cuda")
+    lse = torch.full((B, heads, nq), float("nan"), device="cuda")
+    ops.attention(q16, k16, v16, out, B, heads, nq, nkv, d, Cp, Cp, Cp, C, head_stride=hs, aux_cols=aux, scale=scale, lse=lse)
+    assert rel(out.float().cpu().view(B, nq, heads, d), o.detach()) < 2e-3
+    lse_ref = torch.logsumexp(s.detach(), -1) / math.log(2.0)                      # [B, h, nq], base 2
+    assert float((lse.cpu() - lse_ref).abs().max()) < 2e-3
+    dO16 = dO.reshape(B, nq, C).half().cuda().contiguous()
+    res = {}
+    for mode in ("tc5", "mma"):
+        if mode == "mma":
+            lse_arg = None
+        else:
+            lse_arg = lse
+        dq = torch.full((B, nq, Cp), float("nan"), dtype=torch.float16, device="cuda")
+        dk = torch.full((B, nkv, Cp), float("nan"), dtype=torch.float16, device="cuda")
+        dv = torch.full((B, nkv, Cp), float("nan"), dtype=torch.float16, device="cuda")
+        ops.attention_bwd(q16, k16, v16, dO16, dq, dk, dv, B, heads, nq, nkv, d, Cp, Cp, Cp, C, Cp, Cp, Cp, qk_scale=c, head_stride=hs,
+                          out=out, ld_o=C, lse=lse_arg)
+        torch.cuda.synchronize()
+        res[mode] = (dq, dk, dv)
+    unpad = lambda t, n: t.float().cpu().reshape(B, n, heads, hs)
+    for mode, (dq, dk, dv) in res.items():
+        for name, got, ref, n in (("dq", dq, qr.grad, nq), ("dk", dk, kr.grad, nkv), ("dv", dv, vr.grad, nkv)):
+            g4 = unpad(got, n)
+            assert torch.isfinite(g4).all(), (mode, name)
+            assert float(g4[..., d:].abs().max()) == 0.0, (mode, name)            # padding columns stay zero
+            e = rel(g4[..., :d], ref)
+            print(f"attention backward {mode} B={B} h={heads} nq={nq} nkv={nkv} d={d} {name}: {e:.2e}")
+            assert e < 4e-3, (mode, name, e)
+    assert not torch.equal(res["tc5"][0], res["mma"][0])                          # the two really are different kernels
+    # frozen K/V, accumulated onto an existing gradient
+    dq2 = res["tc5"][0].clone()
+    ops.attention_bwd(q16, k16, v16, dO16, dq2, None, None, B, heads, nq, nkv, d, Cp, Cp, Cp, C, Cp, qk_scale=c, head_stride=hs,
+                      out=out, ld_o=C, lse=lse, accumulate_dq=True)
+    assert rel(unpad(dq2, nq)[..., :d], 2 * qr.grad) < 4e-3
+
+
 @pytest.mark.parametrize("N,HW,C1,C2,silu", [(2, 60, 64, 0, True), (3, 35, 96, 32, True), (2, 16, 320, 0, False), (1, 100, 64, 128, False)])
 def test_groupnorm_backward(ops, N, HW, C1, C2, silu):
     C = C1 + C2
