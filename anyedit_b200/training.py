@@ -507,9 +507,12 @@ class AdapterTrainer:
         if ctx is None:
             qkv = torch.empty(N * n_q, 3 * Cp, dtype=torch.float16, device=dev)
             ops.gemm(xq, ad["qkv_w"], qkv, bias=ad["qkv_b"])
+            # the long small-head self-attention keeps its log-sum-exp: the backward then runs on the tcgen05 kernels
+            d_ext = (ad["d"] + 15) // 16 * 16
+            lse = torch.empty(N, ad["heads"], n_q, dtype=torch.float32, device=dev) if (d_ext <= 64 and hs == d_ext and n_q % 128 == 0) else None
             ops.attention(qkv, qkv[:, Cp:], qkv[:, 2 * Cp:], a, N, ad["heads"], n_q, n_q, ad["d"], 3 * Cp, 3 * Cp, 3 * Cp, C,
-                          head_stride=hs, aux_cols=ad["aux"])
-            c["qkv"], c["a"] = qkv, a
+                          head_stride=hs, aux_cols=ad["aux"], lse=lse)
+            c["qkv"], c["a"], c["lse"] = qkv, a, lse
         else:
             L = ctx.shape[1]
             q = torch.empty(N * n_q, Cp, dtype=torch.float16, device=dev)
@@ -546,7 +549,8 @@ class AdapterTrainer:
             qkv = c["qkv"]
             dqkv = torch.empty_like(qkv)
             ops.attention_bwd(qkv, qkv[:, Cp:], qkv[:, 2 * Cp:], d_a, dqkv, dqkv[:, Cp:], dqkv[:, 2 * Cp:], N, heads, n_q, n_q, d,
-                              3 * Cp, 3 * Cp, 3 * Cp, C, 3 * Cp, 3 * Cp, 3 * Cp, qk_scale=qk, head_stride=hs, out=c["a"], ld_o=C)
+                              3 * Cp, 3 * Cp, 3 * Cp, C, 3 * Cp, 3 * Cp, 3 * Cp, qk_scale=qk, head_stride=hs, out=c["a"], ld_o=C,
+                              lse=c.get("lse"))
             d_x = torch.empty(N * n_q, ad["qkv_w"].shape[1], dtype=torch.float16, device=dev)
             ops.gemm(dqkv, _memo(ad, "qkv", lambda: ad["qkv_w"].t().contiguous()), d_x)
             return d_x
