@@ -66,23 +66,28 @@ __global__ void bwd_prep_kernel(const __half* __restrict__ dout, long long dobs,
 }
 
 // ---- dQ ------------------------------------------------------------------------------------------------------------------
-//   TMEM (512 columns): S 0..127 | dP 128..255 | dQ 256..
-//   smem: Q | dO | 2 x (K, V) | dS (two atoms)
+//   BS = keys per step.  128: TMEM 512 columns (S 0.. | dP 128.. | dQ 256..), one CTA per SM.  64: 256 columns (S 0.. | dP 64.. |
+//   dQ 128..) and 80 KB of smem -> TWO CTAs per SM, so one CTA's exponentials run under the other's products (the products
+//   are issue-bound: ~100 clk of tensor pipe per tcgen05.mma of this size whatever its math).
+//   smem: Q | dO | 2 x (K, V)[BS rows] | dS [128 x BS]
 //   barriers: 0 qdo_full | 1,2 kv_full | 3,4 kv_empty | 5 sdp_full | 6 s_free | 7 ds_full | 8 dq_done
-__global__ void __launch_bounds__(BT_THREADS, 1)
+template <int BS>
+__global__ void __launch_bounds__(BT_THREADS, BS == 64 ? 2 : 1)
 bwd_dq_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const BtArgs p) {
     extern __shared__ __align__(1024) unsigned char bt_smem_raw[];
     const uint32_t base = smem_u32(bt_smem_raw);
     if (base & 1023u) __trap();
     unsigned char* smem = bt_smem_raw;
-    constexpr uint32_t q_off = 0, do_off = BT_ATOM, kv_off = 2 * BT_ATOM, ds_off = kv_off + 4 * BT_ATOM, bar_off = ds_off + 2 * BT_ATOM;
+    constexpr uint32_t KV_TILE = BS * 128;                      // bytes of one [BS rows x 64 halves] K or V tile
+    constexpr uint32_t q_off = 0, do_off = BT_ATOM, kv_off = 2 * BT_ATOM, ds_off = kv_off + 4 * KV_TILE, bar_off = ds_off + (BS / 64) * BT_ATOM;
+    constexpr uint32_t T_DP = BS, T_DQ = 2 * BS, T_COLS = BS == 64 ? 256 : 512;
     const uint32_t bars = base + bar_off;
     auto BAR = [&](int i) { return bars + 8u * i; };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * 9);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 128;
-    const int nt = p.n_kv / 128;
+    const int nt = p.n_kv / BS;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
@@ -99,7 +104,7 @@ bwd_dq_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+                     ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)T_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     a_fence_before();
@@ -116,27 +121,27 @@ bwd_dq_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             for (int j = 0; j < nt; ++j) {
                 const int s = j & 1;
                 am_wait_relaxed(BAR(3 + s), (((uint32_t)j >> 1) & 1) ^ 1);
-                am_expect_tx(BAR(1 + s), 2 * BT_ATOM);
-                const uint32_t kb = base + kv_off + s * 2 * BT_ATOM;
-                a_tma_2d(kb, &tmK, BAR(1 + s), col0, b * p.n_kv + j * 128);
-                a_tma_2d(kb + BT_ATOM, &tmV, BAR(1 + s), col0, b * p.n_kv + j * 128);
+                am_expect_tx(BAR(1 + s), 2 * KV_TILE);
+                const uint32_t kb = base + kv_off + s * 2 * KV_TILE;
+                a_tma_2d(kb, &tmK, BAR(1 + s), col0, b * p.n_kv + j * BS);
+                a_tma_2d(kb + KV_TILE, &tmV, BAR(1 + s), col0, b * p.n_kv + j * BS);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc_s = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc_s = (1u << 4) | ((uint32_t)(BS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t idesc_o = (1u << 4) | (1u << 16) /*B is MN-major*/ | ((uint32_t)(p.d_ext >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const int ksteps = p.d_ext / 16;
             const uint64_t qd = a_desc_k(base + q_off), dod = a_desc_k(base + do_off), dsd = a_desc_k(base + ds_off);
             auto issue_sdp = [&](int j) {
-                const uint32_t kb = base + kv_off + (j & 1) * 2 * BT_ATOM;
-                const uint64_t kd = a_desc_k(kb), vd = a_desc_k(kb + BT_ATOM);
+                const uint32_t kb = base + kv_off + (j & 1) * 2 * KV_TILE;
+                const uint64_t kd = a_desc_k(kb), vd = a_desc_k(kb + KV_TILE);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (k < ksteps) a_umma(tmem, qd + 2 * k, kd + 2 * k, idesc_s, k ? 1u : 0u);               // S = Q K^T
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (k < ksteps) a_umma(tmem + 128, dod + 2 * k, vd + 2 * k, idesc_s, k ? 1u : 0u);        // dP = dO V^T
+                    if (k < ksteps) a_umma(tmem + T_DP, dod + 2 * k, vd + 2 * k, idesc_s, k ? 1u : 0u);       // dP = dO V^T
                 a_commit(BAR(5));
             };
             am_wait(BAR(0), 0);
@@ -152,10 +157,10 @@ bwd_dq_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 }
                 am_wait_relaxed(BAR(7), j & 1);                       // dS(j) written
                 a_fence_after();
-                const uint64_t kmn = a_desc_mn(base + kv_off + (j & 1) * 2 * BT_ATOM, BT_ATOM);
+                const uint64_t kmn = a_desc_mn(base + kv_off + (j & 1) * 2 * KV_TILE, KV_TILE);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)                           // dQ += dS(j) K(j): 16 keys per step
-                    a_umma(tmem + 256, dsd + (k >> 2) * (BT_ATOM >> 4) + (k & 3) * 2, kmn + 128 * k, idesc_o, (j | k) ? 1u : 0u);
+                for (int k = 0; k < BS / 16; ++k)                     // dQ += dS(j) K(j): 16 keys per step
+                    a_umma(tmem + T_DQ, dsd + (k >> 2) * (BT_ATOM >> 4) + (k & 3) * 2, kmn + 128 * k, idesc_o, (j | k) ? 1u : 0u);
                 a_commit(BAR(8));                                     // dS free
                 a_commit(BAR(3 + (j & 1)));                           // K/V stage free
             }
@@ -170,13 +175,13 @@ bwd_dq_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int j = 0; j < nt; ++j) {
             am_wait(BAR(5), j & 1);
             a_fence_after();
-            uint32_t pk[64];
+            uint32_t pk[BS / 2];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < BS / 32; ++c) {
                 uint32_t s[32], dp[32];
                 __syncwarp();
                 a_ld32(tmem + lane_addr + c * 32, s);
-                a_ld32(tmem + 128 + lane_addr + c * 32, dp);
+                a_ld32(tmem + T_DP + lane_addr + c * 32, dp);
                 a_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -196,7 +201,7 @@ bwd_dq_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 a_fence_after();
             }
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
+            for (int c = 0; c < BS / 8; ++c) {
                 uint4 u = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                 *reinterpret_cast<uint4*>(dsrow + (c >> 3) * BT_ATOM + (((c & 7) ^ (row & 7)) << 4)) = u;
             }
@@ -211,7 +216,7 @@ bwd_dq_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int c = 0; c < p.d_ext; c += 16) {
             uint32_t o[16];
             __syncwarp();
-            a_ld16(tmem + 256 + lane_addr + c, o);
+            a_ld16(tmem + T_DQ + lane_addr + c, o);
             a_wait_ld();
 #pragma unroll
             for (int g8 = 0; g8 < 2; ++g8) {
@@ -233,28 +238,32 @@ bwd_dq_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
     a_fence_before();
     __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)T_COLS) : "memory");
 }
 
 // ---- dK, dV ------------------------------------------------------------------------------------------------------------
-//   TMEM (512 columns): S^T 0..127 | dP^T 128..255 | dV 256.. | dK 320..
-//   smem: K | V | 2 x (Q, dO) | P^T (two atoms) | dS^T (two atoms) | 2 x (lse[128], D c[128])
+//   BS = queries per step.  128: TMEM 512 columns (S^T 0.. | dP^T 128.. | dV 256.. | dK 320..), one CTA per SM.  64: 256 columns
+//   (S^T 0.. | dP^T 64.. | dV 128.. | dK 192..) and 98 KB of smem -> two CTAs per SM.
+//   smem: K | V | 2 x (Q, dO)[BS rows] | P^T [128 x BS] | dS^T [128 x BS] | 2 x (lse[BS], D[BS])
 //   barriers: 0 kv_full | 1,2 qdo_full | 3,4 qdo_empty | 5 sdp_full | 6 s_free | 7 ds_full | 8 acc_done
-__global__ void __launch_bounds__(BT_THREADS, 1)
+template <int BS>
+__global__ void __launch_bounds__(BT_THREADS, BS == 64 ? 2 : 1)
 bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const BtArgs p) {
     extern __shared__ __align__(1024) unsigned char bt_smem_raw[];
     const uint32_t base = smem_u32(bt_smem_raw);
     if (base & 1023u) __trap();
     unsigned char* smem = bt_smem_raw;
-    constexpr uint32_t k_off = 0, v_off = BT_ATOM, qdo_off = 2 * BT_ATOM, pt_off = qdo_off + 4 * BT_ATOM, dst_off = pt_off + 2 * BT_ATOM,
-                       vec_off = dst_off + 2 * BT_ATOM, bar_off = vec_off + 2 * 1024;
+    constexpr uint32_t Q_TILE = BS * 128, PT_BYTES = (BS / 64) * BT_ATOM;
+    constexpr uint32_t k_off = 0, v_off = BT_ATOM, qdo_off = 2 * BT_ATOM, pt_off = qdo_off + 4 * Q_TILE, dst_off = pt_off + PT_BYTES,
+                       vec_off = dst_off + PT_BYTES, bar_off = vec_off + 2 * 1024;
+    constexpr uint32_t T_DP = BS, T_DV = 2 * BS, T_DK = 2 * BS + 64, T_COLS = BS == 64 ? 256 : 512;
     const uint32_t bars = base + bar_off;
     auto BAR = [&](int i) { return bars + 8u * i; };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 8 * 9);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * 128;
-    const int nt = p.n_q / 128;
+    const int nt = p.n_q / BS;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
@@ -271,7 +280,7 @@ bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32((const void*)tmem_slot)), "r"(512u) : "memory");
+                     ::"r"(smem_u32((const void*)tmem_slot)), "r"((uint32_t)T_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     a_fence_before();
@@ -290,34 +299,34 @@ bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             for (int i = 0; i < nt; ++i) {
                 const int s = i & 1;
                 am_wait_relaxed(BAR(3 + s), (((uint32_t)i >> 1) & 1) ^ 1);
-                am_expect_tx(BAR(1 + s), 2 * BT_ATOM + 1024);
-                const uint32_t qb = base + qdo_off + s * 2 * BT_ATOM;
-                a_tma_2d(qb, &tmQ, BAR(1 + s), col0, b * p.n_q + i * 128);
-                a_tma_2d(qb + BT_ATOM, &tmDO, BAR(1 + s), col0, b * p.n_q + i * 128);
-                // the tile's 128 log-sum-exps and 128 D: two 512-byte bulk copies on the same barrier
+                am_expect_tx(BAR(1 + s), 2 * Q_TILE + 8 * BS);
+                const uint32_t qb = base + qdo_off + s * 2 * Q_TILE;
+                a_tma_2d(qb, &tmQ, BAR(1 + s), col0, b * p.n_q + i * BS);
+                a_tma_2d(qb + Q_TILE, &tmDO, BAR(1 + s), col0, b * p.n_q + i * BS);
+                // the tile's BS log-sum-exps and BS D: two bulk copies on the same barrier
                 const uint32_t vb = base + vec_off + s * 1024;
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 512, [%2];"
-                             ::"r"(vb), "l"(lse_g + i * 128), "r"(BAR(1 + s)) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 512, [%2];"
-                             ::"r"(vb + 512), "l"(D_g + i * 128), "r"(BAR(1 + s)) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %3, [%2];"
+                             ::"r"(vb), "l"(lse_g + i * BS), "r"(BAR(1 + s)), "n"(4 * BS) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %3, [%2];"
+                             ::"r"(vb + 512), "l"(D_g + i * BS), "r"(BAR(1 + s)), "n"(4 * BS) : "memory");
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc_s = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc_s = (1u << 4) | ((uint32_t)(BS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t idesc_o = (1u << 4) | (1u << 16) /*B is MN-major*/ | ((uint32_t)(p.d_ext >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const int ksteps = p.d_ext / 16;
             const uint64_t kd = a_desc_k(base + k_off), vd = a_desc_k(base + v_off);
             const uint64_t ptd = a_desc_k(base + pt_off), dstd = a_desc_k(base + dst_off);
             auto issue_sdp = [&](int i) {
-                const uint32_t qb = base + qdo_off + (i & 1) * 2 * BT_ATOM;
-                const uint64_t qd = a_desc_k(qb), dod = a_desc_k(qb + BT_ATOM);
+                const uint32_t qb = base + qdo_off + (i & 1) * 2 * Q_TILE;
+                const uint64_t qd = a_desc_k(qb), dod = a_desc_k(qb + Q_TILE);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (k < ksteps) a_umma(tmem, kd + 2 * k, qd + 2 * k, idesc_s, k ? 1u : 0u);               // S^T = K Q^T
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (k < ksteps) a_umma(tmem + 128, vd + 2 * k, dod + 2 * k, idesc_s, k ? 1u : 0u);        // dP^T = V dO^T
+                    if (k < ksteps) a_umma(tmem + T_DP, vd + 2 * k, dod + 2 * k, idesc_s, k ? 1u : 0u);       // dP^T = V dO^T
                 a_commit(BAR(5));
             };
             am_wait(BAR(0), 0);
@@ -333,14 +342,14 @@ bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 }
                 am_wait_relaxed(BAR(7), i & 1);                       // P^T(i), dS^T(i) written
                 a_fence_after();
-                const uint32_t qb = base + qdo_off + (i & 1) * 2 * BT_ATOM;
-                const uint64_t qmn = a_desc_mn(qb, BT_ATOM), domn = a_desc_mn(qb + BT_ATOM, BT_ATOM);
+                const uint32_t qb = base + qdo_off + (i & 1) * 2 * Q_TILE;
+                const uint64_t qmn = a_desc_mn(qb, Q_TILE), domn = a_desc_mn(qb + Q_TILE, Q_TILE);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)                           // dV += P^T(i) dO(i): 16 queries per step
-                    a_umma(tmem + 256, ptd + (k >> 2) * (BT_ATOM >> 4) + (k & 3) * 2, domn + 128 * k, idesc_o, (i | k) ? 1u : 0u);
+                for (int k = 0; k < BS / 16; ++k)                     // dV += P^T(i) dO(i): 16 queries per step
+                    a_umma(tmem + T_DV, ptd + (k >> 2) * (BT_ATOM >> 4) + (k & 3) * 2, domn + 128 * k, idesc_o, (i | k) ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)                           // dK += dS^T(i) Q(i)
-                    a_umma(tmem + 320, dstd + (k >> 2) * (BT_ATOM >> 4) + (k & 3) * 2, qmn + 128 * k, idesc_o, (i | k) ? 1u : 0u);
+                for (int k = 0; k < BS / 16; ++k)                     // dK += dS^T(i) Q(i)
+                    a_umma(tmem + T_DK, dstd + (k >> 2) * (BT_ATOM >> 4) + (k & 3) * 2, qmn + 128 * k, idesc_o, (i | k) ? 1u : 0u);
                 a_commit(BAR(8));                                     // P^T / dS^T free
                 a_commit(BAR(3 + (i & 1)));                           // Q / dO stage free
             }
@@ -356,13 +365,13 @@ bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             a_fence_after();
             const float4* lv = reinterpret_cast<const float4*>(smem + vec_off + (i & 1) * 1024);
             const float4* dv4 = lv + 32;
-            uint32_t pp[64], pd[64];
+            uint32_t pp[BS / 2], pd[BS / 2];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < BS / 32; ++c) {
                 uint32_t s[32], dp[32];
                 __syncwarp();
                 a_ld32(tmem + lane_addr + c * 32, s);
-                a_ld32(tmem + 128 + lane_addr + c * 32, dp);
+                a_ld32(tmem + T_DP + lane_addr + c * 32, dp);
                 a_wait_ld();
 #pragma unroll
                 for (int v = 0; v < 8; ++v) {
@@ -391,7 +400,7 @@ bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 a_fence_after();
             }
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
+            for (int c = 0; c < BS / 8; ++c) {
                 const uint32_t off = (c >> 3) * BT_ATOM + (((c & 7) ^ (row & 7)) << 4);
                 *reinterpret_cast<uint4*>(ptrow + off) = make_uint4(pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
                 *reinterpret_cast<uint4*>(dsrow + off) = make_uint4(pd[4 * c], pd[4 * c + 1], pd[4 * c + 2], pd[4 * c + 3]);
@@ -408,8 +417,8 @@ bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int c = 0; c < p.d_ext; c += 16) {
             uint32_t ov[16], ok[16];
             __syncwarp();
-            a_ld16(tmem + 256 + lane_addr + c, ov);
-            a_ld16(tmem + 320 + lane_addr + c, ok);
+            a_ld16(tmem + T_DV + lane_addr + c, ov);
+            a_ld16(tmem + T_DK + lane_addr + c, ok);
             a_wait_ld();
 #pragma unroll
             for (int g8 = 0; g8 < 2; ++g8) {
@@ -428,7 +437,7 @@ bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     a_fence_before();
     __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)T_COLS) : "memory");
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------------
@@ -470,34 +479,44 @@ int launch_attention_bwd_tc5(const anysd_attn_bwd_params* q, cudaStream_t st) {
     int rc = check_launch("attention_bwd (prep)");
     if (rc) return rc;
     const uint64_t width = (uint64_t)q->heads * hs;
-    CUtensorMap tmQ, tmDO, tmK, tmV;
-    bool ok = a_map(&tmQ, q->q, width, (uint64_t)q->B * q->n_q, q->ld_q, 128) &&
-              a_map(&tmDO, dpad, width, (uint64_t)q->B * q->n_q, (uint64_t)q->heads * hs, 128) &&
-              a_map(&tmK, q->k, width, (uint64_t)q->B * q->n_kv, q->ld_k, 128) &&
-              a_map(&tmV, q->v, width, (uint64_t)q->B * q->n_kv, q->ld_v, 128);
+    // streamed-tile rows: 64 (two CTAs per SM) unless ANYSD_ATTN_BWD_BS=128
+    static const char* bs_env = getenv("ANYSD_ATTN_BWD_BS");
+    const int bs = (bs_env && atoi(bs_env) == 128) ? 128 : 64;
+    CUtensorMap tmQ, tmDO, tmK, tmV, tmQs, tmDOs, tmKs, tmVs;          // whole 128-row tiles / streamed bs-row tiles
+    const uint64_t rq = (uint64_t)q->B * q->n_q, rk = (uint64_t)q->B * q->n_kv, ldp = (uint64_t)q->heads * hs;
+    bool ok = a_map(&tmQ, q->q, width, rq, q->ld_q, 128) && a_map(&tmDO, dpad, width, rq, ldp, 128) &&
+              a_map(&tmK, q->k, width, rk, q->ld_k, 128) && a_map(&tmV, q->v, width, rk, q->ld_v, 128) &&
+              a_map(&tmQs, q->q, width, rq, q->ld_q, bs) && a_map(&tmDOs, dpad, width, rq, ldp, bs) &&
+              a_map(&tmKs, q->k, width, rk, q->ld_k, bs) && a_map(&tmVs, q->v, width, rk, q->ld_v, bs);
     if (!ok) {
         set_error("attention_bwd (tcgen05): cuTensorMapEncodeTiled failed (B=%d n_q=%d n_kv=%d d=%d)", q->B, q->n_q, q->n_kv, q->d);
         return ANYSD_ECUDA;
     }
-    const int smem_dq = 8 * BT_ATOM + 256, smem_dkv = 10 * BT_ATOM + 2048 + 256;
+    const int smem_dq = bs == 64 ? 2 * BT_ATOM + 4 * 64 * 128 + BT_ATOM + 256 : 8 * BT_ATOM + 256;
+    const int smem_dkv = bs == 64 ? 2 * BT_ATOM + 4 * 64 * 128 + 2 * BT_ATOM + 2048 + 256 : 10 * BT_ATOM + 2048 + 256;
     static int attr[64];
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
     if (!attr[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(bwd_dq_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(bwd_dkv_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dkv);
+        cudaError_t e = cudaFuncSetAttribute(bwd_dq_tc5_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * BT_ATOM + 256);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bwd_dkv_tc5_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * BT_ATOM + 2048 + 256);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bwd_dq_tc5_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * BT_ATOM + 4 * 64 * 128 + BT_ATOM + 256);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bwd_dkv_tc5_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * BT_ATOM + 4 * 64 * 128 + 2 * BT_ATOM + 2048 + 256);
         if (e != cudaSuccess) {
             set_error("attention_bwd (tcgen05): smem opt-in failed: %s", cudaGetErrorString(e));
             return ANYSD_ECUDA;
         }
         attr[dev] = 1;
     }
-    bwd_dq_tc5_kernel<<<dim3(q->n_q / 128, q->heads, q->B), BT_THREADS, smem_dq, st>>>(tmQ, tmDO, tmK, tmV, a);
+    const dim3 gq(q->n_q / 128, q->heads, q->B), gk(q->n_kv / 128, q->heads, q->B);
+    if (bs == 64) bwd_dq_tc5_kernel<64><<<gq, BT_THREADS, smem_dq, st>>>(tmQ, tmDO, tmKs, tmVs, a);
+    else bwd_dq_tc5_kernel<128><<<gq, BT_THREADS, smem_dq, st>>>(tmQ, tmDO, tmKs, tmVs, a);
     rc = check_launch("attention_bwd dq (tcgen05)");
     if (rc) return rc;
     if (q->dk != nullptr) {
-        bwd_dkv_tc5_kernel<<<dim3(q->n_kv / 128, q->heads, q->B), BT_THREADS, smem_dkv, st>>>(tmQ, tmDO, tmK, tmV, a);
+        if (bs == 64) bwd_dkv_tc5_kernel<64><<<gk, BT_THREADS, smem_dkv, st>>>(tmQs, tmDOs, tmK, tmV, a);
+        else bwd_dkv_tc5_kernel<128><<<gk, BT_THREADS, smem_dkv, st>>>(tmQs, tmDOs, tmK, tmV, a);
         rc = check_launch("attention_bwd dk/dv (tcgen05)");
     }
     return rc;

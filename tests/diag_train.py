@@ -59,17 +59,23 @@ def main():
         tr.step(lat, noise, t, img, text, vis, code)
         e1.record()
         torch.cuda.synchronize()
-        agg = {}
+        agg, shapes = {}, {}
         for kind, fl, a, b, tag in ops.trace:
             d = agg.setdefault(kind, [0.0, 0])
             d[0] += a.elapsed_time(b)
             d[1] += 1
+            if kind in ("attention_bwd", "expert_attention_bwd", "attention", "groupnorm_bwd"):
+                sd = shapes.setdefault((kind, tag), [0.0, 0])
+                sd[0] += a.elapsed_time(b)
+                sd[1] += 1
         ops.trace = None
         tot = e0.elapsed_time(e1)
         print(f"traced step {tot:.1f} ms")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
             print(f"  {k:16s} {v[1]:5d} launches {v[0]:8.2f} ms")
         print(f"  untraced        {tot - sum(v[0] for v in agg.values()):8.2f} ms")
+        for (k, tag), v in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:14]:
+            print(f"    {v[0]:7.2f} ms {v[1]:3d}x  {k} {tag}")
 
 
 if __name__ == "__main__":
