@@ -505,6 +505,157 @@ __global__ void __launch_bounds__(AB_THREADS) expert_attn_kernel(const ExpArgs p
     }
 }
 
+// ---- expert streams with at most 16 tokens each (AnySD: 16 visual tokens per expert, 11 experts) ---------------------------
+// The kernel above spends a full 64-key tile, a K/V load and two CTA barriers on every expert.  Here ALL experts' keys and values
+// of the (batch, head) are staged once -- expert e in key slots [16 e, 16 e + 16), unused slots zero -- and a 64-key tile of the
+// products covers FOUR experts: each expert's softmax is a segment of 16 columns (two n8 fragments), normalised and gated
+// before P.V, so the accumulator simply adds over all keys.  Same arithmetic per expert as above (fp32 softmax, fp16 P),
+// 3 tile passes instead of 11 for E = 11.  [measured, B = 16, 8 heads, 4096 queries, d = 40, E = 11] forward 378 -> see DESIGN.md 6.
+template <int DP, bool BWD>
+__global__ void __launch_bounds__(AB_THREADS) expert_attn16_kernel(const ExpArgs p, int groups, int qtiles) {
+    constexpr int LDS = DP + 8, TILE = AB_T * LDS, CH = DP / 8;
+    extern __shared__ __align__(128) __half ab_smem[];
+    __half* sQ = ab_smem;
+    __half* sdO = sQ + TILE;             // BWD only (the slot exists either way)
+    __half* sK = sdO + TILE;
+    __half* sV = sK + groups * TILE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.z, h = blockIdx.y;
+    int q0 = blockIdx.x * qtiles * AB_T;                         // the CTA walks `qtiles` query tiles: K/V are staged once for all of them
+    const int dch = p.d / 8;
+    b_load_tile<DP>(p.q + (size_t)b * p.qbs + (size_t)h * p.hs, p.ldq, q0, p.n_q, dch, sQ);
+    if (BWD) b_load_tile<DP>(p.dout + (size_t)b * p.dobs + (size_t)h * p.d, p.lddo, q0, p.n_q, dch, sdO);
+    const __half* kvg = p.kv + (size_t)b * p.kvbs + (size_t)h * p.hs;
+    for (int i = tid; i < groups * AB_T * CH; i += AB_THREADS) {
+        const int row = i / CH, c = i - row * CH;
+        const int e = row >> 4, r = row & 15;
+        const bool ok = e < p.E && r < p.n_kv && c < dch;
+        const __half* src = kvg + (ok ? (size_t)e * p.set_stride + (size_t)r * p.ldkv + c * 8 : 0);
+        cp_async16(smem_u32(sK + row * LDS + c * 8), src, ok);
+        cp_async16(smem_u32(sV + row * LDS + c * 8), src + (ok ? p.v_off : 0), ok);
+    }
+    cp_async_commit();
+    for (int qt = 0; qt < qtiles && q0 < p.n_q; ++qt, q0 += AB_T) {
+    if (qt > 0) {
+        __syncthreads();                 // every warp is through with the previous query tile
+        b_load_tile<DP>(p.q + (size_t)b * p.qbs + (size_t)h * p.hs, p.ldq, q0, p.n_q, dch, sQ);
+        if (BWD) b_load_tile<DP>(p.dout + (size_t)b * p.dobs + (size_t)h * p.d, p.lddo, q0, p.n_q, dch, sdO);
+        cp_async_commit();
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    float acc[DP / 8][4];                // forward: O;  backward: dq
+#pragma unroll
+    for (int i = 0; i < DP / 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int g4 = 0; g4 < groups; ++g4) {
+        float s[AB_T / 8][4];
+        b_mma_nt<DP, AB_T>(s, sQ, warp * 16, sK + g4 * TILE, lane);
+        float dp[AB_T / 8][4];
+        if (BWD) b_mma_nt<DP, AB_T>(dp, sdO, warp * 16, sV + g4 * TILE, lane);
+        uint32_t af[AB_T / 16][4];
+#pragma unroll
+        for (int el = 0; el < 4; ++el) {
+            const int e = g4 * 4 + el;
+            const bool valid = e < p.E;
+            const float g = valid ? p.gates[(size_t)b * p.gate_b_stride + e] : 0.f;
+            float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int col = jj * 8 + (lane & 3) * 2 + (t & 1);
+                    const float v = (valid && col < p.n_kv) ? s[2 * el + jj][t] * p.c_log2 : -INFINITY;
+                    s[2 * el + jj][t] = v;
+                    mx[t >> 1] = fmaxf(mx[t >> 1], v);
+                }
+            float l[2] = {0.f, 0.f};
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+                if (!valid) mx[r] = 0.f;                           // an empty slot group: every p = exp2(-inf) = 0, no NaN
+            }
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    s[2 * el + jj][t] = b_ex2(s[2 * el + jj][t] - mx[t >> 1]);
+                    l[t >> 1] += s[2 * el + jj][t];
+                }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+                l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+            }
+            const float inv[2] = {valid ? 1.0f / l[0] : 0.f, valid ? 1.0f / l[1] : 0.f};
+            if (!BWD) {
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = 2 * el + jj;
+                    af[j >> 1][(j & 1) * 2 + 0] = pack_h2(s[j][0] * inv[0] * g, s[j][1] * inv[0] * g);
+                    af[j >> 1][(j & 1) * 2 + 1] = pack_h2(s[j][2] * inv[1] * g, s[j][3] * inv[1] * g);
+                }
+            } else {
+                float d_raw[2] = {0.f, 0.f};
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        s[2 * el + jj][t] *= inv[t >> 1];             // p_ij
+                        d_raw[t >> 1] += s[2 * el + jj][t] * dp[2 * el + jj][t];
+                    }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    d_raw[r] += __shfl_xor_sync(0xffffffffu, d_raw[r], 1);
+                    d_raw[r] += __shfl_xor_sync(0xffffffffu, d_raw[r], 2);
+                }
+                float dg_part = 0.f;
+                if (valid) {
+                    const size_t base = (((size_t)b * p.heads + h) * p.E + e) * p.n_q;
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int row = q0 + warp * 16 + (lane >> 2) + r * 8;
+                        if (row < p.n_q && (lane & 3) == 0) {
+                            p.lse[base + row] = mx[r] + log2f(l[r]);
+                            p.D[base + row] = g * d_raw[r];
+                            dg_part += d_raw[r];
+                        }
+                    }
+                }
+                dg_part = warp_sum(dg_part);
+                if (valid && lane == 0 && dg_part != 0.f) atomicAdd(p.dgates + (size_t)b * p.gate_b_stride + e, dg_part);
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = 2 * el + jj;
+                    float ds[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) ds[t] = p.c_nat * g * s[j][t] * (dp[j][t] - d_raw[t >> 1]);
+                    af[j >> 1][(j & 1) * 2 + 0] = pack_h2(ds[0], ds[1]);
+                    af[j >> 1][(j & 1) * 2 + 1] = pack_h2(ds[2], ds[3]);
+                }
+            }
+        }
+        if (!BWD) b_mma_nn<DP, AB_T, DP>(acc, af, sV + g4 * TILE, 0, lane);      // O += sum over the group's experts (g / l) P V
+        else b_mma_nn<DP, AB_T, DP>(acc, af, sK + g4 * TILE, 0, lane);            // dq += dS K
+    }
+    __half* og = BWD ? p.dq + (size_t)b * p.dqbs + (size_t)h * p.hs : p.out + (size_t)b * p.obs + (size_t)h * p.d;
+    const int ld = BWD ? p.lddq : p.ldo;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int row = q0 + warp * 16 + (lane >> 2) + r * 8;
+        if (row >= p.n_q) continue;
+#pragma unroll
+        for (int i = 0; i < DP / 8; ++i) {
+            const int col = i * 8 + (lane & 3) * 2;
+            if (col >= p.d) continue;
+            __half2* dst = reinterpret_cast<__half2*>(og + (size_t)row * ld + col);
+            const float2 prev = __half22float2(*dst);
+            *dst = __floats2half2_rn(prev.x + acc[i][r * 2], prev.y + acc[i][r * 2 + 1]);
+        }
+    }
+    }                                    // query tiles
+}
+
 template <int DP>
 static int launch_experts(const ExpArgs& a, const BwdArgs* dkv, int B, cudaStream_t st) {
     constexpr int LDS = DP + 8;
@@ -520,12 +671,36 @@ static int launch_experts(const ExpArgs& a, const BwdArgs* dkv, int B, cudaStrea
         cudaFuncSetAttribute(attn_bwd_dkv_kernel<DP, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         done[dev] = true;
     }
-    const dim3 grid(cdiv(a.n_q, AB_T), a.heads, B);
+    dim3 grid(cdiv(a.n_q, AB_T), a.heads, B);
+    // few tokens per expert: all experts staged once, four per key tile (expert_attn16_kernel); ANYSD_EXPERT16=0 switches it off
+    static const char* e16 = getenv("ANYSD_EXPERT16");
+    const int groups = (a.E + 3) / 4;
+    const int smem16 = (2 + 2 * groups) * AB_T * LDS * (int)sizeof(__half);
+    const bool use16 = a.n_kv <= 16 && smem16 <= 200 * 1024 && !(e16 && e16[0] == '0');
+    if (use16) {
+        static int set16[64];
+        if (set16[dev] < smem16) {
+            cudaFuncSetAttribute(expert_attn16_kernel<DP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16);
+            cudaFuncSetAttribute(expert_attn16_kernel<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16);
+            set16[dev] = smem16;
+        }
+    }
+    // query tiles per CTA: as many as keep >= 4 CTAs per SM busy (K/V staging amortised), at most 8
+    static const char* qt_env = getenv("ANYSD_EXPERT_QT");
+    int qtiles = 1;
+    if (use16) {
+        const long ctas1 = (long)cdiv(a.n_q, AB_T) * a.heads * B;
+        while (qtiles < 8 && ctas1 / (qtiles * 2) >= 4L * sm_count()) qtiles *= 2;
+        if (qt_env) qtiles = atoi(qt_env) > 0 ? atoi(qt_env) : 1;
+    }
+    const dim3 grid16(cdiv(a.n_q, AB_T * qtiles), a.heads, B);
     if (dkv == nullptr) {
-        expert_attn_kernel<DP, false><<<grid, AB_THREADS, smem, st>>>(a);
+        if (use16) expert_attn16_kernel<DP, false><<<grid16, AB_THREADS, smem16, st>>>(a, groups, qtiles);
+        else expert_attn_kernel<DP, false><<<grid, AB_THREADS, smem, st>>>(a);
         return check_launch("expert attention");
     }
-    expert_attn_kernel<DP, true><<<grid, AB_THREADS, smem, st>>>(a);
+    if (use16) expert_attn16_kernel<DP, true><<<grid16, AB_THREADS, smem16, st>>>(a, groups, qtiles);
+    else expert_attn_kernel<DP, true><<<grid, AB_THREADS, smem, st>>>(a);
     int rc = check_launch("expert attention backward (dq)");
     if (rc) return rc;
     attn_bwd_dkv_kernel<DP, DC><<<dim3(cdiv(a.n_kv, AB_T), a.heads, B * a.E), AB_THREADS, smem, st>>>(*dkv);
