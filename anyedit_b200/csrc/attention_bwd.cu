@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(AB_THREADS) expert_attn_kernel(const ExpArgs p
 // of the (batch, head) are staged once -- expert e in key slots [16 e, 16 e + 16), unused slots zero -- and a 64-key tile of the
 // products covers FOUR experts: each expert's softmax is a segment of 16 columns (two n8 fragments), normalised and gated
 // before P.V, so the accumulator simply adds over all keys.  Same arithmetic per expert as above (fp32 softmax, fp16 P),
-// 3 tile passes instead of 11 for E = 11.  [measured, B = 16, 8 heads, 4096 queries, d = 40, E = 11] forward 378 -> see DESIGN.md 6.
+// 3 tile passes instead of 11 for E = 11.  [measured, B = 16, 8 heads, 4096 queries, d = 40, E = 11] forward 373 -> 206 us.
 template <int DP, bool BWD>
 __global__ void __launch_bounds__(AB_THREADS) expert_attn16_kernel(const ExpArgs p, int groups, int qtiles) {
     constexpr int LDS = DP + 8, TILE = AB_T * LDS, CH = DP / 8;
@@ -685,14 +685,11 @@ static int launch_experts(const ExpArgs& a, const BwdArgs* dkv, int B, cudaStrea
             set16[dev] = smem16;
         }
     }
-    // query tiles per CTA: as many as keep >= 4 CTAs per SM busy (K/V staging amortised), at most 8
+    // query tiles per CTA: 1.  [measured, B = 16, 8 heads, 4096 queries, E = 11] 1 / 2 / 4 / 8 tiles per CTA: 1.94 / 1.96 / 1.99 /
+    // 1.98 ms per training step for the 16 forward launches -- staging the 37 KB of K/V is not what the kernel waits for (ncu: 33 %
+    // issue slots, 2.2 K instructions per warp and tile, most of them the segmented softmax).  ANYSD_EXPERT_QT overrides.
     static const char* qt_env = getenv("ANYSD_EXPERT_QT");
-    int qtiles = 1;
-    if (use16) {
-        const long ctas1 = (long)cdiv(a.n_q, AB_T) * a.heads * B;
-        while (qtiles < 8 && ctas1 / (qtiles * 2) >= 4L * sm_count()) qtiles *= 2;
-        if (qt_env) qtiles = atoi(qt_env) > 0 ? atoi(qt_env) : 1;
-    }
+    const int qtiles = (use16 && qt_env && atoi(qt_env) > 0) ? atoi(qt_env) : 1;
     const dim3 grid16(cdiv(a.n_q, AB_T * qtiles), a.heads, B);
     if (dkv == nullptr) {
         if (use16) expert_attn16_kernel<DP, false><<<grid16, AB_THREADS, smem16, st>>>(a, groups, qtiles);
