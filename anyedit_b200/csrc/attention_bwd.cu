@@ -279,7 +279,10 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dq_kernel(const BwdArgs p
     }
 }
 
-template <int DP, int DC>
+// PACK (expert streams with <= 16 tokens per expert, launch_experts): the 64 key rows of the CTA are FOUR experts' 16 token slots
+// -- warp w owns expert 4 blockIdx.z' + w: its own gate, log-sum-exp / D rows and output rows -- instead of one expert's 16 tokens
+// and 48 idle rows: a quarter of the CTAs for the same tile products.
+template <int DP, int DC, bool PACK = false>
 __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const BwdArgs p) {
     constexpr int LDS = DP + 8, TILE = AB_T * LDS;
     extern __shared__ __align__(128) __half ab_smem[];
@@ -287,23 +290,41 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const BwdArgs 
     __half* sV = sK + TILE;
     __half* sQ = sV + TILE;
     __half* sdO = sQ + TILE;
-    float* s_lse = reinterpret_cast<float*>(sdO + TILE);
-    float* s_D = s_lse + AB_T;
+    float* s_lse = reinterpret_cast<float*>(sdO + TILE);       // PACK: [4][AB_T] each
+    float* s_D = s_lse + (PACK ? 4 : 1) * AB_T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int e = p.sets > 1 ? blockIdx.z % p.sets : 0;
-    const int b = p.sets > 1 ? blockIdx.z / p.sets : blockIdx.z;
+    const int egroups = PACK ? (p.sets + 3) / 4 : 1;
+    const int e = PACK ? (blockIdx.z % egroups) * 4 + warp : (p.sets > 1 ? blockIdx.z % p.sets : 0);       // PACK: this warp's expert
+    const int b = PACK ? blockIdx.z / egroups : (p.sets > 1 ? blockIdx.z / p.sets : blockIdx.z);
+    const bool e_ok = !PACK || e < p.sets;
     const int h = blockIdx.y, k0 = blockIdx.x * AB_T;
     const int dch = p.d / 8;
     const __half* qg = p.q + (size_t)b * p.qbs + (size_t)h * p.hs;
     const __half* kg = p.k + (size_t)b * p.kbs + (size_t)h * p.hs + (size_t)e * p.set_stride;
     const __half* vg = p.v + (size_t)b * p.vbs + (size_t)h * p.hs + (size_t)e * p.set_stride;
     const __half* og = p.dout + (size_t)b * p.dobs + (size_t)h * p.d;
-    const float g = p.gate ? p.gate[(size_t)b * p.gate_stride + (size_t)e * p.gate_set_stride] : 1.0f;
-    const size_t sbase = (((size_t)b * p.heads + h) * p.sets + e) * p.n_q;
+    const float g = (p.gate && e_ok) ? p.gate[(size_t)b * p.gate_stride + (size_t)e * p.gate_set_stride] : (e_ok ? 1.0f : 0.f);
+    const size_t sbase = (((size_t)b * p.heads + h) * p.sets + (e_ok ? e : 0)) * p.n_q;
     const int nqt = (p.n_q + AB_T - 1) / AB_T;
 
-    b_load_tile<DP>(kg, p.ldk, k0, p.n_kv, dch, sK);
-    b_load_tile<DP>(vg, p.ldv, k0, p.n_kv, dch, sV);
+    if (PACK) {
+        // key slot r of the tile = token r % 16 of expert 4 z' + r / 16 (zero when the expert or the token does not exist)
+        constexpr int CH = DP / 8;
+        const int e0 = (blockIdx.z % egroups) * 4;
+        const __half* kb = p.k + (size_t)b * p.kbs + (size_t)h * p.hs;
+        const __half* vb = p.v + (size_t)b * p.vbs + (size_t)h * p.hs;
+        for (int i = tid; i < AB_T * CH; i += AB_THREADS) {
+            const int r = i / CH, c = i - r * CH;
+            const int ee = e0 + (r >> 4), tok = r & 15;
+            const bool ok = ee < p.sets && tok < p.n_kv && c < dch;
+            const size_t off = ok ? (size_t)ee * p.set_stride + (size_t)tok * p.ldk + c * 8 : 0;
+            cp_async16(smem_u32(sK + r * LDS + c * 8), kb + off, ok);
+            cp_async16(smem_u32(sV + r * LDS + c * 8), vb + (ok ? (size_t)ee * p.set_stride + (size_t)tok * p.ldv + c * 8 : 0), ok);
+        }
+    } else {
+        b_load_tile<DP>(kg, p.ldk, k0, p.n_kv, dch, sK);
+        b_load_tile<DP>(vg, p.ldv, k0, p.n_kv, dch, sV);
+    }
     cp_async_commit();
 
     for (int c0 = 0; c0 < DP; c0 += DC) {
@@ -318,7 +339,13 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const BwdArgs 
             b_load_tile<DP>(qg, p.ldq, t * AB_T, p.n_q, dch, sQ);
             b_load_tile<DP>(og, p.lddo, t * AB_T, p.n_q, dch, sdO);
             cp_async_commit();
-            if (tid < AB_T) {
+            if (PACK) {                                               // every warp stages its own expert's rows
+                for (int c = lane; c < AB_T; c += 32) {
+                    const int row = t * AB_T + c;
+                    s_lse[warp * AB_T + c] = (row < p.n_q && e_ok) ? p.lse[sbase + row] : INFINITY;
+                    s_D[warp * AB_T + c] = (row < p.n_q && e_ok) ? p.D[sbase + row] : 0.f;
+                }
+            } else if (tid < AB_T) {
                 const int row = t * AB_T + tid;
                 s_lse[tid] = row < p.n_q ? p.lse[sbase + row] : INFINITY;     // exp2(x - inf) = 0: padded queries vanish
                 s_D[tid] = row < p.n_q ? p.D[sbase + row] : 0.f;
@@ -335,8 +362,8 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const BwdArgs 
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int col = j * 8 + (lane & 3) * 2 + (e & 1);
-                    pr[e] = b_ex2(st[j][e] * p.c_log2 - s_lse[col]);
-                    ds[e] = p.c_nat * pr[e] * (g * dpt[j][e] - s_D[col]);
+                    pr[e] = b_ex2(st[j][e] * p.c_log2 - s_lse[(PACK ? warp * AB_T : 0) + col]);
+                    ds[e] = p.c_nat * pr[e] * (g * dpt[j][e] - s_D[(PACK ? warp * AB_T : 0) + col]);
                 }
                 pf[j >> 1][(j & 1) * 2 + 0] = pack_h2(pr[0], pr[1]);
                 pf[j >> 1][(j & 1) * 2 + 1] = pack_h2(pr[2], pr[3]);
@@ -346,12 +373,12 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const BwdArgs 
             b_mma_nn<DP, AB_T, DC>(dv, pf, sdO, c0, lane);          // dv += P^T dO
             b_mma_nn<DP, AB_T, DC>(dk, dsf, sQ, c0, lane);          // dk += dS^T Q
         }
-        __half* dkg = p.dk + (size_t)b * p.dkbs + (size_t)h * p.hs + (size_t)e * p.set_stride;
-        __half* dvg = p.dv + (size_t)b * p.dvbs + (size_t)h * p.hs + (size_t)e * p.set_stride;
+        __half* dkg = p.dk + (size_t)b * p.dkbs + (size_t)h * p.hs + (size_t)(e_ok ? e : 0) * p.set_stride;
+        __half* dvg = p.dv + (size_t)b * p.dvbs + (size_t)h * p.hs + (size_t)(e_ok ? e : 0) * p.set_stride;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            const int row = k0 + warp * 16 + (lane >> 2) + r * 8;
-            if (row >= p.n_kv) continue;
+            const int row = PACK ? (lane >> 2) + r * 8 : k0 + warp * 16 + (lane >> 2) + r * 8;      // PACK: token index inside the warp's expert
+            if (row >= p.n_kv || !e_ok) continue;
 #pragma unroll
             for (int i = 0; i < DC / 8; ++i) {
                 const int col = c0 + i * 8 + (lane & 3) * 2;
@@ -700,7 +727,17 @@ static int launch_experts(const ExpArgs& a, const BwdArgs* dkv, int B, cudaStrea
     else expert_attn_kernel<DP, true><<<grid, AB_THREADS, smem, st>>>(a);
     int rc = check_launch("expert attention backward (dq)");
     if (rc) return rc;
-    attn_bwd_dkv_kernel<DP, DC><<<dim3(cdiv(a.n_kv, AB_T), a.heads, B * a.E), AB_THREADS, smem, st>>>(*dkv);
+    if (use16) {
+        const int smem_p = 4 * AB_T * LDS * (int)sizeof(__half) + 8 * AB_T * (int)sizeof(float);
+        static int setp[64];
+        if (!setp[dev]) {
+            cudaFuncSetAttribute(attn_bwd_dkv_kernel<DP, DC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
+            setp[dev] = 1;
+        }
+        attn_bwd_dkv_kernel<DP, DC, true><<<dim3(1, a.heads, B * groups), AB_THREADS, smem_p, st>>>(*dkv);
+    } else {
+        attn_bwd_dkv_kernel<DP, DC><<<dim3(cdiv(a.n_kv, AB_T), a.heads, B * a.E), AB_THREADS, smem, st>>>(*dkv);
+    }
     return check_launch("expert attention backward (dk, dv)");
 }
 
