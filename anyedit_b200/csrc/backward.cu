@@ -2,6 +2,7 @@
 // latency-bound elementwise and reduction kernels; every contraction of the backward pass reuses anysd_gemm_f16 with
 // transposed / rotated weight packs (host side), attention has its own file (attention_bwd.cu).
 // Activation gradients are fp16 (the caller scales the loss), statistics and parameter gradients fp32.
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -59,24 +60,32 @@ __global__ void silu_bwd_f32_kernel(const float* __restrict__ x, const float* __
 // ---- GroupNorm(+SiLU) backward ---------------------------------------------------------------------------------
 // y = [silu](z), z = xhat * gamma + beta, xhat = (x - mean) * rstd over the group's HW x cpg elements:
 //   dz = dy * silu'(z);  w = dz * gamma;  dx = rstd * (w - mean(w) - xhat * mean(w * xhat))
-// One CTA per (image, span of `gpc` whole groups that is also a whole number of 16-byte channel vectors): VC =
-// gpc*cpg/8 vector columns x RL row lanes.  Three passes over the slab (statistics; the two sums; dx), the slab
-// stays in L2.  Per-channel partials are folded over the row lanes in smem, then per group.
+// One thread-block CLUSTER per (image, span of `gpc` whole groups that is also a whole number of 16-byte channel vectors); the
+// cluster's CS CTAs split the HW rows, each with VC = gpc*cpg/8 vector columns x RL row lanes.  Three passes over the slab
+// (statistics; the two sums; dx), the slab stays in L2.  Per-channel partials are folded over the row lanes in smem, then per
+// group, then over the cluster through distributed shared memory in rank order (deterministic).  [measured, round 2] one CTA
+// per slab left the 64x64 level at 128 CTAs with one 16-byte load in flight per thread (118-204 us per launch, ~1 TB/s).
 constexpr int GNB_THREADS = 256;
 __global__ void __launch_bounds__(GNB_THREADS) gn_bwd_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              const __half* __restrict__ dy, __half* __restrict__ dx, int HW, int cpg,
-                                                             int gpc, float eps, int fuse_silu) {
-    extern __shared__ float gsm[];                 // [2][RL][VC*8] partials | [VC*8] a | [VC*8] b | per group 4 floats
+                                                             int gpc, float eps, int fuse_silu, int CS) {
+    extern __shared__ float gsm[];                 // [2][RL][VC*8] partials | per group 4 floats | per group 2 cluster partials
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = CS > 1 ? (int)cluster.block_rank() : 0;
     const int n = blockIdx.y;
     const int C = C1 + C2;
     const int VC = gpc * cpg / 8, CW = VC * 8;     // channel vectors / channels of this CTA
-    const int c_base = blockIdx.x * CW;
+    const int c_base = (blockIdx.x / CS) * CW;
+    const int rows_per = (HW + CS - 1) / CS;
+    const int row_lo = crank * rows_per, row_hi = min(HW, row_lo + rows_per);
     const int RL = GNB_THREADS / VC;
     const int vl = threadIdx.x % VC, rl = threadIdx.x / VC;
     const bool active = rl < RL;
     float* part = gsm;                             // [2][RL][CW]
     float* grp = gsm + 2 * RL * CW;                // [gpc][4]: mean, rstd, mean(w), mean(w*xhat)
+    float* cpart = grp + 4 * gpc;                  // [gpc][2]: this CTA's raw sums, read by the whole cluster
     const int c0 = c_base + vl * 8;                // first channel of this thread's vector (a vector never straddles x1|x2: C1 % 8 == 0)
     const bool first = c0 < C1;
     const __half* xb = first ? x1 + (size_t)n * HW * C1 + c0 : x2 + (size_t)n * HW * C2 + (c0 - C1);
@@ -109,17 +118,38 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_bwd_kernel(const __half* __res
                 ta += part[c];
                 tb += part[RL * CW + c];
             }
-            grp[threadIdx.x * 4 + slot_a] = ta * inv_cnt;
-            grp[threadIdx.x * 4 + slot_b] = tb * inv_cnt;
+            if (CS > 1) {
+                cpart[threadIdx.x * 2] = ta;
+                cpart[threadIdx.x * 2 + 1] = tb;
+            } else {
+                grp[threadIdx.x * 4 + slot_a] = ta * inv_cnt;
+                grp[threadIdx.x * 4 + slot_b] = tb * inv_cnt;
+            }
         }
-        __syncthreads();
+        if (CS > 1) {
+            cluster.sync();                        // every CTA's raw sums are in its own shared memory
+            if (threadIdx.x < gpc) {
+                float ta = 0.f, tb = 0.f;
+                for (int rk = 0; rk < CS; ++rk) {  // rank order: the same sum in every CTA, whatever finishes first
+                    const float* rp = cluster.map_shared_rank(cpart, rk);
+                    ta += rp[threadIdx.x * 2];
+                    tb += rp[threadIdx.x * 2 + 1];
+                }
+                grp[threadIdx.x * 4 + slot_a] = ta * inv_cnt;
+                grp[threadIdx.x * 4 + slot_b] = tb * inv_cnt;
+            }
+            cluster.sync();                        // nobody overwrites its partials while a neighbour still reads them
+        } else {
+            __syncthreads();
+        }
     };
 
     float a8[8], b8[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) a8[j] = b8[j] = 0.f;
     if (active)
-        for (int r = rl; r < HW; r += RL) {
+#pragma unroll 4
+        for (int r = row_lo + rl; r < row_hi; r += RL) {
             float f[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(xb + (size_t)r * xs)), f);
 #pragma unroll
@@ -150,7 +180,8 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_bwd_kernel(const __half* __res
 #pragma unroll
     for (int j = 0; j < 8; ++j) a8[j] = b8[j] = 0.f;
     if (active)
-        for (int r = rl; r < HW; r += RL) {
+#pragma unroll 4
+        for (int r = row_lo + rl; r < row_hi; r += RL) {
             float f[8], d[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(xb + (size_t)r * xs)), f);
             unpack8(__ldg(reinterpret_cast<const uint4*>(dyb + (size_t)r * C)), d);
@@ -173,7 +204,8 @@ __global__ void __launch_bounds__(GNB_THREADS) gn_bwd_kernel(const __half* __res
             mw8[j] = grp[gl * 4 + 2];
             mwx8[j] = grp[gl * 4 + 3];
         }
-        for (int r = rl; r < HW; r += RL) {
+#pragma unroll 4
+        for (int r = row_lo + rl; r < row_hi; r += RL) {
             float f[8], d[8], o[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(xb + (size_t)r * xs)), f);
             unpack8(__ldg(reinterpret_cast<const uint4*>(dyb + (size_t)r * C)), d);
@@ -631,13 +663,32 @@ int anysd_groupnorm_bwd_nhwc_f16(const void* x1, int C1, const void* x2, int C2,
     ANYSD_REQUIRE(G % gpc == 0 && gpc * cpg / 8 <= GNB_THREADS, ANYSD_EUNSUPPORTED,
                   "groupnorm_bwd: C=%d, G=%d does not tile into 16-byte channel vectors", C, G);
     const int VC = gpc * cpg / 8, RL = GNB_THREADS / VC;
-    const size_t smem = ((size_t)2 * RL * VC * 8 + 4 * gpc) * sizeof(float);
+    const size_t smem = ((size_t)2 * RL * VC * 8 + 6 * gpc) * sizeof(float);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(gn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         ANYSD_REQUIRE(e == cudaSuccess, ANYSD_ECUDA, "groupnorm_bwd: smem opt-in failed: %s", cudaGetErrorString(e));
     }
-    gn_bwd_kernel<<<dim3(G / gpc, N), GNB_THREADS, smem, (cudaStream_t)stream>>>((const __half*)x1, C1, (const __half*)x2, C2, gamma, beta,
-                                                                               (const __half*)dy, (__half*)dx, HW, cpg, gpc, eps, fuse_silu);
+    // CTAs per slab (cluster along x): enough rows per CTA to keep the RL row lanes busy
+    static const char* cs_env = getenv("ANYSD_GNBWD_CLUSTER");
+    // [measured, B = 16] 64x64x320: 198 -> 131 us with 8 CTAs per slab; 32x32x640 and below get SLOWER (two cluster barriers per
+    // fold cost more than the parallelism buys): clusters only for the large maps
+    int CS = HW >= 2048 ? 8 : 1;
+    if (cs_env) CS = atoi(cs_env) >= 1 ? atoi(cs_env) : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((G / gpc) * CS, N);
+    cfg.blockDim = dim3(GNB_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gn_bwd_kernel, (const __half*)x1, C1, (const __half*)x2, C2, gamma, beta, (const __half*)dy,
+                                        (__half*)dx, HW, cpg, gpc, eps, fuse_silu, CS);
+    ANYSD_REQUIRE(le == cudaSuccess, ANYSD_ECUDA, "groupnorm_bwd: launch failed: %s", cudaGetErrorString(le));
     return check_launch("groupnorm_bwd");
 }
 

@@ -162,7 +162,8 @@ def test_attention_backward_tcgen05(ops, monkeypatch, B, heads, nq, nkv, d, aux)
     assert rel(unpad(dq2, nq)[..., :d], 2 * qr.grad) < 4e-3
 
 
-@pytest.mark.parametrize("N,HW,C1,C2,silu", [(2, 60, 64, 0, True), (3, 35, 96, 32, True), (2, 16, 320, 0, False), (1, 100, 64, 128, False)])
+@pytest.mark.parametrize("N,HW,C1,C2,silu", [(2, 60, 64, 0, True), (3, 35, 96, 32, True), (2, 16, 320, 0, False), (1, 100, 64, 128, False),
+                                              (2, 4096, 64, 0, True), (1, 1030, 96, 32, True), (2, 200, 320, 0, False)])   # 8 / 4 / 2 CTAs per slab
 def test_groupnorm_backward(ops, N, HW, C1, C2, silu):
     C = C1 + C2
     x = h16(randn(11, N, HW, C) * 1.5 + 0.3)
