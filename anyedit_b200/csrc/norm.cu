@@ -375,6 +375,91 @@ __global__ void __launch_bounds__(512, 2) gn_fused_kernel(const GnFusedArgs a) {
     }
 }
 
+// ---- GroupNorm(+SiLU) with the slab in shared memory (small maps) ----------------------------------------------------------
+// One CTA per (image, span of `gpc` whole groups that is a whole number of 16-byte channel vectors): the HW x CW slab (<= 96 KB)
+// is read ONCE into shared memory, the moments are exact two-pass sums over it (mean, then centred squares: no E[x^2] - mean^2
+// cancellation) in a fixed order -- every output bit independent of the batch -- and the normalised rows stream out.  One plain
+// launch; the cooperative statistics + apply kernel costs 14-19 us on the 8x8 / 16x16 maps, whose data would move in 2 us.
+constexpr int GNS_THREADS = 256;
+__global__ void __launch_bounds__(GNS_THREADS) gn_slab_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, uint4* __restrict__ y, int HW, int CV, int VC,
+                                                              int cpg, int gpc, float eps, int fuse_silu) {
+    extern __shared__ __align__(16) unsigned char gns_raw[];
+    uint4* slab = reinterpret_cast<uint4*>(gns_raw);                      // [HW][VC] vectors of 8 halves
+    float* red = reinterpret_cast<float*>(gns_raw + (size_t)HW * VC * 16);   // [RL][CW] partials | [gpc] mean | [gpc] rstd
+    const int n = blockIdx.y, v0 = blockIdx.x * VC;
+    const int tid = threadIdx.x;
+    const int CW = VC * 8;
+    const uint4* xb = x + (size_t)n * HW * CV + v0;
+    uint4* yb = y + (size_t)n * HW * CV + v0;
+    const int total = HW * VC;
+    for (int i = tid; i < total; i += GNS_THREADS) {
+        const int r = i / VC, v = i - r * VC;
+        slab[i] = __ldg(xb + (size_t)r * CV + v);
+    }
+    __syncthreads();
+    // moments: thread (row lane rl, vector vl) accumulates its 8 channels over rows rl, rl + RL, ...; the row lanes are folded per
+    // channel, the channels per group -- all in a fixed order.  Pass 0: sums -> mean; pass 1: centred squares -> rstd.
+    const int RL = GNS_THREADS / VC;
+    const int vl = tid % VC, rl = tid / VC;
+    const bool active = rl < RL;
+    float* part = red;                                 // [RL][CW]
+    float* mean_s = red + RL * CW;
+    float* rstd_s = mean_s + gpc;
+    const float inv_cnt = 1.0f / ((float)HW * cpg);
+    for (int pass = 0; pass < 2; ++pass) {
+        float a8[8], m8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a8[j] = 0.f;
+            m8[j] = pass ? mean_s[(vl * 8 + j) / cpg] : 0.f;
+        }
+        if (active)
+#pragma unroll 4
+            for (int r = rl; r < HW; r += RL) {
+                float f[8];
+                unpack8(slab[r * VC + vl], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float v = f[j] - m8[j];
+                    a8[j] += pass ? v * v : v;
+                }
+            }
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) part[rl * CW + vl * 8 + j] = a8[j];
+        }
+        __syncthreads();
+        for (int c = tid; c < CW; c += GNS_THREADS) {
+            float t = 0.f;
+            for (int r = 0; r < RL; ++r) t += part[r * CW + c];
+            part[c] = t;
+        }
+        __syncthreads();
+        if (tid < gpc) {
+            float t = 0.f;
+            for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) t += part[c];
+            if (pass == 0) mean_s[tid] = t * inv_cnt;
+            else rstd_s[tid] = rsqrtf(t * inv_cnt + eps);
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < total; i += GNS_THREADS) {
+        const int r = i / VC, v = i - r * VC;
+        float f[8], o[8];
+        unpack8(slab[i], f);
+        const int c0 = v * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int gl = (c0 + j) / cpg;
+            const float ga = __ldg(gamma + (size_t)(v0 * 8 + c0 + j)), be = __ldg(beta + (size_t)(v0 * 8 + c0 + j));
+            const float z = (f[j] - mean_s[gl]) * rstd_s[gl] * ga + be;
+            o[j] = fuse_silu ? silu_f(z) : z;
+        }
+        yb[(size_t)r * CV + v] = pack8(o);
+    }
+}
+
 // ---- LayerNorm: LPR lanes per token row (8 / 16 / 32), VPL 16-byte vectors per lane held in registers ---------
 // C = 320 / 640 / 1280 map to LPR = 8 / 16 / 32 with exactly 5 vectors per lane: a warp then normalises
 // 4 / 2 / 1 rows at once with 5 independent 16-byte loads in flight per lane (the one-warp-per-row version left
@@ -466,8 +551,32 @@ int anysd_groupnorm_nhwc_f16(const void* x1, int C1, const void* x2, int C2, con
     ANYSD_REQUIRE(C / 8 <= 1024, ANYSD_EINVAL, "groupnorm: C=%d too large", C);
     ANYSD_REQUIRE(workspace_bytes >= anysd_groupnorm_workspace_bytes(N, G, C), ANYSD_EINVAL,
                   "groupnorm: workspace too small (%zu bytes)", workspace_bytes);
-    const GnGeom g = gn_geom(C1, C2);
     const int cpg = C / G;
+    {
+        // small maps: the slab-resident kernel (geometry-only decision: the same kernel whatever the batch).  ANYSD_GN_SLAB=0: off.
+        static const char* slab_env = getenv("ANYSD_GN_SLAB");
+        int gpc = 1;
+        while ((gpc * cpg) % 8 != 0) ++gpc;
+        const int VC = gpc * cpg / 8;
+        const size_t smem_slab = (size_t)HW * VC * 16 + ((size_t)(GNS_THREADS / VC) * VC * 8 + 2 * gpc) * sizeof(float);
+        if (x2 == nullptr && G % gpc == 0 && VC <= GNS_THREADS && HW <= 1024 && smem_slab <= 96 * 1024 && !(slab_env && slab_env[0] == '0')) {
+            if (smem_slab > 48 * 1024) {
+                static size_t set_for[64];
+                int dev = 0;
+                cudaGetDevice(&dev);
+                dev &= 63;
+                if (set_for[dev] < smem_slab) {
+                    cudaError_t e = cudaFuncSetAttribute(gn_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+                    ANYSD_REQUIRE(e == cudaSuccess, ANYSD_ECUDA, "groupnorm (slab): smem opt-in failed: %s", cudaGetErrorString(e));
+                    set_for[dev] = 96 * 1024;
+                }
+            }
+            gn_slab_kernel<<<dim3(G / gpc, N), GNS_THREADS, smem_slab, (cudaStream_t)stream>>>((const uint4*)x1, gamma, beta, (uint4*)y, HW, C / 8, VC,
+                                                                                            cpg, gpc, eps, fuse_silu);
+            return check_launch("groupnorm (slab)");
+        }
+    }
+    const GnGeom g = gn_geom(C1, C2);
     // The spatial split depends on the image geometry only (never on N): the summation order, and hence
     // every output bit, is independent of how many samples share the batch.  >= 8 row-steps per block.
     // A chunk is one batch of GN_U row-steps per thread (more only when that would exceed GN_MAX_SPLITS chunks).
