@@ -84,6 +84,7 @@ SIGNATURES = {
     "anysd_emb_finalize": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _I, _I, _VP]),
     "anysd_router_gate_f32": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "anysd_groupnorm_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "anysd_groupnorm_resident": (_I, [_I, _I, _I, _I]),
     "anysd_groupnorm_nhwc_f16": (_I, [_VP, _I, _VP, _I, _VP, _VP, _VP, _I, _I, _I, _F, _I, _VP, _SZ, _VP]),
     "anysd_layernorm_f16": (_I, [_VP, _VP, _VP, _VP, _LL, _I, _F, _VP]),
     "anysd_gemm_f16": (_I, [C.POINTER(GemmParams), _VP]),

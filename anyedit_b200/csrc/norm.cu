@@ -375,89 +375,174 @@ __global__ void __launch_bounds__(512, 2) gn_fused_kernel(const GnFusedArgs a) {
     }
 }
 
-// ---- GroupNorm(+SiLU) with the slab in shared memory (small maps) ----------------------------------------------------------
-// One CTA per (image, span of `gpc` whole groups that is a whole number of 16-byte channel vectors): the HW x CW slab (<= 96 KB)
-// is read ONCE into shared memory, the moments are exact two-pass sums over it (mean, then centred squares: no E[x^2] - mean^2
-// cancellation) in a fixed order -- every output bit independent of the batch -- and the normalised rows stream out.  One plain
-// launch; the cooperative statistics + apply kernel costs 14-19 us on the 8x8 / 16x16 maps, whose data would move in 2 us.
-constexpr int GNS_THREADS = 256;
-__global__ void __launch_bounds__(GNS_THREADS) gn_slab_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, uint4* __restrict__ y, int HW, int CV, int VC,
-                                                              int cpg, int gpc, float eps, int fuse_silu) {
-    extern __shared__ __align__(16) unsigned char gns_raw[];
-    uint4* slab = reinterpret_cast<uint4*>(gns_raw);                      // [HW][VC] vectors of 8 halves
-    float* red = reinterpret_cast<float*>(gns_raw + (size_t)HW * VC * 16);   // [RL][CW] partials | [gpc] mean | [gpc] rstd
-    const int n = blockIdx.y, v0 = blockIdx.x * VC;
-    const int tid = threadIdx.x;
-    const int CW = VC * 8;
-    const uint4* xb = x + (size_t)n * HW * CV + v0;
-    uint4* yb = y + (size_t)n * HW * CV + v0;
-    const int total = HW * VC;
-    for (int i = tid; i < total; i += GNS_THREADS) {
-        const int r = i / VC, v = i - r * VC;
-        slab[i] = __ldg(xb + (size_t)r * CV + v);
-    }
-    __syncthreads();
-    // moments: thread (row lane rl, vector vl) accumulates its 8 channels over rows rl, rl + RL, ...; the row lanes are folded per
-    // channel, the channels per group -- all in a fixed order.  Pass 0: sums -> mean; pass 1: centred squares -> rstd.
-    const int RL = GNS_THREADS / VC;
+// ---- GroupNorm(+SiLU), register-resident (small maps: one read, one write, one plain launch) -------------------------------
+// One CTA per (image, span of `gpc` whole groups that is a whole number of 16-byte channel vectors, VC of them); a CTA is
+// VC x RL threads (RL = 32 or 64 row lanes), thread (rl, vl) owns the vector column vl of rows rl, rl + RL, ... -- at most V of
+// them (V <= 8: maps of up to 8 RL pixels), all loaded up front and KEPT IN REGISTERS until the store.  Moments are exact
+// two-pass sums (mean, then centred squares: no E[x^2] - mean^2 cancellation) folded in a fixed order: thread -> 8 row lanes ->
+// group (one warp, lane-strided + shuffle tree).  The decomposition is a function of (C, HW, G) only, so every output bit is
+// independent of the batch.  Against the cooperative statistics + apply kernel: no second read of x, no grid barrier.
+// [measured, B200, batch 16, tests/diag_gn.py, profiles/r2_diag_gn_resident.txt] 16x16x1280: 14.9 vs 18.9 us; 8x8x1280: 10.9 vs
+// 14.3; 16x16x2560: 19.5 vs 35.4; 8x8x2560: 13.8 vs 14.9.  A cluster version of the same kernel (up to 16 CTAs per span splitting
+// the rows, partials exchanged through distributed shared memory) was built for the large maps and was SLOWER than the
+// epilogue-statistics path: 64x64x320 46.5 us (vs 31), 64x64x960 202 us (vs 69), 32x32x640 23.2 (vs 21.3) -- two cluster
+// barriers + the remote reads are ~5 us of latency per CTA that two resident CTAs per SM cannot hide -- so it is not kept.
+struct GnResArgs {
+    const uint4* x1; const uint4* x2; uint4* y;
+    const float* gamma; const float* beta;
+    int CV1, CV2, HW, VC, RL, cpg, gpc, fuse_silu;
+    float eps, inv_cnt;
+};
+
+template <int V>
+__global__ void __maxnreg__(V <= 4 ? 64 : 96) gn_res_kernel(const GnResArgs a) {
+    extern __shared__ __align__(16) float gnr_sm[];
+    const int VC = a.VC, RL = a.RL, CW = VC * 8, P = RL / 8, gpc = a.gpc, cpg = a.cpg;
+    float* part = gnr_sm;                       // [RL][CW] per-thread channel partials
+    float* part2 = part + RL * CW;              // [P][CW]  after the fold over 8 row lanes
+    float* chm = part2 + P * CW;                // [CW] per channel: mean of its group
+    float* cha = chm + CW;                      // [CW] rstd * gamma
+    float* chb = cha + CW;                      // [CW] beta - mean * rstd * gamma
+    float* gsum = chb + CW;                     // [gpc] group sums of the current pass
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int vl = tid % VC, rl = tid / VC;
-    const bool active = rl < RL;
-    float* part = red;                                 // [RL][CW]
-    float* mean_s = red + RL * CW;
-    float* rstd_s = mean_s + gpc;
-    const float inv_cnt = 1.0f / ((float)HW * cpg);
-    for (int pass = 0; pass < 2; ++pass) {
-        float a8[8], m8[8];
+    const int n = blockIdx.y;
+    const int gv = blockIdx.x * VC + vl;                         // global vector column (a vector never straddles x1 | x2)
+    const bool first = gv < a.CV1;
+    const uint4* src = first ? a.x1 + (size_t)n * a.HW * a.CV1 + gv : a.x2 + (size_t)n * a.HW * a.CV2 + (gv - a.CV1);
+    const int xs = first ? a.CV1 : a.CV2, CV = a.CV1 + a.CV2;
+    uint4 d[V];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            a8[j] = 0.f;
-            m8[j] = pass ? mean_s[(vl * 8 + j) / cpg] : 0.f;
+    for (int k = 0; k < V; ++k) {
+        const int r = rl + k * RL;
+        d[k] = r < a.HW ? __ldg(src + r * xs) : make_uint4(0u, 0u, 0u, 0u);
+    }
+
+    // per-thread 8-channel partials -> per-group sums in gsum[g]
+    auto fold = [&](const float* v8) {
+        float4* pw = reinterpret_cast<float4*>(part + rl * CW + vl * 8);
+        pw[0] = make_float4(v8[0], v8[1], v8[2], v8[3]);
+        pw[1] = make_float4(v8[4], v8[5], v8[6], v8[7]);
+        __syncthreads();
+        {
+            const int c = tid % CW, p = tid / CW;               // blockDim = VC * RL = CW * P threads exactly
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += part[(p * 8 + i) * CW + c];
+            part2[p * CW + c] = t;
         }
-        if (active)
-#pragma unroll 4
-            for (int r = rl; r < HW; r += RL) {
+        __syncthreads();
+        for (int g = warp; g < gpc; g += nwarps) {
+            float t = 0.f;
+            for (int i = lane; i < cpg * P; i += 32) t += part2[(i / cpg) * CW + g * cpg + (i % cpg)];
+            t = warp_sum(t);
+            if (lane == 0) gsum[g] = t;
+        }
+        __syncthreads();
+    };
+
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        float f[8];
+        unpack8(d[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];             // rows beyond HW hold zeros
+    }
+    fold(acc);
+    if (tid < CW) chm[tid] = gsum[tid / cpg] * a.inv_cnt;
+    __syncthreads();
+    {
+        const float4 m0 = *reinterpret_cast<const float4*>(chm + vl * 8), m1 = *reinterpret_cast<const float4*>(chm + vl * 8 + 4);
+        const float m8[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            if (rl + k * RL < a.HW) {
                 float f[8];
-                unpack8(slab[r * VC + vl], f);
+                unpack8(d[k], f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float v = f[j] - m8[j];
-                    a8[j] += pass ? v * v : v;
+                    const float c = f[j] - m8[j];
+                    acc[j] = fmaf(c, c, acc[j]);
                 }
             }
-        if (active) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) part[rl * CW + vl * 8 + j] = a8[j];
         }
-        __syncthreads();
-        for (int c = tid; c < CW; c += GNS_THREADS) {
-            float t = 0.f;
-            for (int r = 0; r < RL; ++r) t += part[r * CW + c];
-            part[c] = t;
-        }
-        __syncthreads();
-        if (tid < gpc) {
-            float t = 0.f;
-            for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) t += part[c];
-            if (pass == 0) mean_s[tid] = t * inv_cnt;
-            else rstd_s[tid] = rsqrtf(t * inv_cnt + eps);
-        }
-        __syncthreads();
     }
-    for (int i = tid; i < total; i += GNS_THREADS) {
-        const int r = i / VC, v = i - r * VC;
-        float f[8], o[8];
-        unpack8(slab[i], f);
-        const int c0 = v * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int gl = (c0 + j) / cpg;
-            const float ga = __ldg(gamma + (size_t)(v0 * 8 + c0 + j)), be = __ldg(beta + (size_t)(v0 * 8 + c0 + j));
-            const float z = (f[j] - mean_s[gl]) * rstd_s[gl] * ga + be;
-            o[j] = fuse_silu ? silu_f(z) : z;
-        }
-        yb[(size_t)r * CV + v] = pack8(o);
+    fold(acc);
+    if (tid < CW) {
+        const float rstd = rsqrtf(gsum[tid / cpg] * a.inv_cnt + a.eps);
+        const float ga = __ldg(a.gamma + blockIdx.x * CW + tid) * rstd;
+        cha[tid] = ga;
+        chb[tid] = __ldg(a.beta + blockIdx.x * CW + tid) - chm[tid] * ga;
     }
+    __syncthreads();
+    {
+        const float4 a0 = *reinterpret_cast<const float4*>(cha + vl * 8), a1 = *reinterpret_cast<const float4*>(cha + vl * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(chb + vl * 8), b1 = *reinterpret_cast<const float4*>(chb + vl * 8 + 4);
+        const float a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint4* dst = a.y + (size_t)n * a.HW * CV + gv;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const int r = rl + k * RL;
+            if (r < a.HW) {
+                float f[8], o[8];
+                unpack8(d[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float z = fmaf(f[j], a8[j], b8[j]);
+                    o[j] = a.fuse_silu ? silu_fast(z) : z;
+                }
+                dst[r * CV] = pack8(o);
+            }
+        }
+    }
+}
+
+// Geometry of the register-resident kernel for (C1 + C2 channels, HW pixels, G groups), or false when it does not apply.
+struct GnResPlan { int VC, RL, gpc, V; };
+static bool gn_res_plan(int C1, int C2, int HW, int G, GnResPlan* pl) {
+    static const char* env = getenv("ANYSD_GN_RES");
+    if (env && env[0] == '0') return false;
+    const int C = C1 + C2;
+    if (G <= 0 || C % G != 0 || C1 % 8 != 0 || C2 % 8 != 0 || HW <= 0) return false;
+    const int cpg = C / G;
+    int gpc = 1;
+    while ((gpc * cpg) % 8 != 0) ++gpc;
+    const int VC = gpc * cpg / 8;
+    if (G % gpc != 0 || VC > 16) return false;
+    const int RL = VC * 64 <= 512 ? 64 : 32;
+    const int v = cdiv(HW, RL);
+    if (v > 8) return false;
+    int V = 1;
+    while (V < v) V <<= 1;
+    pl->VC = VC; pl->RL = RL; pl->gpc = gpc; pl->V = V;
+    return true;
+}
+
+static int launch_gn_res(const GnResPlan& pl, const void* x1, int C1, const void* x2, int C2, const float* gamma, const float* beta, void* y,
+                         int N, int HW, int G, float eps, int fuse_silu, cudaStream_t st) {
+    GnResArgs a;
+    a.x1 = (const uint4*)x1; a.x2 = (const uint4*)x2; a.y = (uint4*)y;
+    a.gamma = gamma; a.beta = beta;
+    a.CV1 = C1 / 8; a.CV2 = C2 / 8; a.HW = HW; a.VC = pl.VC; a.RL = pl.RL; a.cpg = (C1 + C2) / G; a.gpc = pl.gpc;
+    a.fuse_silu = fuse_silu; a.eps = eps;
+    a.inv_cnt = 1.0f / ((float)HW * (float)a.cpg);
+    const int CW = pl.VC * 8;
+    const dim3 grid((unsigned)(G / pl.gpc), (unsigned)N);
+    const unsigned T = (unsigned)(pl.VC * pl.RL);
+    const size_t smem = (size_t)(pl.RL * CW + pl.RL / 8 * CW + 3 * CW + pl.gpc) * sizeof(float);
+    switch (pl.V) {
+        case 1: gn_res_kernel<1><<<grid, T, smem, st>>>(a); break;
+        case 2: gn_res_kernel<2><<<grid, T, smem, st>>>(a); break;
+        case 4: gn_res_kernel<4><<<grid, T, smem, st>>>(a); break;
+        default: gn_res_kernel<8><<<grid, T, smem, st>>>(a); break;
+    }
+    return check_launch("groupnorm (resident)");
 }
 
 // ---- LayerNorm: LPR lanes per token row (8 / 16 / 32), VPL 16-byte vectors per lane held in registers ---------
@@ -529,6 +614,11 @@ using namespace anysd;
 
 extern "C" {
 
+int anysd_groupnorm_resident(int C1, int C2, int HW, int G) {
+    GnResPlan pl;
+    return gn_res_plan(C1, C2 < 0 ? 0 : C2, HW, G, &pl) ? 1 : 0;
+}
+
 size_t anysd_groupnorm_workspace_bytes(int N, int G, int C) {
     (void)C;
     if (N <= 0 || G <= 0) return 0;
@@ -553,28 +643,10 @@ int anysd_groupnorm_nhwc_f16(const void* x1, int C1, const void* x2, int C2, con
                   "groupnorm: workspace too small (%zu bytes)", workspace_bytes);
     const int cpg = C / G;
     {
-        // small maps: the slab-resident kernel (geometry-only decision: the same kernel whatever the batch).  ANYSD_GN_SLAB=0: off.
-        static const char* slab_env = getenv("ANYSD_GN_SLAB");
-        int gpc = 1;
-        while ((gpc * cpg) % 8 != 0) ++gpc;
-        const int VC = gpc * cpg / 8;
-        const size_t smem_slab = (size_t)HW * VC * 16 + ((size_t)(GNS_THREADS / VC) * VC * 8 + 2 * gpc) * sizeof(float);
-        if (x2 == nullptr && G % gpc == 0 && VC <= GNS_THREADS && HW <= 1024 && smem_slab <= 96 * 1024 && !(slab_env && slab_env[0] == '0')) {
-            if (smem_slab > 48 * 1024) {
-                static size_t set_for[64];
-                int dev = 0;
-                cudaGetDevice(&dev);
-                dev &= 63;
-                if (set_for[dev] < smem_slab) {
-                    cudaError_t e = cudaFuncSetAttribute(gn_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-                    ANYSD_REQUIRE(e == cudaSuccess, ANYSD_ECUDA, "groupnorm (slab): smem opt-in failed: %s", cudaGetErrorString(e));
-                    set_for[dev] = 96 * 1024;
-                }
-            }
-            gn_slab_kernel<<<dim3(G / gpc, N), GNS_THREADS, smem_slab, (cudaStream_t)stream>>>((const uint4*)x1, gamma, beta, (uint4*)y, HW, C / 8, VC,
-                                                                                            cpg, gpc, eps, fuse_silu);
-            return check_launch("groupnorm (slab)");
-        }
+        // geometry-only decision (the same kernel whatever the batch): the register-resident kernel wherever it applies
+        GnResPlan pl;
+        if (gn_res_plan(C1, C2, HW, G, &pl))
+            return launch_gn_res(pl, x1, C1, x2, C2, gamma, beta, y, N, HW, G, eps, fuse_silu, (cudaStream_t)stream);
     }
     const GnGeom g = gn_geom(C1, C2);
     // The spatial split depends on the image geometry only (never on N): the summation order, and hence

@@ -206,6 +206,8 @@ def _want_stats(p, images, dev, reuse=None):
     # and 15 vs 14 us at 8x8, where two launches cost more than the statistics pass they replace: maps of >= 1024 pixels only
     if not _GN_EPILOGUE or p.rows_per_batch < GN_EPILOGUE_MIN_ROWS:
         return None
+    if _lib.load().anysd_groupnorm_resident(p.N, 0, p.rows_per_batch, 32):
+        return None                          # the register-resident GroupNorm reads x once and needs no statistics from here
     S = _lib.load().anysd_gemm_stats_slabs(C.byref(p))
     if S <= 0:
         return None

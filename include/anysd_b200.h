@@ -85,6 +85,10 @@ size_t anysd_groupnorm_workspace_bytes(int N, int G, int C);
 int anysd_groupnorm_nhwc_f16(const void* x1, int C1, const void* x2, int C2, const float* gamma,
                              const float* beta, void* y, int N, int HW, int G, float eps, int fuse_silu,
                              void* workspace, size_t workspace_bytes, anysd_stream_t stream);
+/* 1 when anysd_groupnorm_nhwc_f16 serves (C1 + C2 channels, HW pixels, G groups) with its register-resident kernel (one read,
+ * one write, one launch: the statistics need no help from the producer's epilogue), 0 when it takes the statistics + apply
+ * path.  A function of the geometry only.  Host-side query, no launch. */
+int anysd_groupnorm_resident(int C1, int C2, int HW, int G);
 /* GroupNorm whose statistics were produced by the epilogue(s) of the contraction(s) that wrote x (anysd_gemm_params::stats):
  * a fixed-order fold of the slab partials per (image, group) in double, then ONE streaming pass y = [silu](x a + b).
  * x: NHWC fp16 [N, HW, C]; its channels [0, C1) come with stats1 ([>= N, S, C1, 2]) and, when the tensor is a channel concat

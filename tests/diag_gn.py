@@ -25,7 +25,7 @@ def timeit(fn, iters=20):
 def main():
     N = 16
     big = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # L2 flush between calls
-    for HW, C in ((4096, 320), (1024, 640), (256, 1280), (64, 1280), (4096, 960)):
+    for HW, C in ((4096, 320), (1024, 640), (256, 1280), (64, 1280), (4096, 960), (4096, 640), (1024, 1280), (1024, 1920), (256, 2560), (64, 2560)):
         x = torch.randn(N, HW, C, device="cuda").half()
         y = torch.empty_like(x)
         g, b = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
@@ -35,7 +35,8 @@ def main():
         fn2 = lambda: (big.zero_(), ops.groupnorm(x, g, b, y, N, HW, 1e-5, True, ws))
         t2 = timeit(fn2) - timeit(lambda: big.zero_())
         mb = x.numel() * 2 / 1e6
-        print(f"groupnorm fused={os.environ.get('ANYSD_GN_FUSED', '1')} N={N} HW={HW} C={C}: warm {t * 1e6:7.1f} us  cold {t2 * 1e6:7.1f} us "
+        res = ops._lib.load().anysd_groupnorm_resident(C, 0, HW, 32)
+        print(f"groupnorm fused={os.environ.get('ANYSD_GN_FUSED', '1')} resident={res} N={N} HW={HW} C={C}: warm {t * 1e6:7.1f} us  cold {t2 * 1e6:7.1f} us "
               f"({2 * mb / t2 / 1e6:5.2f} TB/s algorithmic, {mb:.0f} MB tensor)", flush=True)
         # statistics from a producer's epilogue (here: an identity-sized 1x1 contraction), then finalize + streaming apply
         if C <= 1280:

@@ -79,7 +79,11 @@ def test_timestep_embedding_golden(ops):
 
 
 @pytest.mark.parametrize("shape,C2", [((2, 64, 6, 10), 0), ((3, 320, 16, 16), 0), ((2, 640, 8, 8), 320),
-                                      ((1, 2560, 8, 8), 0), ((2, 960, 32, 32), 640), ((2, 32, 5, 3), 0)])
+                                      ((1, 2560, 8, 8), 0), ((2, 960, 32, 32), 640), ((2, 32, 5, 3), 0),
+                                      # bench-sized maps: the register-resident kernel (<= 8 rows per thread, norm.cu gn_res_plan) and the statistics + apply path
+                                      ((2, 320, 64, 64), 0), ((1, 960, 64, 64), 320), ((2, 640, 32, 32), 0), ((1, 320, 96, 96), 0),
+                                      ((1, 1920, 48, 48), 640), ((2, 1280, 16, 16), 0), ((1, 2560, 16, 16), 1280), ((1, 128, 40, 40), 0),
+                                      ((1, 1280, 48, 48), 0)])
 @pytest.mark.parametrize("silu,eps", [(True, 1e-5), (False, 1e-6)])
 def test_groupnorm(ops, shape, C2, silu, eps):
     N, C, H, W = shape
@@ -98,6 +102,20 @@ def test_groupnorm(ops, shape, C2, silu, eps):
         ops.groupnorm(xh, gamma.cuda(), beta.cuda(), y, N, H * W, eps, silu, ws)
     e = rel(from_nhwc(y, N, H, W), ref)
     assert e < 1e-3, e
+
+
+def test_groupnorm_batch_independent_bits(ops):
+    """Every output bit of an image is independent of its position in / the size of the batch (geometry-only decomposition)."""
+    for (C, H, W) in ((320, 64, 64), (640, 32, 32), (1280, 8, 8), (960, 16, 16)):
+        x = to_nhwc16(randn(17, 3, C, H, W, scale=1.5) - 0.3)
+        gamma, beta = (1 + 0.2 * randn(18, C)).cuda(), (0.1 * randn(19, C)).cuda()
+        y3 = torch.empty_like(x)
+        ops.groupnorm(x, gamma, beta, y3, 3, H * W, 1e-5, True, ops.groupnorm_workspace(3))
+        for i in range(3):
+            xi = x[i:i + 1].contiguous()
+            y1 = torch.empty_like(xi)
+            ops.groupnorm(xi, gamma, beta, y1, 1, H * W, 1e-5, True, ops.groupnorm_workspace(1))
+            assert torch.equal(y1[0], y3[i]), (C, H, W, i)
 
 
 def test_groupnorm_silu_golden_kat(ops):
