@@ -204,10 +204,9 @@ def _want_stats(p, images, dev, reuse=None):
     # [measured, tests/diag_gn.py, batch 16] finalize + streaming apply vs the one-launch statistics + apply kernel:
     # 31 vs 42 us (64x64 map, 320 ch), 21 vs 29 us (32x32, 640 ch), 69 vs 103 us (64x64, 960 ch) -- but 23 vs 19 us at 16x16
     # and 15 vs 14 us at 8x8, where two launches cost more than the statistics pass they replace: maps of >= 1024 pixels only
+    # (below that the register-resident kernel -- anysd_groupnorm_resident -- reads x once and needs no statistics)
     if not _GN_EPILOGUE or p.rows_per_batch < GN_EPILOGUE_MIN_ROWS:
         return None
-    if _lib.load().anysd_groupnorm_resident(p.N, 0, p.rows_per_batch, 32):
-        return None                          # the register-resident GroupNorm reads x once and needs no statistics from here
     S = _lib.load().anysd_gemm_stats_slabs(C.byref(p))
     if S <= 0:
         return None

@@ -9,6 +9,7 @@ kernels (``csrc/backward.cu``, ``csrc/attention_bwd.cu``), parameter gradients e
 PyTorch holds memory and the stream; autograd is not used.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -38,6 +39,12 @@ def conditioning_dropout(text, null_text, image_latent, random_p, prob):
     text = torch.where(prompt_mask, null_text.expand_as(text), text)
     keep = 1 - ((random_p >= prob).to(image_latent.dtype) * (random_p < 3 * prob).to(image_latent.dtype))
     return text, keep.reshape(b, 1, 1, 1) * image_latent
+
+
+# ANYSD_TRAIN_ALLREDUCE=overlap (default): each layer's gradient region is all-reduced as soon as it is final, under the rest of
+# the backward (DDP bucket semantics); =end: one all-reduce of the whole flat buffer after the backward (no NCCL CTAs beside the
+# persistent contraction kernels, no overlap).
+_AR_OVERLAP = os.environ.get("ANYSD_TRAIN_ALLREDUCE", "overlap") != "end"
 
 
 def _memo(d, key, build):
@@ -304,7 +311,12 @@ class AdapterTrainer:
         d_table = self._grad_view("task_embs.weight")
         ops.scatter_add_rows(d_te, edit_code, d_table)
         grads["task_embs.weight"] = d_table
-        if self._reduce:
+        if self._reduce and not _AR_OVERLAP:             # one collective over the whole flat gradient buffer after the backward
+            from . import distributed
+            w = distributed.allreduce_sum_async(flat["G"])
+            if w is not None:
+                self._works.append(w)
+        elif self._reduce:
             for name in flat["regions"]:                 # whatever the backward did not reduce on the fly, in layout order
                 if name not in self._reduced:
                     self._reduce_region(name)
@@ -578,7 +590,7 @@ class AdapterTrainer:
                 at = torch.empty(E * C, Mp, dtype=torch.float16, device=dev)
                 ops.gather_transpose(dekv[:, off:], at, Mv, E * C, lda=ld, head_d=d, head_stride=hs, group_c=C, group_stride=2 * Cp)
                 ops.gemm(at, st["vis_t"], gw)
-            if self._reduce:                              # this layer's expert gradients are final: reduce them under the rest
+            if self._reduce and _AR_OVERLAP:              # this layer's expert gradients are final: reduce them under the rest
                 self._reduce_region(f"kv{layer}")
             Lp = st["MP"]["layers"][layer]
             d_vis = torch.empty(N * n_vis, vis.shape[1], dtype=torch.float16, device=dev)

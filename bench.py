@@ -55,8 +55,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline and parity_check legs (profiling runs)")
     ap.add_argument("--skip-roofline", action="store_true")
-    ap.add_argument("--skip-extra", action="store_true", help="skip the C2 / C3 / C4 / dpm20 legs")
-    ap.add_argument("--extra", default="C2,C3,C4,dpm20", help="comma list of extra legs to run")
+    ap.add_argument("--skip-extra", action="store_true", help="skip the C2 / C3 / C4 / dpm20 / pipeline legs")
+    ap.add_argument("--extra", default="C2,C3,C4,dpm20,pipeline", help="comma list of extra legs to run")
     ap.add_argument("--c2-total", type=int, default=64, help="configs[2]: requests summed over all GPUs")
     ap.add_argument("--c2-chunk", type=int, default=16, help="configs[2]: requests per sampling call on one GPU")
     return ap.parse_args()
@@ -578,6 +578,67 @@ def extra_leg(leg, args, net, model, dev, rank, world, sampling_leg, timed, peak
                 "config": {"workload": "BASELINE configs[1] requests, sampled with the reference's DPMSolverSampler settings "
                                        "(dpm_solver/sampler.py:14-87: multistep, order 2, time_uniform, 20 steps) instead of 50-step DDIM",
                            "global_batch": B * world, "latent": h, "steps": 20}}
+    if leg == "pipeline":
+        # The whole edit request, stage by stage as visual_reference_tool.py:190-225 / the IP2P loop run it:
+        # CLIP-L text tower on the prompt and on the null prompt, first-stage encode of the source image (mode of the posterior,
+        # ddpm.py encode_first_stage / get_first_stage_encoding), the CFG DDIM loop of the headline, first-stage decode.
+        from anyedit_b200.autoencoder import AutoencoderKL
+        from anyedit_b200.encoders import CLIPTextModel
+        B, h = args.batch, args.latent
+        px = 8 * h
+        if not hasattr(extra_leg, "_stages"):
+            torch.manual_seed(91)
+            ddconfig = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4, 4],
+                            num_res_blocks=2, attn_resolutions=[], dropout=0.0)          # the SD-1.x kl-f8 first stage (anydoor.yaml)
+            with torch.device(dev):
+                vae = AutoencoderKL(ddconfig, embed_dim=4)
+                txt = CLIPTextModel({})                                                     # CLIP ViT-L/14 text tower defaults
+            D.broadcast_module_(vae, src=0)
+            D.broadcast_module_(txt, src=0)
+            extra_leg._stages = (vae, txt)
+        vae, txt = extra_leg._stages
+        gen = torch.Generator().manual_seed(3100 + rank)
+        ids = torch.randint(1000, 40000, (B, 77), generator=gen)
+        ids[:, 0], ids[:, 20:] = 49406, 49407                                               # <bos> 19 tokens <eos> padding
+        null_ids = torch.full((1, 77), 49407, dtype=torch.int64)
+        null_ids[0, 0] = 49406
+        host = {"img": (torch.rand(B, 3, px, px, generator=gen) * 2 - 1), "ids": ids, "null_ids": null_ids,
+                "x_T": torch.randn(B, 4, h, h, generator=gen)}
+        host = {k: v.pin_memory() for k, v in host.items()}
+        out_host = torch.empty(B, 3, px, px).pin_memory()
+        smp = DDIMSampler(model, use_cuda_graph=not args.no_graph)
+        scale_factor = 0.18215
+
+        def run(d_):
+            c_txt = txt(d_["ids"]).last_hidden_state
+            u_txt = txt(d_["null_ids"]).last_hidden_state.expand(B, -1, -1).contiguous()
+            c_cat = vae.encode(d_["img"]).mode()
+            cond = {"c_concat": [c_cat], "c_crossattn": [c_txt]}
+            uncond = {"c_concat": [c_cat], "c_crossattn": [u_txt]}
+            z, _ = smp.sample(50, B, (4, h, h), cond, verbose=False, x_T=d_["x_T"], eta=0.0, unconditional_guidance_scale=args.scale,
+                              unconditional_conditioning=uncond)
+            return vae.decode(z, z_scale=1.0 / scale_factor)
+
+        devt = {k: v.to(dev) for k, v in host.items()}
+        resident = lambda: run(devt)
+        e2e = lambda: out_host.copy_(run({k: v.to(dev, non_blocking=True) for k, v in host.items()}), non_blocking=True)
+        resident()
+        n0 = ops.launch_count
+        steps = 2
+        t_res = timed(resident, steps)
+        launches = (ops.launch_count - n0) // steps
+        t_e2e = timed(e2e, steps)
+        n = B * world * steps
+        finite = bool(torch.isfinite(out_host).all())
+        return {"metric": "edited images/sec, whole request (CLIP-L text encode x2 + first-stage encode + 50-step CFG DDIM + first-stage decode, "
+                          "512x512 pixels in, 512x512 pixels out)",
+                "value": n / t_res, "unit": "images/s", "scaling": "weak", "ms_per_step": 1e3 * t_res / steps,
+                "e2e": {"value": n / t_e2e, "unit": "images/s", "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()),
+                        "d2h_bytes_per_step": out_host.numel() * 4},
+                "gpu_launches": launches, "output_finite": finite,
+                "config": {"workload": f"BASELINE configs[1] requests end to end: {B} RGB source images {px}x{px} + token ids per GPU -> edited RGB "
+                                       f"images; kl-f8 AutoencoderKL (ch 128, mult 1-2-4-4) and CLIP ViT-L/14 text tower, random-init weights",
+                           "global_batch": B * world, "latent": h, "ddim_steps": 50, "guidance_scale": args.scale}}
     raise ValueError(f"unknown extra leg {leg!r}")
 
 
