@@ -41,10 +41,13 @@ def conditioning_dropout(text, null_text, image_latent, random_p, prob):
     return text, keep.reshape(b, 1, 1, 1) * image_latent
 
 
-# ANYSD_TRAIN_ALLREDUCE=overlap (default): each layer's gradient region is all-reduced as soon as it is final, under the rest of
-# the backward (DDP bucket semantics); =end: one all-reduce of the whole flat buffer after the backward (no NCCL CTAs beside the
-# persistent contraction kernels, no overlap).
-_AR_OVERLAP = os.environ.get("ANYSD_TRAIN_ALLREDUCE", "overlap") != "end"
+# Gradient all-reduce schedule.  ANYSD_TRAIN_ALLREDUCE=end (default): ONE all-reduce of the whole flat gradient buffer after the
+# backward; =overlap: each layer's region is all-reduced as soon as it is final, under the rest of the backward (DDP bucket
+# semantics).  [measured, 2 x B200, batch 16 per GPU, profiles/r2_train_allreduce.md] 74.8 ms per step on one GPU; overlap 80.3 ms,
+# overlap with NCCL_MAX_CTAS=4 76.9 ms, end 76.9 ms: NCCL's CTAs take SMs the persistent one-CTA-per-SM contraction kernels count
+# on (a 148-CTA grid with a few SMs occupied runs its last CTAs as a second wave), which costs more than the 2.2 ms the 0.85 GB
+# collective takes at full speed on its own.
+_AR_OVERLAP = os.environ.get("ANYSD_TRAIN_ALLREDUCE", "end") == "overlap"
 
 
 def _memo(d, key, build):
