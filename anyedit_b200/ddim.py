@@ -188,10 +188,7 @@ class DDIMSampler(object):
         """``image_guidance_scale`` + ``image_conditioning`` (extension): InstructPix2Pix three-way
         guidance of tools/global_tool.py:166-177 -- the batch is [cond (text + image) ; image_conditioning (null text +
         image) ; unconditional_conditioning (null text + zero image)], ``unconditional_guidance_scale`` is the text scale."""
-        if quantize_denoised or score_corrector is not None:
-            # both hook foreign modules into the middle of the fused update (a VQ first stage, ddim.py:239-240; a score
-            # corrector, :219-221); neither exists on the AnySD / SD-1.5 path (KL autoencoder, no corrector)
-            raise NotImplementedError("quantize_denoised / score_corrector are not on the AnySD path")
+        hooks = self._step_hooks(score_corrector, corrector_kwargs, quantize_denoised, cond, image_conditioning)
         if dynamic_threshold is not None:
             raise NotImplementedError()
         if getattr(self.model, "parameterization", "eps") not in ("eps", "v"):
@@ -226,8 +223,9 @@ class DDIMSampler(object):
         sigma_nonzero = bool(np.any(sigmas_used[:total_steps] != 0))
 
         stepper = self._get_stepper(cond, unconditional_conditioning, use_cfg, b, tuple(shape), device,
-                                    graph=self.use_cuda_graph and ucg_schedule is None,
+                                    graph=self.use_cuda_graph and ucg_schedule is None and hooks is None,
                                     img_cond=image_conditioning if three else None, img_scale=image_guidance_scale if three else None)
+        stepper.hooks = hooks
         for i, step in enumerate(time_range):
             index = total_steps - i - 1
             if mask is not None:
@@ -256,18 +254,31 @@ class DDIMSampler(object):
                 intermediates["pred_x0"].append(pred_x0.clone())
         return img, intermediates
 
+    def _step_hooks(self, score_corrector, corrector_kwargs, quantize_denoised, cond, image_conditioning):
+        """``score_corrector`` (ddim.py:219-221) and ``quantize_denoised`` (:239-240) hook foreign modules -- a corrector's
+        ``modify_score``, a VQ first stage's ``quantize`` -- between the model call and the update.  Neither exists on the AnySD /
+        SD-1.5 path (KL autoencoder, no corrector), so they get no kernel: a step that carries one runs the model on the kernels,
+        then the reference's own sequence of tensor ops for the update (_Stepper._hooked_update), eagerly, without a CUDA graph."""
+        if not quantize_denoised and score_corrector is None:
+            return None
+        if image_conditioning is not None:
+            raise NotImplementedError("score_corrector / quantize_denoised with three-way image guidance")
+        if score_corrector is not None:
+            assert getattr(self.model, "parameterization", "eps") == "eps", 'not implemented'       # ddim.py:220
+        return (score_corrector, dict(corrector_kwargs or {}), bool(quantize_denoised), cond)
+
     @torch.no_grad()
     def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False, quantize_denoised=False,
                       temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
                       unconditional_guidance_scale=1., unconditional_conditioning=None, dynamic_threshold=None):
         """One step (ddim.py:181-251); used by ``decode`` and by callers that drive the loop themselves."""
-        if quantize_denoised or score_corrector is not None:
-            raise NotImplementedError("quantize_denoised / score_corrector are not on the AnySD path")
+        hooks = self._step_hooks(score_corrector, corrector_kwargs, quantize_denoised, c, None)
         if dynamic_threshold is not None:
             raise NotImplementedError()
         b = x.shape[0]
         use_cfg = not (unconditional_conditioning is None or unconditional_guidance_scale == 1.)
         stepper = _Stepper(self, c, unconditional_conditioning, use_cfg, b, tuple(x.shape), x.device, graph=False)
+        stepper.hooks = hooks
         noise = None
         sigma = self.ddim_sigmas_for_original_num_steps[index] if use_original_steps else self.ddim_sigmas[index]
         if float(sigma) != 0.0:
@@ -474,6 +485,28 @@ class _Stepper:
         # cross-attention K/V of the (static) conditioning: projected once per sampling run, not once per step
         self.kv = {"mode": "fill", "bufs": []} if self.unet is not None and os.environ.get("ANYSD_CTX_KV", "1")[:1] != "0" else None
         self.kv_dirty = True
+        self.hooks = None                            # (score_corrector, its kwargs, quantize_denoised, cond): see DDIMSampler._step_hooks
+
+    def _hooked_update(self, eps, scale, noise):
+        """ddim.py:194-251 as the reference writes it (separate fp32 tensor ops, in its order), with the hooks in place."""
+        corrector, ckw, quantize, cond = self.hooks
+        assert self.update == "ddim" and not self.three
+        b, co, x = self.b, self.coef_buf, self.x_buf
+        out = eps[:b] + scale * (eps[b:2 * b] - eps[:b]) if self.use_cfg else eps      # model_uncond + s (model_t - model_uncond)
+        if self.v_param:                                                              # :214-218, 224-226
+            e_t = co[5] * out + co[6] * x
+        else:
+            e_t = out
+        if corrector is not None:
+            e_t = corrector.modify_score(self.s.model, e_t, x, self.t_buf[:b], cond, **ckw)
+        pred_x0 = (co[5] * x - co[6] * out) if self.v_param else (x - co[0] * e_t) / co[1]
+        if quantize:
+            pred_x0, _, *_ = self.s.model.first_stage_model.quantize(pred_x0)
+        x_prev = co[2] * pred_x0 + co[3] * e_t
+        if noise is not None:
+            x_prev = x_prev + co[4] * noise
+        self.x_prev.copy_(x_prev)
+        self.pred_x0.copy_(pred_x0)
 
     def reset(self):
         """Start of a sampling run: clear the multistep history (zeros, so that a zero coefficient never meets NaN)."""
@@ -511,7 +544,9 @@ class _Stepper:
                 self.unet._ctx_kv = None
         eps = eps.float().contiguous()
         self.last_eps = eps                              # the model output of the latest step (parity tests / bench read it)
-        if self.update == "plms":
+        if self.hooks is not None:
+            self._hooked_update(eps, scale, noise)
+        elif self.update == "plms":
             ops.cfg_plms_step(self.x_buf, eps, self.coef_buf, scale, self.use_cfg, self.hist, self.x_prev, self.pred_x0)
         elif self.update == "dpmpp":
             ops.cfg_dpmpp_step(self.x_buf, eps, self.coef_buf, scale, self.use_cfg, self.m_prev, self.x_prev, self.pred_x0)

@@ -146,6 +146,85 @@ def test_ddim_tiny_golden():
             assert e < 5e-3, e
 
 
+def test_ddim_score_corrector_and_quantize_hooks():
+    """``score_corrector`` (ddim.py:219-221) and ``quantize_denoised`` (:239-240): identity hooks reproduce the plain run (the
+    hooked update is the reference's own sequence of fp32 tensor ops, the fused kernel the same operations without FMA
+    contraction); a non-trivial corrector follows a restatement of ddim.py:194-251 driven step by step through ``apply_model``; a
+    rounding quantiser puts every ``pred_x0`` on its grid; ``p_sample_ddim`` takes the same hooks."""
+    from anyedit_b200.ddim import DDIMSampler, _cat_cond
+    g = np.load(os.path.join(G, "ddim_tiny.npz"))
+    net, _, _ = _build("tiny_a", 11)
+    model = _denoiser(net)
+    f = lambda k: torch.from_numpy(g[k]).cuda()
+    cond = {"c_concat": [f("c_cat")], "c_crossattn": [f("c_txt")]}
+    uncond = {"c_concat": [f("c_cat")], "c_crossattn": [f("u_txt")]}
+    S, scale, b = 6, 7.5, 2
+    calls = []
+
+    class Identity:
+        def modify_score(self, mdl, e_t, x, t, c, **kw):
+            calls.append(int(t[0]))
+            assert mdl is model and c is cond and t.shape == (b,) and e_t.shape == x.shape
+            return e_t
+
+    class Bend:
+        def modify_score(self, mdl, e_t, x, t, c, gain=1.0):
+            return gain * e_t + 0.01 * x
+
+    class FirstStage:                                    # a stand-in VQ first stage: quantize -> (z_q, loss, info)
+        def __init__(self, step):
+            self.step = step
+
+        def quantize(self, z):
+            return (z if self.step is None else torch.round(z / self.step) * self.step), None, (None, None, None)
+
+    sampler = DDIMSampler(model, use_cuda_graph=True)
+    kw = dict(verbose=False, x_T=f("x_T"), eta=0.0, unconditional_guidance_scale=scale, unconditional_conditioning=uncond)
+    plain, _ = sampler.sample(S, b, (4, 16, 16), cond, **kw)
+    model.first_stage_model = FirstStage(None)
+    ident, _ = sampler.sample(S, b, (4, 16, 16), cond, score_corrector=Identity(), quantize_x0=True, **kw)
+    assert calls == [int(t) for t in np.flip(sampler.ddim_timesteps)]
+    e = rel(ident, plain)
+    print(f"[ddim hooks] identity hooks vs the fused update: rel-L2 = {e:.3e}, bit-equal = {torch.equal(ident, plain)}")
+    assert e < 1e-6, e
+    again, _ = sampler.sample(S, b, (4, 16, 16), cond, **kw)           # the cached graph stepper is untouched by the hooked run
+    assert torch.equal(again, plain)
+
+    got, _ = sampler.sample(S, b, (4, 16, 16), cond, score_corrector=Bend(), corrector_kwargs={"gain": 0.9}, **kw)
+    x = f("x_T").clone()
+    c_in = _cat_cond(uncond, cond)
+    T = len(sampler.ddim_timesteps)                     # 7 for S = 6: range(0, 1000, 1000 // 6) has 7 entries (ddim util.py:22-23)
+    for i, step in enumerate(np.flip(sampler.ddim_timesteps)):
+        index = T - i - 1
+        t = torch.full((2 * b,), int(step), device="cuda", dtype=torch.long)
+        out = model.apply_model(torch.cat([x, x]), t, c_in).float()
+        e_t = out[:b] + scale * (out[b:] - out[:b])
+        e_t = 0.9 * e_t + 0.01 * x
+        a_t, a_prev = float(sampler.ddim_alphas[index]), float(sampler.ddim_alphas_prev[index])
+        s1m = float(sampler.ddim_sqrt_one_minus_alphas[index])
+        pred = (x - s1m * e_t) / (a_t ** 0.5)
+        x = (a_prev ** 0.5) * pred + ((1. - a_prev) ** 0.5) * e_t
+    e = rel(got, x)
+    print(f"[ddim hooks] corrector vs step-by-step restatement rel-L2 = {e:.3e}")
+    assert e < 1e-5, e
+    assert rel(got, plain) > 1e-2                        # ... and the corrector did change the trajectory
+
+    model.first_stage_model = FirstStage(0.05)
+    qz, inter = sampler.sample(S, b, (4, 16, 16), cond, quantize_x0=True, log_every_t=1, **kw)
+    for p0 in inter["pred_x0"][1:]:
+        r = p0 / 0.05
+        assert float((r - torch.round(r)).abs().max()) < 1e-3
+    assert rel(qz, plain) > 1e-3
+
+    x0 = f("x_T")
+    t0 = torch.full((b,), int(sampler.ddim_timesteps[T - 1]), device="cuda", dtype=torch.long)
+    model.first_stage_model = FirstStage(None)
+    a, pa = sampler.p_sample_ddim(x0, cond, t0, T - 1, unconditional_guidance_scale=scale, unconditional_conditioning=uncond)
+    h, ph = sampler.p_sample_ddim(x0, cond, t0, T - 1, unconditional_guidance_scale=scale, unconditional_conditioning=uncond,
+                                  score_corrector=Identity(), quantize_denoised=True)
+    assert rel(h, a) < 1e-6 and rel(ph, pa) < 1e-6
+
+
 def test_ddim_graph_equals_eager():
     from anyedit_b200.ddim import DDIMSampler
     g = np.load(os.path.join(G, "ddim_tiny.npz"))

@@ -32,6 +32,89 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert handle.anysd_version() >= 100
 
 
+def test_groupnorm_path_choice_is_geometry_only():
+    """anysd_groupnorm_resident (a host-side query, no launch): the register-resident GroupNorm kernel serves the maps of at most
+    8 x RL pixels (RL = 64 row lanes, 32 when a span is wider than 8 vectors) -- a function of (channels, pixels, groups) only, so the
+    kernel an image runs through never depends on the batch."""
+    from anyedit_b200 import _lib
+    q = _lib.load().anysd_groupnorm_resident
+    assert q(1280, 0, 256, 32) == 1 and q(1280, 0, 64, 32) == 1          # 16x16, 8x8 levels
+    assert q(2560, 0, 256, 32) == 1 and q(1280, 1280, 256, 32) == 1      # 80 channels per group, as one tensor or as a skip concat
+    assert q(640, 320, 64, 32) == 1                                      # 30 channels per group: 15-vector spans, 32 row lanes
+    assert q(640, 0, 512, 32) == 1 and q(640, 0, 576, 32) == 0           # 8 x 64 pixels is the limit
+    assert q(320, 0, 4096, 32) == 0 and q(640, 0, 1024, 32) == 0         # large maps: statistics from the producer's epilogue
+    assert q(1920, 0, 256, 32) == 1 and q(1920, 0, 512, 32) == 0         # 32 row lanes: 256 pixels is the limit
+    assert q(324, 0, 64, 32) == 0                                        # channels not divisible into the groups
+
+
+def test_ddim_hooks_host_logic_duck_typed_model():
+    """``score_corrector`` / ``quantize_denoised`` (ddim.py:219-221, 239-240) are host-side hooks between the model call and the update:
+    the step then runs the reference's own tensor ops (no kernel), so with a duck-typed model (``apply_model``,
+    ``betas``, ``alphas_cumprod`` ...) the whole loop is checkable on the CPU against a step-by-step restatement of ddim.py:194-251,
+    for the eps and the v parameterisation."""
+    from anyedit_b200.ddim import DDIMSampler, _cat_cond
+    from anyedit_b200.diffusion import make_beta_schedule
+
+    class Duck(torch.nn.Module):
+        def __init__(self, parameterization):
+            super().__init__()
+            acp = np.cumprod(1 - make_beta_schedule("linear", 1000, 0.00085, 0.012))
+            self.num_timesteps, self.parameterization, self.device = 1000, parameterization, torch.device("cpu")
+            self.betas = torch.tensor(1 - acp / np.append(1., acp[:-1]), dtype=torch.float32)
+            self.alphas_cumprod = torch.tensor(acp, dtype=torch.float32)
+            self.alphas_cumprod_prev = torch.tensor(np.append(1., acp[:-1]), dtype=torch.float32)
+
+        def apply_model(self, x, t, c):
+            ctx = c["c_crossattn"][0].mean(dim=(1, 2)).view(-1, 1, 1, 1)
+            return torch.tanh(0.5 * x + ctx) + 0.1 * c["c_concat"][0] * torch.cos(t.float()).view(-1, 1, 1, 1)
+
+    class Bend:
+        def modify_score(self, mdl, e_t, x, t, c, gain=1.0):
+            return gain * e_t + 0.01 * x
+
+    class FirstStage:
+        def __init__(self, step):
+            self.step = step
+
+        def quantize(self, z):
+            return torch.round(z / self.step) * self.step, None, (None, None, None)
+
+    b, S, scale = 2, 6, 7.5
+    g = torch.Generator().manual_seed(0)
+    cond = {"c_concat": [torch.randn(b, 4, 8, 8, generator=g)], "c_crossattn": [torch.randn(b, 5, 16, generator=g)]}
+    uncond = {"c_concat": [cond["c_concat"][0]], "c_crossattn": [torch.randn(b, 5, 16, generator=g)]}
+    xT = torch.randn(b, 4, 8, 8, generator=g)
+    c_in = _cat_cond(uncond, cond)
+    kw = dict(verbose=False, x_T=xT, eta=0.0, unconditional_guidance_scale=scale, unconditional_conditioning=uncond)
+    for par in ("eps", "v"):
+        model = Duck(par)
+        model.first_stage_model = FirstStage(0.05)
+        smp = DDIMSampler(model, use_cuda_graph=False)
+        corr = Bend() if par == "eps" else None                  # the reference asserts eps for a corrector (ddim.py:220)
+        got, inter = smp.sample(S, b, (4, 8, 8), cond, score_corrector=corr, corrector_kwargs={"gain": 0.9}, quantize_x0=True,
+                                log_every_t=1, **kw)
+        T = len(smp.ddim_timesteps)
+        x = xT.clone()
+        for i, step in enumerate(np.flip(smp.ddim_timesteps)):
+            index = T - i - 1
+            out = model.apply_model(torch.cat([x, x]), torch.full((2 * b,), int(step), dtype=torch.long), c_in)
+            out = out[:b] + scale * (out[b:] - out[:b])
+            a_t, a_prev = float(smp.ddim_alphas[index]), float(smp.ddim_alphas_prev[index])
+            if par == "v":
+                sa, s1 = float(model.alphas_cumprod[int(step)]) ** 0.5, (1 - float(model.alphas_cumprod[int(step)])) ** 0.5
+                e_t, pred = sa * out + s1 * x, sa * x - s1 * out
+            else:
+                e_t = 0.9 * out + 0.01 * x
+                pred = (x - float(smp.ddim_sqrt_one_minus_alphas[index]) * e_t) / (a_t ** 0.5)
+            pred = torch.round(pred / 0.05) * 0.05
+            x = (a_prev ** 0.5) * pred + ((1. - a_prev) ** 0.5) * e_t
+        assert float((got - x).norm() / x.norm()) < 1e-5, par
+        for p0 in inter["pred_x0"][1:]:
+            assert float((p0 / 0.05 - torch.round(p0 / 0.05)).abs().max()) < 1e-3
+    with pytest.raises(AssertionError):                          # 'not implemented' in the reference too
+        DDIMSampler(Duck("v"), use_cuda_graph=False).sample(S, b, (4, 8, 8), cond, score_corrector=Bend(), **kw)
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the product path must fail loudly, never fall back."""
     from anyedit_b200 import ops
