@@ -115,6 +115,33 @@ def test_ddim_hooks_host_logic_duck_typed_model():
         DDIMSampler(Duck("v"), use_cuda_graph=False).sample(S, b, (4, 8, 8), cond, score_corrector=Bend(), **kw)
 
 
+def test_bench_reference_arm_contract(tmp_path):
+    """``bench.py --impl reference`` (the driver's reference arm): rank 0 prints ONE JSON line with the contract's keys, timed on the
+    reference's own CPU implementation (``oracle/_ref`` staged sources when present, the restatement otherwise); any other rank exits
+    0 without output.  Run on a shrunken workload (8x8 latent, 4 DDIM steps) so that the CPU suite stays short."""
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--latent", "8", "--ddim-steps", "4",
+           "--steps", "1", "--warmup", "1"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    other = subprocess.run(cmd, env={**env, "RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}, capture_output=True, text=True, timeout=600)
+    assert other.returncode == 0 and other.stdout.strip() == ""
+    r0 = subprocess.run(cmd, env={**env, "RANK": "0", "LOCAL_RANK": "0", "WORLD_SIZE": "2"}, capture_output=True, text=True, timeout=900)
+    assert r0.returncode == 0, r0.stderr[-2000:]
+    lines = [ln for ln in r0.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 1 and d["warmup"] == 1
+    assert d["unit"] == "images/s" and d["higher_is_better"] is True and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["metric"].startswith("edited images/sec") and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["config"]["workload"] and d["config"]["latent"] == 8 and d["config"]["ddim_steps"] == 4
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    from oracle import ref_import
+    assert cb["kind"] == ("reference" if ref_import.available() else "port")
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the product path must fail loudly, never fall back."""
     from anyedit_b200 import ops
